@@ -1,0 +1,271 @@
+// C ABI of libaudiolab_b200.so -- see include/audiolab_b200.h for the contract of every entry point
+// and the reference interface each one replaces.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/audiolab_b200.h"
+#include "al_kernels.h"
+
+namespace al {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace al
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(AL_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+}  // namespace
+
+struct al_plan {
+    int n_fft, hop, normalized, D;
+    float* d_win_a = nullptr;     // analysis window * (normalized ? n_fft^-1/2 : 1)
+    float* d_win_s = nullptr;     // synthesis window * 1/n_fft * (normalized ? n_fft^1/2 : 1)
+    float* d_win_raw = nullptr;   // window as given (for the OLA envelope)
+    float2* d_tw = nullptr;       // [32*32]
+    float2* d_ctw = nullptr;      // [(D-1)*513]
+    std::mutex mu;
+    std::map<int, float*> env;    // n_frames_total -> inv_env table
+};
+
+extern "C" {
+
+int al_version(void) { return 100; }
+
+const char* al_last_error(void) { return g_err.c_str(); }
+
+int64_t al_launch_count(void) { return al::g_launches.load(std::memory_order_relaxed); }
+
+int al_plan_create(int n_fft, int hop, const float* window_host, int normalized, al_plan** out) {
+    if (!out) return fail(AL_E_ARG, "al_plan_create: out is NULL");
+    *out = nullptr;
+    if (n_fft != 2048 && n_fft != 4096 && n_fft != 6144)
+        return fail(AL_E_UNSUPPORTED, "al_plan_create: n_fft %d not in {2048, 4096, 6144}", n_fft);
+    if (hop <= 0 || hop > n_fft) return fail(AL_E_ARG, "al_plan_create: bad hop %d", hop);
+    al_plan* p = new al_plan;
+    p->n_fft = n_fft;
+    p->hop = hop;
+    p->normalized = normalized ? 1 : 0;
+    p->D = n_fft / 1024;
+    const int N = n_fft, D = p->D;
+    const double kPi = 3.14159265358979323846;
+    std::vector<float> raw(N), wa(N), ws(N);
+    for (int i = 0; i < N; ++i) {
+        // torch.hann_window(N, periodic=True) evaluated in float32 like torch does is within 1 ulp of this
+        raw[i] = window_host ? window_host[i] : (float)(0.5 - 0.5 * cos(2.0 * kPi * i / N));
+        const double sa = normalized ? 1.0 / sqrt((double)N) : 1.0;
+        const double ss = (normalized ? sqrt((double)N) : 1.0) / (double)N;
+        wa[i] = (float)((double)raw[i] * sa);
+        ws[i] = (float)((double)raw[i] * ss);
+    }
+    std::vector<float2> tw(1024), ctw((size_t)(D - 1) * 513);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = -2.0 * kPi * (double)(k1 * n2) / 1024.0;
+            tw[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
+        }
+    for (int r = 1; r < D; ++r)
+        for (int k = 0; k <= 512; ++k) {
+            const double a = -2.0 * kPi * (double)r * (double)k / (double)N;
+            ctw[(size_t)(r - 1) * 513 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    cudaError_t e;
+#define AL_UP(dst, src, bytes)                                                     \
+    do {                                                                           \
+        e = cudaMalloc((void**)&(dst), (bytes));                                   \
+        if (e == cudaSuccess) e = cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice); \
+        if (e != cudaSuccess) { al_plan_destroy(p); return cuda_fail(e, "al_plan_create"); } \
+    } while (0)
+    AL_UP(p->d_win_a, wa.data(), N * sizeof(float));
+    AL_UP(p->d_win_s, ws.data(), N * sizeof(float));
+    AL_UP(p->d_win_raw, raw.data(), N * sizeof(float));
+    AL_UP(p->d_tw, tw.data(), tw.size() * sizeof(float2));
+    AL_UP(p->d_ctw, ctw.data(), ctw.size() * sizeof(float2));
+#undef AL_UP
+    *out = p;
+    return AL_OK;
+}
+
+int al_plan_destroy(al_plan* p) {
+    if (!p) return AL_OK;
+    cudaFree(p->d_win_a);
+    cudaFree(p->d_win_s);
+    cudaFree(p->d_win_raw);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_ctw);
+    for (auto& kv : p->env) cudaFree(kv.second);
+    delete p;
+    return AL_OK;
+}
+
+int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch_stride, int channels,
+            const int64_t* chunk_offsets, int64_t off0, int64_t off_step, int n_chunks, int chunk_len,
+            int center_pad, int n_frames, float* spec, int layout, int n_bins_out, int zero_low_bins,
+            void* stream) {
+    if (!plan || !track || !spec) return fail(AL_E_ARG, "al_stft: NULL argument");
+    if (n_chunks == 0 || n_frames == 0) return AL_OK;
+    if (channels <= 0 || n_chunks < 0 || n_frames < 0 || chunk_len <= 0)
+        return fail(AL_E_ARG, "al_stft: bad sizes (channels %d chunks %d frames %d chunk_len %d)", channels,
+                    n_chunks, n_frames, chunk_len);
+    if (layout < 0 || layout > 2) return fail(AL_E_ARG, "al_stft: bad layout %d", layout);
+    if (n_bins_out <= 0 || n_bins_out > plan->n_fft / 2 + 1) return fail(AL_E_ARG, "al_stft: bad n_bins_out %d", n_bins_out);
+    if (center_pad < 0 || center_pad >= chunk_len)
+        return fail(AL_E_ARG, "al_stft: center_pad %d must be < chunk_len %d (single reflection)", center_pad, chunk_len);
+    // right edge: the last frame may reach at most chunk_len - 1 samples past the end
+    const long long last = (long long)(n_frames - 1) * plan->hop - center_pad + plan->n_fft - 1;
+    if (last > 2LL * (chunk_len - 1))
+        return fail(AL_E_ARG, "al_stft: frames reach %lld, beyond a single reflection of chunk_len %d", last, chunk_len);
+    if ((reinterpret_cast<uintptr_t>(spec) & 7) != 0) return fail(AL_E_ARG, "al_stft: spec must be 8-byte aligned");
+    al::StftParams p{};
+    p.track = track;
+    p.n_valid = n_valid;
+    p.ch_stride = ch_stride;
+    p.channels = channels;
+    p.chunk_offsets = reinterpret_cast<const long long*>(chunk_offsets);
+    p.off0 = off0;
+    p.off_step = off_step;
+    p.chunk_len = chunk_len;
+    p.center = center_pad;
+    p.hop = plan->hop;
+    p.n_frames = n_frames;
+    p.window = plan->d_win_a;
+    p.tw = plan->d_tw;
+    p.ctw = plan->d_ctw;
+    p.spec = spec;
+    p.layout = layout;
+    p.n_bins_out = n_bins_out;
+    p.zero_low_bins = zero_low_bins;
+    cudaError_t e = al::launch_stft(p, plan->n_fft, n_chunks * channels, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_stft");
+    return AL_OK;
+}
+
+static int get_env(al_plan* plan, int n_frames_total, cudaStream_t stream, const float** out) {
+    std::lock_guard<std::mutex> lk(plan->mu);
+    auto it = plan->env.find(n_frames_total);
+    if (it != plan->env.end()) { *out = it->second; return AL_OK; }
+    const long long total = (long long)(n_frames_total - 1) * plan->hop + plan->n_fft;
+    float* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, total * sizeof(float));
+    if (e != cudaSuccess) return cuda_fail(e, "al_istft: envelope alloc");
+    // built on the legacy default stream and synchronised so every later stream sees it
+    e = al::launch_env(plan->d_win_raw, plan->n_fft, plan->hop, n_frames_total, d, (cudaStream_t)0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "al_istft: envelope build"); }
+    (void)stream;
+    plan->env[n_frames_total] = d;
+    *out = d;
+    return AL_OK;
+}
+
+int al_istft(const al_plan* plan_c, const float* spec, const float* mask, int layout, int n_bins_in,
+             int n_frames_in, int frame_pad, int n_chunks, int stems, int channels, int spec_has_stems,
+             int zero_low_bins, int out_start, int out_len, const float* weight, float* dst,
+             int64_t dst_ch_stride, int64_t dst_chunk_stride, const int64_t* dst_offsets,
+             int64_t dst_off0, int64_t dst_off_step, int64_t dst_limit, void* stream) {
+    al_plan* plan = const_cast<al_plan*>(plan_c);
+    if (!plan || !spec || !dst) return fail(AL_E_ARG, "al_istft: NULL argument");
+    if (n_chunks == 0 || out_len == 0) return AL_OK;
+    if (n_chunks < 0 || stems <= 0 || channels <= 0 || n_frames_in <= 0 || out_len < 0 || frame_pad < 0)
+        return fail(AL_E_ARG, "al_istft: bad sizes");
+    if (layout < 0 || layout > 2) return fail(AL_E_ARG, "al_istft: bad layout %d", layout);
+    if (mask && layout == 2) return fail(AL_E_UNSUPPORTED, "al_istft: mask multiply needs a complex layout");
+    if (n_bins_in <= 0 || n_bins_in > plan->n_fft / 2 + 1) return fail(AL_E_ARG, "al_istft: bad n_bins_in %d", n_bins_in);
+    const int T = n_frames_in + 2 * frame_pad;
+    const long long ola_len = (long long)(T - 1) * plan->hop + plan->n_fft;
+    if (out_start < 0 || (long long)out_start + out_len > ola_len)
+        return fail(AL_E_ARG, "al_istft: [out_start %d, +%d) exceeds the overlap-add length %lld", out_start, out_len, ola_len);
+    const float* inv_env = nullptr;
+    int rc = get_env(plan, T, (cudaStream_t)stream, &inv_env);
+    if (rc != AL_OK) return rc;
+    al::IstftParams p{};
+    p.spec = spec;
+    p.mask = mask;
+    p.layout = layout;
+    p.n_bins_in = n_bins_in;
+    p.n_frames_in = n_frames_in;
+    p.frame_pad = frame_pad;
+    p.n_frames_total = T;
+    p.stems = stems;
+    p.channels = channels;
+    p.spec_has_stems = spec_has_stems;
+    p.zero_low_bins = zero_low_bins;
+    p.hop = plan->hop;
+    p.window = plan->d_win_s;
+    p.tw = plan->d_tw;
+    p.ctw = plan->d_ctw;
+    p.inv_env = inv_env;
+    p.out_start = out_start;
+    p.out_len = out_len;
+    p.weight = weight;
+    p.dst = dst;
+    p.dst_ch_stride = dst_ch_stride;
+    p.dst_chunk_stride = dst_chunk_stride;
+    p.dst_offsets = reinterpret_cast<const long long*>(dst_offsets);
+    p.dst_off0 = dst_off0;
+    p.dst_off_step = dst_off_step;
+    p.dst_limit = dst_limit;
+    cudaError_t e = al::launch_istft(p, plan->n_fft, n_chunks, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_istft");
+    return AL_OK;
+}
+
+int al_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len, const int64_t* offsets,
+                  const int32_t* mult, const float* wtab, const int32_t* tab_id, int64_t n_total,
+                  int64_t p0, int64_t p1, const float* halo_in, int raw_out, float eps, float scale,
+                  float* track, int64_t track_stride, void* stream) {
+    if (!chunks || !offsets || !track) return fail(AL_E_ARG, "al_ola_gather: NULL argument");
+    if (n_chunks <= 0 || rows <= 0 || chunk_len <= 0 || p0 < 0 || p1 < p0)
+        return fail(AL_E_ARG, "al_ola_gather: bad sizes");
+    cudaError_t e = al::launch_ola_gather(chunks, n_chunks, rows, chunk_len,
+                                          reinterpret_cast<const long long*>(offsets), mult, wtab, tab_id, n_total,
+                                          p0, p1, halo_in, raw_out, eps, scale, track, track_stride,
+                                          (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_ola_gather");
+    return AL_OK;
+}
+
+int al_resample_poly(const float* in, int64_t in_stride, float* out, int64_t out_stride, int rows,
+                     int64_t n_in, int64_t n_out, int up, int down, const float* taps, int n_taps,
+                     void* stream) {
+    if (!in || !out || !taps) return fail(AL_E_ARG, "al_resample_poly: NULL argument");
+    if (rows < 0 || n_in < 0 || n_out < 0 || up <= 0 || down <= 0 || n_taps <= 0 || (n_taps & 1) == 0)
+        return fail(AL_E_ARG, "al_resample_poly: bad sizes (n_taps must be odd)");
+    if (n_out > (n_in * up + down - 1) / down)
+        return fail(AL_E_ARG, "al_resample_poly: n_out %lld > ceil(n_in*up/down)", (long long)n_out);
+    cudaError_t e = al::launch_resample(in, in_stride, out, out_stride, rows, n_in, n_out, up, down, taps, n_taps,
+                                        (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_resample_poly");
+    return AL_OK;
+}
+
+int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream) {
+    if (!a || !b || !out) return fail(AL_E_ARG, "al_sub: NULL argument");
+    cudaError_t e = al::launch_sub(a, b, out, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_sub");
+    return AL_OK;
+}
+
+}  // extern "C"

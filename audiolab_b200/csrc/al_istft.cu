@@ -1,0 +1,220 @@
+// K2: fused (complex mask (.) spec | CaC -> complex) + zero freq-pad + complex-to-real iFFT +
+// synthesis window + overlap-add over frames + / sum(window^2) + centre trim (+ chunk weight,
+// + trim-and-concat placement).  Replaces torch.istft and its surroundings
+// (reference: modules/rvc/infer/modules/uvr5/mdxnet.py:58-75, :178-183).
+//
+// HBM-bound.  Algorithmic bytes per frame: n_bins_in*8 (spectrum) [+ n_bins*8 mask] + hop*4 (wave).
+//
+// Determinism: every output sample is owned by exactly one thread of one CTA and is the
+// left-to-right sum of its frames in ascending frame order (a carry buffer hands partial sums
+// from one round of G frames to the next), so the result does not depend on the tiling, the
+// batch composition or the number of GPUs.  The R-1 frames that precede a CTA's first owned
+// sample are recomputed (halo) instead of exchanged through global atomics.
+#include "al_kernels.h"
+
+namespace al {
+
+template <int D>
+__global__ void __launch_bounds__(Cfg<D>::UW * 32)
+istft_kernel(const IstftParams p) {
+    constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, NT = UW * 32, N = D * 1024, HW = D / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);     // [1024]
+    float2* s_slot = s_tw + 1024;                            // [UW][kSlotF2]
+    float* s_carry = reinterpret_cast<float*>(s_slot + UW * kSlotF2);   // [2][N - hop]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int orow = blockIdx.x / p.segs, seg = blockIdx.x - orow * p.segs;   // orow = (chunk*stems + s)*channels + c
+    const int ch = orow % p.channels;
+    const int cs = orow / p.channels;
+    const int stem = cs % p.stems, chunk = cs / p.stems;
+    const long long srow = p.spec_has_stems ? orow : (long long)chunk * p.channels + ch;
+    const int hop = p.hop;
+    const int carry_len = N - hop;
+
+    const SpecView sview{const_cast<float*>(p.spec), p.layout, p.n_frames_in, p.n_bins_in};
+    const SpecView mview{const_cast<float*>(p.mask), p.layout, p.n_frames_in, N / 2 + 1};
+
+    // owned untrimmed OLA positions [Pa, Pb)
+    const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
+    const long long Pend = (long long)p.out_start + p.out_len;
+    const long long Pb = min(Pa + (long long)p.hops_per_cta * hop, Pend);
+    if (Pa >= Pb) return;
+    int ta = (int)((Pa - N) / hop) + 1;                 // first frame touching Pa  (Pa >= N/2 > 0)
+    if (Pa < N) ta = 0;
+    ta = max(ta, 0);
+    const int tb = min((int)((Pb - 1) / hop), p.n_frames_total - 1);   // last frame touching Pb-1
+
+    const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
+    float* __restrict__ dst = p.dst + ((long long)stem * p.channels + ch) * p.dst_ch_stride +
+                              (long long)chunk * p.dst_chunk_stride + place;
+
+    for (int i = tid; i < 1024; i += NT) s_tw[i] = p.tw[i];
+    for (int i = tid; i < 2 * carry_len; i += NT) s_carry[i] = 0.f;
+
+    // rounds run past the last frame until the carry has been flushed up to Pb
+    const int t_last = (int)((Pb - 1) / hop);
+    int cbuf = 0;
+    for (int tr = ta; tr <= t_last; tr += G, cbuf ^= 1) {
+        __syncthreads();   // slots free (previous OLA finished), tables visible
+        const int nf = max(0, min(G, tb - tr + 1));   // live frames in this round (CTA-uniform)
+        if (nf > 0) {
+
+        // ---- stage A: load (x mask), Hermitian extension, inverse radix-D -> X_r[kappa] -------------
+        const bool t_fast = p.layout != 0;
+        for (int it = tid; it < G * 513; it += NT) {
+            int f, kappa;
+            if (t_fast) { kappa = it / G; f = it - kappa * G; }
+            else        { f = it / 513;  kappa = it - f * 513; }
+            const int t = tr + f;
+            const int ts = t - p.frame_pad;
+            const bool live = (t <= tb) && ts >= 0 && ts < p.n_frames_in;
+            float2 y[D];
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+                const int k = kappa + 1024 * q;
+                const int bin = (k <= N / 2) ? k : N - k;
+                float2 v = make_float2(0.f, 0.f);
+                if (live && bin < p.n_bins_in && bin >= p.zero_low_bins) {
+                    v = spec_load(sview, srow, ts, bin);
+                    if (p.mask) v = cmul(v, spec_load(mview, orow, ts, bin));
+                }
+                if (bin == 0 || bin == N / 2) v.y = 0.f;   // C2R ignores Im of DC / Nyquist
+                if (k > N / 2) v.y = -v.y;
+                y[q] = v;
+            }
+            SmallDft<D, true>::run(y);
+            float2* xs = s_slot + (f * HW) * kSlotF2 + kappa;
+            xs[0] = y[0];
+#pragma unroll
+            for (int r = 1; r < D; ++r)
+                xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
+        }
+        __syncthreads();
+
+        // ---- unit inverse FFT: warp = (frame f, pair w) ----------------------------------------------
+        {
+            const int f = warp / HW, w = warp - f * HW;
+            float2* slot = s_slot + warp * kSlotF2;
+            float re[32], im[32];
+            // Z_w[kappa] = X_2w[kappa] + i X_2w+1[kappa]; kappa > 512 through Hermitian symmetry
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int kappa = 32 * r + lane;
+                if (r < 16 || (r == 16 && lane == 0)) {
+                    const float2 a = slot[kappa], b = slot[kXHalf + kappa];
+                    re[r] = a.x - b.y;
+                    im[r] = a.y + b.x;
+                } else {
+                    const float2 a = slot[1024 - kappa], b = slot[kXHalf + 1024 - kappa];
+                    re[r] = a.x + b.y;
+                    im[r] = b.x - a.y;
+                }
+            }
+            __syncwarp();
+            warp_fft1024<true>(re, im, slot, s_tw, lane);
+            // z[n] = (x[D n + 2w], x[D n + 2w + 1]); apply the synthesis window, park the frame in the slot
+            const float2* __restrict__ win2 = reinterpret_cast<const float2*>(p.window) + w + HW * lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 wv = __ldg(win2 + HW * 32 * r);
+                slot[32 * r + lane] = make_float2(re[r] * wv.x, im[r] * wv.y);
+            }
+        }
+        __syncthreads();
+        }  // nf > 0
+
+        // ---- overlap-add: span [S, S + G*hop + carry_len), ascending frame order ---------------------
+        const long long S = (long long)tr * hop;
+        const float* cin = s_carry + cbuf * carry_len;
+        float* cout = s_carry + (cbuf ^ 1) * carry_len;
+        const float* frames = reinterpret_cast<const float*>(s_slot);
+        const int span = G * hop + carry_len;
+        for (int i = tid; i < span; i += NT) {
+            float acc = (i < carry_len) ? cin[i] : 0.f;
+            int f_lo = (i - N) / hop + 1;
+            if (i < N) f_lo = 0;
+            const int f_hi = min(nf - 1, i / hop);
+            for (int f = f_lo; f <= f_hi; ++f) {
+                const int j = i - f * hop;   // 0 <= j < N
+                const int w = (j % D) >> 1, n = j / D, c = j & 1;
+                acc += frames[((f * HW + w) * kSlotF2 + n) * 2 + c];
+            }
+            if (i < G * hop) {
+                const long long P = S + i;
+                if (P >= Pa && P < Pb) {
+                    const long long pp = P - p.out_start;
+                    float v = acc * __ldg(p.inv_env + P);
+                    if (p.weight) v *= __ldg(p.weight + pp);
+                    const long long q = place + pp;
+                    if (q >= 0 && q < p.dst_limit) dst[pp] = v;
+                }
+            } else {
+                cout[i - G * hop] = acc;
+            }
+        }
+    }
+}
+
+template <int D>
+static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStream_t stream) {
+    constexpr int UW = Cfg<D>::UW, N = D * 1024;
+    IstftParams p = p0;
+    const int rows = n_chunks * p.stems * p.channels;
+    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
+    // enough CTAs for ~4 waves over 148 SMs, but segments no shorter than 16 hops (halo <= ~30 %)
+    int segs = (4 * 148 + rows - 1) / rows;
+    int hpc = (total_hops + segs - 1) / segs;
+    hpc = max(hpc, 16);
+    p.hops_per_cta = hpc;
+    p.segs = (total_hops + hpc - 1) / hpc;
+    const size_t smem = 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) +
+                        2 * (size_t)(N - p.hop) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    istft_kernel<D><<<(unsigned)(rows * p.segs), UW * 32, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_istft(const IstftParams& p, int n_fft, int n_chunks, cudaStream_t stream) {
+    switch (n_fft) {
+        case 2048: return launch_istft_d<2>(p, n_chunks, stream);
+        case 4096: return launch_istft_d<4>(p, n_chunks, stream);
+        case 6144: return launch_istft_d<6>(p, n_chunks, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// inv_env[P] = 1 / sum_t w[P - t*hop]^2 over frames t in [0, n_frames_total)   (0 where empty)
+__global__ void env_kernel(const float* __restrict__ w, int n_fft, int hop, int n_frames_total,
+                           float* __restrict__ inv_env, long long total) {
+    const long long P = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= total) return;
+    long long t_lo = (P - n_fft) / hop + 1;
+    if (P < n_fft) t_lo = 0;
+    long long t_hi = P / hop;
+    if (t_hi > n_frames_total - 1) t_hi = n_frames_total - 1;
+    double acc = 0.0;
+    for (long long t = t_lo; t <= t_hi; ++t) {
+        const float v = w[P - t * hop];
+        acc += (double)v * (double)v;
+    }
+    inv_env[P] = acc > 1e-11 ? (float)(1.0 / acc) : 0.f;
+}
+
+cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
+                       cudaStream_t stream) {
+    const long long total = (long long)(n_frames_total - 1) * hop + n_fft;
+    env_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(window_raw, n_fft, hop, n_frames_total,
+                                                                    inv_env, total);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace al

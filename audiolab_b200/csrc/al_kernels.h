@@ -1,0 +1,83 @@
+// Internal kernel parameter blocks and launchers shared by the .cu files (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "al_fft.cuh"
+
+namespace al {
+
+void count_launch();
+
+struct StftParams {
+    const float* track;
+    long long n_valid;
+    long long ch_stride;
+    int channels;
+    const long long* chunk_offsets;
+    long long off0, off_step;
+    int chunk_len;
+    int center;
+    int hop;
+    int n_frames;
+    const float* window;   // [N] analysis window (already scaled)
+    const float2* tw;      // [32*32]  exp(-2 pi i k1 n2 / 1024)
+    const float2* ctw;     // [(D-1)*513] exp(-2 pi i r kappa / N), r = 1..D-1
+    float* spec;
+    int layout;
+    int n_bins_out;
+    int zero_low_bins;
+    // filled by the launcher
+    int ps;
+    int rounds_per_cta;
+    int tiles;
+};
+
+struct IstftParams {
+    const float* spec;
+    const float* mask;
+    int layout;
+    int n_bins_in;
+    int n_frames_in;
+    int frame_pad;
+    int n_frames_total;    // n_frames_in + 2*frame_pad
+    int stems, channels;
+    int spec_has_stems;
+    int zero_low_bins;
+    int hop;
+    const float* window;   // [N] synthesis window * 1/N (* sqrt(N) if normalized)
+    const float2* tw;
+    const float2* ctw;     // forward combine twiddles; the inverse uses their conjugate
+    const float* inv_env;  // [(n_frames_total-1)*hop + N]
+    int out_start;
+    int out_len;
+    const float* weight;
+    float* dst;
+    long long dst_ch_stride, dst_chunk_stride;
+    const long long* dst_offsets;
+    long long dst_off0, dst_off_step;
+    long long dst_limit;
+    // filled by the launcher
+    int hops_per_cta;
+    int segs;
+};
+
+cudaError_t launch_stft(const StftParams& p, int n_fft, int rows, cudaStream_t stream);
+cudaError_t launch_istft(const IstftParams& p, int n_fft, int n_chunks, cudaStream_t stream);
+
+cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len,
+                              const long long* offsets, const int* mult, const float* wtab,
+                              const int* tab_id, long long n_total, long long p0, long long p1,
+                              const float* halo_in, int raw_out, float eps, float scale, float* track,
+                              long long track_stride, cudaStream_t stream);
+
+cudaError_t launch_resample(const float* in, long long in_stride, float* out, long long out_stride,
+                            int rows, long long n_in, long long n_out, int up, int down,
+                            const float* taps, int n_taps, cudaStream_t stream);
+
+cudaError_t launch_sub(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+
+cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
+                       cudaStream_t stream);
+
+}  // namespace al

@@ -1,0 +1,164 @@
+/*
+ * audiolab_b200.h -- C ABI of libaudiolab_b200.so (hand-written sm_100a kernels for the
+ * AudioLab source-separation spectral hot path).
+ *
+ * The reference (d8ahazard/AudioLab) has NO FFI: its hot path is Python calling
+ * torch.stft / torch.istft / numpy inside the third-party `audio_separator` package.
+ * Each entry point below therefore cites the reference *Python* interface it replaces
+ * (paths relative to /root/reference); INTEGRATION.md shows the ctypes binding and the
+ * monkey-patch a maintainer would add (same mechanism as handlers/patch_separate.py:71-78).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (AL_E_*); al_last_error() gives the
+ *     message for the calling thread.  Nothing throws.  Nothing allocates caller-visible memory.
+ *   - all data pointers are DEVICE pointers owned by the caller (fp32 unless stated); work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous.
+ *   - plans own small read-only device tables (twiddles, windows, OLA envelopes); they are
+ *     immutable after creation except for an internal mutex-guarded envelope cache, so one plan
+ *     may be used from several streams / threads.
+ *   - spectrogram layouts (`layout`), `Fo` = number of stored bins (dim_f crop, <= n_fft/2+1):
+ *       AL_LAYOUT_FRAME_MAJOR 0   complex64 [rows, T, Fo]          (rows = chunk*channels + ch)
+ *       AL_LAYOUT_BIN_MAJOR   1   complex64 [rows, Fo, T]          == torch.stft(return_complex=True)
+ *       AL_LAYOUT_CAC         2   float32   [chunks, channels*2, Fo, T]   "complex as channels",
+ *                                 channel order (L.re, L.im, R.re, R.im)  == mdxnet.py:51-56
+ */
+#ifndef AUDIOLAB_B200_H_
+#define AUDIOLAB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AL_OK 0
+#define AL_E_ARG (-1)     /* bad argument */
+#define AL_E_CUDA (-2)    /* CUDA runtime error */
+#define AL_E_UNSUPPORTED (-3)
+
+#define AL_LAYOUT_FRAME_MAJOR 0
+#define AL_LAYOUT_BIN_MAJOR 1
+#define AL_LAYOUT_CAC 2
+
+typedef struct al_plan al_plan;
+
+/* Library version, e.g. 100 = 0.1.0. */
+int al_version(void);
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* al_last_error(void);
+
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t al_launch_count(void);
+
+/*
+ * Plan for one (n_fft, hop, window, normalized) STFT configuration.
+ *   n_fft in {2048, 4096, 6144}; window = HOST pointer to n_fft floats, or NULL for the
+ *   periodic Hann window torch.hann_window(n_fft) every reference call site uses
+ *   (modules/rvc/infer/modules/uvr5/mdxnet.py:27); normalized != 0 reproduces
+ *   torch.stft(normalized=True) (HTDemucs `spectro`).
+ */
+int al_plan_create(int n_fft, int hop, const float* window_host, int normalized, al_plan** out);
+int al_plan_destroy(al_plan* plan);
+
+/*
+ * K1  al_stft -- fused pad-and-chunk + reflect-pad + framing + window + R2C FFT + layout.
+ * Replaces: torch.stft(x, n_fft, hop, window, center=True) plus the layout shuffles around it:
+ *   modules/rvc/infer/modules/uvr5/mdxnet.py:41-56 (ConvTDFNetTrim.stft), the chunk gather of
+ *   mdxnet.py:152-164 (Predictor.demix_base), and upstream audio_separator STFT.__call__ /
+ *   BSRoformer.forward stft / HTDemucs._spec.
+ *
+ * track         [channels, >= n_valid] fp32, channel stride `ch_stride` floats; samples outside
+ *               [0, n_valid) read as zero (the reference's explicit zero padding).
+ * chunk c       covers track[off_c : off_c + chunk_len], off_c = chunk_offsets[c] (device int64
+ *               array) if non-NULL else off0 + c*off_step; off_c may be negative.
+ * center_pad    samples of reflect padding before chunk sample 0 (n_fft/2 for center=True;
+ *               HTDemucs._spec folded with its frame crop gives 3*hop/2). Requires chunk_len > center_pad.
+ * n_frames      frames to emit: frame t covers chunk samples [t*hop - center_pad, ... + n_fft).
+ * spec          output, `layout` above with T = n_frames, Fo = n_bins_out; bins < zero_low_bins are
+ *               written as 0 (upstream MDXSeparator zeroes spek[:, :, :3, :]).
+ */
+int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch_stride, int channels,
+            const int64_t* chunk_offsets, int64_t off0, int64_t off_step, int n_chunks, int chunk_len,
+            int center_pad, int n_frames, float* spec, int layout, int n_bins_out, int zero_low_bins,
+            void* stream);
+
+/*
+ * K2  al_istft -- fused (complex mask (.) spec | CaC -> complex) + zero freq-pad + C2R iFFT +
+ *                 synthesis window + overlap-add over frames + / sum(window^2) + centre trim
+ *                 [+ per-sample chunk weight] [+ trim-and-concat placement into a track buffer].
+ * Replaces: torch.istft(...) and its surroundings: mdxnet.py:58-75 (ConvTDFNetTrim.istft),
+ *   mdxnet.py:178-183 (trim + concat), BSRoformer.forward `stft_repr * mask` + istft,
+ *   HTDemucs._mask/_ispec.
+ *
+ * spec          `layout`, T = n_frames_in, Fo = n_bins_in, rows = chunk*channels + ch; bins >= n_bins_in
+ *               are zero (mdxnet.py:34-36,59-64 freq_pad).  When spec_has_stems != 0 the spectrogram
+ *               carries the stem axis itself: rows = (chunk*stems + stem)*channels + ch (HTDemucs).
+ * mask          NULL, or complex64 FRAME_MAJOR/BIN_MAJOR (same `layout`) with rows
+ *               (chunk*stems + stem)*channels + ch: out = istft(spec * mask) (complex multiply).
+ * frame_pad     zero frames virtually added before and after (HTDemucs._ispec pads 2): frame index
+ *               t of the padded sequence reads spec frame t - frame_pad.
+ * out_start     untrimmed OLA position of output sample 0 (n_fft/2 for center=True, plus any crop).
+ * out_len       samples produced per row.
+ * weight        NULL or [out_len] device floats multiplied into the output (chunk window).
+ * dst           out rows are written at
+ *                 dst + (stem*channels + ch)*dst_ch_stride + chunk*dst_chunk_stride + place_c + p
+ *               for p in [0, out_len) when 0 <= place_c + p < dst_limit, with
+ *               place_c = dst_offsets[c] (device int64) if non-NULL else dst_off0 + c*dst_off_step.
+ *               Dense chunk waves: dst_ch_stride = out_len, dst_chunk_stride = stems*channels*out_len,
+ *               place = 0, dst_limit = out_len.
+ */
+int al_istft(const al_plan* plan, const float* spec, const float* mask, int layout, int n_bins_in,
+             int n_frames_in, int frame_pad, int n_chunks, int stems, int channels, int spec_has_stems,
+             int zero_low_bins, int out_start, int out_len, const float* weight, float* dst,
+             int64_t dst_ch_stride, int64_t dst_chunk_stride, const int64_t* dst_offsets,
+             int64_t dst_off0, int64_t dst_off_step, int64_t dst_limit, void* stream);
+
+/*
+ * K2b al_ola_gather -- deterministic windowed overlap-add of chunk outputs into a track:
+ *   track[r, p] = (halo_in[r, p - p0] + sum_{c ascending, off_c <= p < off_c + len_c}
+ *                  mult_c * W_c[p - off_c] * chunks[c, r, p - off_c]) / max(sum_c mult_c * W_c[..], eps)
+ * Replaces: `result[..., s:e] += x * window; counter[..., s:e] += window; result / counter` of
+ *   upstream MDXSeparator.demix / MDXCSeparator.demix / demucs.apply.apply_model (SURVEY.md
+ *   A.1-A.3; stem_separator.py never sees it because it happens inside `separator.separate`,
+ *   modules/separator/stem_separator.py:281).
+ *
+ * chunks        [n_chunks, rows, chunk_len] fp32 dense chunk waves (al_istft dense output).
+ * offsets       device int64 [n_chunks], ascending; len_c = min(chunk_len, n_total - off_c).
+ * mult          device int32 [n_chunks] or NULL (all 1): tail-aligned chunks the reference evaluates
+ *               several times.
+ * wtab          device [n_tab, chunk_len] weight tables; chunk c uses table tab_id[c] (NULL -> 0);
+ *               wtab NULL means weight 1.
+ * [p0, p1)      track positions this call produces into track[r*track_stride + p] (chunk-range
+ *               sharding owns a sub-range).  halo_in (NULL or [rows, p1-p0]) holds partial sums
+ *               received from the left neighbour; when raw_out != 0 the un-normalised running sum
+ *               is written instead (the partial sums a rank sends to its right neighbour).
+ */
+int al_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len, const int64_t* offsets,
+                  const int32_t* mult, const float* wtab, const int32_t* tab_id, int64_t n_total,
+                  int64_t p0, int64_t p1, const float* halo_in, int raw_out, float eps, float scale,
+                  float* track, int64_t track_stride, void* stream);
+
+/*
+ * K3  al_resample_poly -- polyphase FIR resampler with scipy.signal.resample_poly semantics
+ *   (zero-phase, zero-padded ends): out[m] = sum_k taps[k] * x_up[m*down + half - k].
+ * Replaces: librosa.load(sr=44100) resampling (modules/separator/stem_separator.py:865) /
+ *   res_type "polyphase" (modules/rvc/infer/lib/uvr5_pack/lib_v5/model_param_init.py:22).
+ * taps = DEVICE pointer to n_taps floats (already multiplied by `up`), n_taps odd, half=(n_taps-1)/2.
+ * in [rows, n_in] (row stride in_stride) -> out [rows, n_out] (row stride out_stride),
+ * n_out = ceil(n_in*up/down).
+ */
+int al_resample_poly(const float* in, int64_t in_stride, float* out, int64_t out_stride, int rows,
+                     int64_t n_in, int64_t n_out, int up, int down, const float* taps, int n_taps,
+                     void* stream);
+
+/*
+ * al_sub_scaled -- secondary stem: out = a - b (elementwise), the `mix - primary` complement of
+ * upstream MDXCSeparator / MDXSeparator when spectral inversion is off.
+ */
+int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOLAB_B200_H_ */
