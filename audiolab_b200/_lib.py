@@ -33,7 +33,7 @@ SIGNATURES = {
     "al_istft": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_i64, c_i64, c_i64p,
                            c_i64, c_i64, c_i64, C.c_void_p]),
-    "al_ola_gather": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64p, c_i32p, c_f32p, c_i32p, c_i64, c_i64,
+    "al_ola_gather": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p, c_i32p, c_f32p, c_i32p, c_i64, c_i64,
                                 c_i64, c_f32p, C.c_int, C.c_float, C.c_float, c_f32p, c_i64, C.c_void_p]),
     "al_resample_poly": (C.c_int, [c_f32p, c_i64, c_f32p, c_i64, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_f32p,
                                    C.c_int, C.c_void_p]),

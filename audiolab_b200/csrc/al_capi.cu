@@ -129,7 +129,7 @@ int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch
     if (channels <= 0 || n_chunks < 0 || n_frames < 0 || chunk_len <= 0)
         return fail(AL_E_ARG, "al_stft: bad sizes (channels %d chunks %d frames %d chunk_len %d)", channels,
                     n_chunks, n_frames, chunk_len);
-    if (layout < 0 || layout > 2) return fail(AL_E_ARG, "al_stft: bad layout %d", layout);
+    if (layout < 0 || layout > 3) return fail(AL_E_ARG, "al_stft: bad layout %d", layout);
     if (n_bins_out <= 0 || n_bins_out > plan->n_fft / 2 + 1) return fail(AL_E_ARG, "al_stft: bad n_bins_out %d", n_bins_out);
     if (center_pad < 0 || center_pad >= chunk_len)
         return fail(AL_E_ARG, "al_stft: center_pad %d must be < chunk_len %d (single reflection)", center_pad, chunk_len);
@@ -190,7 +190,7 @@ int al_istft(const al_plan* plan_c, const float* spec, const float* mask, int la
     if (n_chunks == 0 || out_len == 0) return AL_OK;
     if (n_chunks < 0 || stems <= 0 || channels <= 0 || n_frames_in <= 0 || out_len < 0 || frame_pad < 0)
         return fail(AL_E_ARG, "al_istft: bad sizes");
-    if (layout < 0 || layout > 2) return fail(AL_E_ARG, "al_istft: bad layout %d", layout);
+    if (layout < 0 || layout > 3) return fail(AL_E_ARG, "al_istft: bad layout %d", layout);
     if (mask && layout == 2) return fail(AL_E_UNSUPPORTED, "al_istft: mask multiply needs a complex layout");
     if (n_bins_in <= 0 || n_bins_in > plan->n_fft / 2 + 1) return fail(AL_E_ARG, "al_istft: bad n_bins_in %d", n_bins_in);
     const int T = n_frames_in + 2 * frame_pad;
@@ -232,14 +232,14 @@ int al_istft(const al_plan* plan_c, const float* spec, const float* mask, int la
     return AL_OK;
 }
 
-int al_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len, const int64_t* offsets,
+int al_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len, const int64_t* offsets,
                   const int32_t* mult, const float* wtab, const int32_t* tab_id, int64_t n_total,
                   int64_t p0, int64_t p1, const float* halo_in, int raw_out, float eps, float scale,
                   float* track, int64_t track_stride, void* stream) {
     if (!chunks || !offsets || !track) return fail(AL_E_ARG, "al_ola_gather: NULL argument");
-    if (n_chunks <= 0 || rows <= 0 || chunk_len <= 0 || p0 < 0 || p1 < p0)
+    if (n_chunks <= 0 || rows <= 0 || chunk_len <= 0 || p0 < 0 || p1 < p0 || data_chunk0 < 0 || data_chunk0 > n_chunks)
         return fail(AL_E_ARG, "al_ola_gather: bad sizes");
-    cudaError_t e = al::launch_ola_gather(chunks, n_chunks, rows, chunk_len,
+    cudaError_t e = al::launch_ola_gather(chunks, n_chunks, data_chunk0, rows, chunk_len,
                                           reinterpret_cast<const long long*>(offsets), mult, wtab, tab_id, n_total,
                                           p0, p1, halo_in, raw_out, eps, scale, track, track_stride,
                                           (cudaStream_t)stream);

@@ -118,35 +118,42 @@ template <> struct Cfg<4> { static constexpr int G = 4, UW = 8; };
 template <> struct Cfg<6> { static constexpr int G = 4, UW = 12; };
 
 // ---- spectrogram addressing --------------------------------------------------------------------
-// layout 0: c64 [rows, T, Fo]; 1: c64 [rows, Fo, T]; 2: f32 [rows*2 (re, im planes), Fo, T]
+// row = group*channels + ch  (group = chunk, or chunk*stems + stem)
+// layout 0: c64 [rows, T, Fo]; 1: c64 [rows, Fo, T]; 2: f32 [rows*2 (re, im planes), Fo, T];
+// layout 3: c64 [groups, T, Fo, channels]  (upstream RoFormer 'b t (f s c)')
 struct SpecView {
     float* base;
     int layout;
     int T;
     int Fo;
+    int channels;
 };
 
+__device__ __forceinline__ int64_t spec_index(const SpecView& v, int64_t row, int t, int bin) {
+    if (v.layout == 0) return (row * v.T + t) * v.Fo + bin;
+    if (v.layout == 1) return (row * v.Fo + bin) * (int64_t)v.T + t;
+    if (v.layout == 3) {
+        const int64_t g = row / v.channels;
+        const int ch = (int)(row - g * v.channels);
+        return ((g * v.T + t) * v.Fo + bin) * v.channels + ch;
+    }
+    return ((row * 2) * v.Fo + bin) * (int64_t)v.T + t;
+}
+
 __device__ __forceinline__ void spec_store(const SpecView& v, int64_t row, int t, int bin, float2 val) {
-    if (v.layout == 0) {
-        reinterpret_cast<float2*>(v.base)[(row * v.T + t) * v.Fo + bin] = val;
-    } else if (v.layout == 1) {
-        reinterpret_cast<float2*>(v.base)[(row * v.Fo + bin) * (int64_t)v.T + t] = val;
+    const int64_t o = spec_index(v, row, t, bin);
+    if (v.layout != 2) {
+        reinterpret_cast<float2*>(v.base)[o] = val;
     } else {
-        const int64_t o = ((row * 2) * v.Fo + bin) * (int64_t)v.T + t;
         v.base[o] = val.x;
         v.base[o + (int64_t)v.Fo * v.T] = val.y;
     }
 }
 
 __device__ __forceinline__ float2 spec_load(const SpecView& v, int64_t row, int t, int bin) {
-    if (v.layout == 0) {
-        return __ldg(reinterpret_cast<const float2*>(v.base) + (row * v.T + t) * v.Fo + bin);
-    } else if (v.layout == 1) {
-        return __ldg(reinterpret_cast<const float2*>(v.base) + (row * v.Fo + bin) * (int64_t)v.T + t);
-    } else {
-        const int64_t o = ((row * 2) * v.Fo + bin) * (int64_t)v.T + t;
-        return make_float2(__ldg(v.base + o), __ldg(v.base + o + (int64_t)v.Fo * v.T));
-    }
+    const int64_t o = spec_index(v, row, t, bin);
+    if (v.layout != 2) return __ldg(reinterpret_cast<const float2*>(v.base) + o);
+    return make_float2(__ldg(v.base + o), __ldg(v.base + o + (int64_t)v.Fo * v.T));
 }
 
 }  // namespace al

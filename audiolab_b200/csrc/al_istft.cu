@@ -32,8 +32,8 @@ istft_kernel(const IstftParams p) {
     const int hop = p.hop;
     const int carry_len = N - hop;
 
-    const SpecView sview{const_cast<float*>(p.spec), p.layout, p.n_frames_in, p.n_bins_in};
-    const SpecView mview{const_cast<float*>(p.mask), p.layout, p.n_frames_in, N / 2 + 1};
+    const SpecView sview{const_cast<float*>(p.spec), p.layout, p.n_frames_in, p.n_bins_in, p.channels};
+    const SpecView mview{const_cast<float*>(p.mask), p.layout, p.n_frames_in, N / 2 + 1, p.channels};
 
     // owned untrimmed OLA positions [Pa, Pb)
     const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
@@ -61,7 +61,7 @@ istft_kernel(const IstftParams p) {
         if (nf > 0) {
 
         // ---- stage A: load (x mask), Hermitian extension, inverse radix-D -> X_r[kappa] -------------
-        const bool t_fast = p.layout != 0;
+        const bool t_fast = (p.layout == 1 || p.layout == 2);
         for (int it = tid; it < G * 513; it += NT) {
             int f, kappa;
             if (t_fast) { kappa = it / G; f = it - kappa * G; }

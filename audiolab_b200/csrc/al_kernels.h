@@ -65,7 +65,7 @@ struct IstftParams {
 cudaError_t launch_stft(const StftParams& p, int n_fft, int rows, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_fft, int n_chunks, cudaStream_t stream);
 
-cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len,
+cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                               const long long* offsets, const int* mult, const float* wtab,
                               const int* tab_id, long long n_total, long long p0, long long p1,
                               const float* halo_in, int raw_out, float eps, float scale, float* track,

@@ -11,7 +11,7 @@
 namespace al {
 
 __global__ void __launch_bounds__(256)
-ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int rows, int chunk_len,
+ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                   const long long* __restrict__ offsets, const int* __restrict__ mult,
                   const float* __restrict__ wtab, const int* __restrict__ tab_id, long long n_total,
                   long long p0, long long p1, const float* __restrict__ halo_in, int raw_out, float eps,
@@ -37,7 +37,9 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int rows, int 
             float w = 1.f;
             if (wtab) w = __ldg(wtab + (long long)(tab_id ? __ldg(tab_id + c) : 0) * chunk_len + j);
             const int m = mult ? __ldg(mult + c) : 1;
-            const float x = __ldg(chunks + ((long long)c * rows + r) * chunk_len + j);
+            // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive through
+            // halo_in, only their weights are counted here
+            const float x = c >= data_chunk0 ? __ldg(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j) : 0.f;
             for (int k = 0; k < m; ++k) {   // the reference re-adds a tail chunk m times; keep its rounding
                 acc += x * w;
                 wsum += w;
@@ -50,7 +52,7 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int rows, int 
     }
 }
 
-cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len,
+cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                               const long long* offsets, const int* mult, const float* wtab,
                               const int* tab_id, long long n_total, long long p0, long long p1,
                               const float* halo_in, int raw_out, float eps, float scale, float* track,
@@ -58,7 +60,7 @@ cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int rows, int c
     if (p1 <= p0) return cudaSuccess;
     const long long n = p1 - p0;
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)min(rows, 8));
-    ola_gather_kernel<<<grid, 256, 0, stream>>>(chunks, n_chunks, rows, chunk_len, offsets, mult, wtab, tab_id,
+    ola_gather_kernel<<<grid, 256, 0, stream>>>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id,
                                                 n_total, p0, p1, halo_in, raw_out, eps, scale, track,
                                                 track_stride);
     count_launch();

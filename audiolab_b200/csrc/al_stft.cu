@@ -27,7 +27,7 @@ stft_kernel(const StftParams p) {
     const float* __restrict__ src = p.track + (long long)ch * p.ch_stride;
     const int ps = p.ps;
     const int span = (G - 1) * p.hop + N;
-    const SpecView view{p.spec, p.layout, p.n_frames, p.n_bins_out};
+    const SpecView view{p.spec, p.layout, p.n_frames, p.n_bins_out, p.channels};
 
     for (int i = tid; i < 1024; i += NT) s_tw[i] = p.tw[i];
 
@@ -84,7 +84,7 @@ stft_kernel(const StftParams p) {
         __syncthreads();
 
         // ---- radix-D combine + store ----------------------------------------------------------------
-        const bool t_fast = p.layout != 0;
+        const bool t_fast = (p.layout == 1 || p.layout == 2);
         for (int it = tid; it < G * 513; it += NT) {
             int f, kappa;
             if (t_fast) { kappa = it / G; f = it - kappa * G; }

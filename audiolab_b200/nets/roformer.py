@@ -1,0 +1,251 @@
+"""BS-RoFormer / Mel-Band RoFormer mask networks for the CUDA demix path.
+
+The module tree and parameter names follow upstream (lucidrains / ZFTurbo as vendored by
+`audio-separator`), so a released checkpoint's ``state_dict`` loads unchanged.
+What differs from upstream's ``forward``: STFT, the complex mask multiply and the iSTFT are
+NOT here -- they are the al_stft / al_istft kernels.  ``mask()`` consumes the spectrogram in the
+kernels' FRAME_INTERLEAVED layout ``[b, t, f, s]`` complex64 (bit-identical to upstream's
+``'b s f t c -> b t (f s c)'`` view) and returns the mask ``[b, n, t, f, s]`` complex64 in the
+layout al_istft multiplies in-kernel, so no permute copies surround the network.
+
+Compute dtype: ``torch.bfloat16`` runs the network under autocast (the reference constructs its
+Separator with ``use_autocast=True``, /root/reference/modules/separator/stem_separator.py:106);
+``torch.float32`` is the parity configuration.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..configs import RoformerConfig
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        return F.normalize(x, dim=-1) * self.scale * self.gamma
+
+
+class RotaryEmbedding(nn.Module):
+    def __init__(self, dim: int, theta: float = 10000.0):
+        super().__init__()
+        self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)),
+                                  requires_grad=False)
+        self._cache = {}
+
+    def tables(self, n: int, device, dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+        key = (n, str(device), dtype)
+        hit = self._cache.get(key)
+        if hit is None:
+            pos = torch.arange(n, device=device, dtype=torch.float32)
+            ang = torch.repeat_interleave(pos[:, None] * self.freqs.to(device)[None, :], 2, dim=-1)
+            hit = (ang.cos().to(dtype), ang.sin().to(dtype))
+            self._cache[key] = hit
+        return hit
+
+    def rotate(self, t: torch.Tensor) -> torch.Tensor:
+        cos, sin = self.tables(t.shape[-2], t.device, t.dtype)
+        x = t.unflatten(-1, (-1, 2))
+        rot = torch.stack((-x[..., 1], x[..., 0]), dim=-1).flatten(-2)
+        return t * cos + rot * sin
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int, mult: int = 4):
+        super().__init__()
+        inner = int(dim * mult)
+        self.net = nn.Sequential(RMSNorm(dim), nn.Linear(dim, inner), nn.GELU(), nn.Dropout(0.0),
+                                 nn.Linear(inner, dim), nn.Dropout(0.0))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, heads: int, dim_head: int, rotary_embed: Optional[RotaryEmbedding]):
+        super().__init__()
+        self.heads = heads
+        inner = heads * dim_head
+        self.rotary_embed = rotary_embed
+        self.norm = RMSNorm(dim)
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_gates = nn.Linear(dim, heads)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), nn.Dropout(0.0))
+
+    def forward(self, x):
+        b, n, _ = x.shape
+        x = self.norm(x)
+        q, k, v = self.to_qkv(x).view(b, n, 3, self.heads, -1).permute(2, 0, 3, 1, 4)
+        if self.rotary_embed is not None:
+            q = self.rotary_embed.rotate(q)
+            k = self.rotary_embed.rotate(k)
+        out = F.scaled_dot_product_attention(q, k, v)
+        gates = self.to_gates(x)
+        out = out * gates.permute(0, 2, 1).unsqueeze(-1).sigmoid()
+        return self.to_out(out.permute(0, 2, 1, 3).reshape(b, n, -1))
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, ff_mult, rotary_embed, norm_output):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            nn.ModuleList([Attention(dim, heads, dim_head, rotary_embed), FeedForward(dim, ff_mult)])
+            for _ in range(depth)
+        ])
+        self.norm = RMSNorm(dim) if norm_output else nn.Identity()
+
+    def forward(self, x):
+        for attn, ff in self.layers:
+            x = attn(x) + x
+            x = ff(x) + x
+        return self.norm(x)
+
+
+class BandSplit(nn.Module):
+    def __init__(self, dim: int, dim_inputs: Tuple[int, ...]):
+        super().__init__()
+        self.dim_inputs = tuple(dim_inputs)
+        self.to_features = nn.ModuleList([nn.Sequential(RMSNorm(d), nn.Linear(d, dim)) for d in dim_inputs])
+
+    def forward(self, x):
+        parts = x.split(self.dim_inputs, dim=-1)
+        return torch.stack([f(p) for p, f in zip(parts, self.to_features)], dim=-2)
+
+
+def _mlp(dim_in, dim_out, dim_hidden, depth):
+    dims = (dim_in,) + (dim_hidden,) * (depth - 1) + (dim_out,)
+    net = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        net.append(nn.Linear(a, b))
+        if i != len(dims) - 2:
+            net.append(nn.Tanh())
+    return nn.Sequential(*net)
+
+
+class MaskEstimator(nn.Module):
+    def __init__(self, dim, dim_inputs, depth, mlp_expansion_factor=4):
+        super().__init__()
+        self.dim_inputs = tuple(dim_inputs)
+        self.to_freqs = nn.ModuleList([
+            nn.Sequential(_mlp(dim, d * 2, dim * mlp_expansion_factor, depth), nn.GLU(dim=-1)) for d in dim_inputs
+        ])
+
+    def forward(self, x):
+        return torch.cat([mlp(b) for b, mlp in zip(x.unbind(dim=-2), self.to_freqs)], dim=-1)
+
+
+# ---- mel band membership (librosa.filters.mel, Slaney scale / norm; only `> 0` is used) ------------
+def _hz_to_mel(f):
+    f = np.asarray(f, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, f / f_sp)
+
+
+def _mel_to_hz(m):
+    m = np.asarray(m, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_band_membership(sr: int, n_fft: int, n_mels: int) -> np.ndarray:
+    fftfreqs = np.linspace(0, sr / 2.0, 1 + n_fft // 2)
+    mel_f = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    fb = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        fb[i] = np.maximum(0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    fb *= (2.0 / (mel_f[2: n_mels + 2] - mel_f[:n_mels]))[:, None]
+    fb = fb.astype(np.float32)
+    fb[0, 0] = 1.0
+    fb[-1, -1] = 1.0
+    member = fb > 0
+    if not member.any(axis=0).all():
+        raise ValueError("mel bands do not cover every frequency bin")
+    return member
+
+
+class RoformerMaskNet(nn.Module):
+    """spec [b, t, f, s] complex64 -> mask [b, n, t, f, s] complex64."""
+
+    def __init__(self, cfg: RoformerConfig):
+        super().__init__()
+        self.cfg = c = cfg
+        mel = c.kind == "mel"
+        time_rot, freq_rot = RotaryEmbedding(c.dim_head), RotaryEmbedding(c.dim_head)
+        self.layers = nn.ModuleList([
+            nn.ModuleList([
+                Transformer(c.dim, c.time_transformer_depth, c.heads, c.dim_head, c.ff_mult, time_rot, mel),
+                Transformer(c.dim, c.freq_transformer_depth, c.heads, c.dim_head, c.ff_mult, freq_rot, mel),
+            ]) for _ in range(c.depth)
+        ])
+        ch = c.audio_channels
+        if mel:
+            member = torch.from_numpy(mel_band_membership(c.sample_rate, c.stft_n_fft, c.num_bands))
+            freqs = member.shape[1]
+            freq_indices = torch.arange(freqs)[None].expand(c.num_bands, freqs)[member]
+            if c.stereo:
+                freq_indices = (freq_indices[:, None] * 2 + torch.arange(2)[None]).reshape(-1)
+            self.register_buffer("freq_indices", freq_indices, persistent=False)
+            self.register_buffer("num_bands_per_freq", member.sum(dim=0), persistent=False)
+            bands = member.sum(dim=1).tolist()
+        else:
+            self.final_norm = RMSNorm(c.dim)
+            bands = list(c.freqs_per_bands)
+            if sum(bands) != c.stft_n_fft // 2 + 1:
+                raise ValueError("freqs_per_bands must sum to n_fft/2+1")
+        dims = tuple(2 * f * ch for f in bands)
+        self.band_split = BandSplit(c.dim, dims)
+        self.mask_estimators = nn.ModuleList([
+            MaskEstimator(c.dim, dims, c.mask_estimator_depth, c.mlp_expansion_factor) for _ in range(c.num_stems)
+        ])
+        self.compute_dtype = torch.float32
+
+    def set_compute_dtype(self, dtype: torch.dtype) -> "RoformerMaskNet":
+        self.compute_dtype = dtype
+        return self
+
+    def _axial(self, x):
+        for time_transformer, freq_transformer in self.layers:
+            b, t, f, d = x.shape
+            x = time_transformer(x.permute(0, 2, 1, 3).reshape(b * f, t, d))
+            x = freq_transformer(x.view(b, f, t, d).permute(0, 2, 1, 3).reshape(b * t, f, d))
+            x = x.view(b, t, f, d)
+        return x
+
+    @torch.no_grad()
+    def mask(self, spec: torch.Tensor) -> torch.Tensor:
+        c = self.cfg
+        b, t, f, s = spec.shape
+        feats = torch.view_as_real(spec).reshape(b, t, f * s * 2)          # 'b t (f s c)', zero-copy
+        ac = self.compute_dtype != torch.float32
+        with torch.autocast("cuda", dtype=self.compute_dtype, enabled=ac):
+            if c.kind == "mel":
+                rows = torch.view_as_real(spec).reshape(b, t, f * s, 2)
+                x = rows[:, :, self.freq_indices].reshape(b, t, -1)
+            else:
+                x = feats
+            x = self.band_split(x)
+            x = self._axial(x)
+            if c.kind != "mel":
+                x = self.final_norm(x)
+            m = torch.stack([fn(x) for fn in self.mask_estimators], dim=1)  # b n t (f' s c)
+        n = m.shape[1]
+        m = m.float()
+        if c.kind == "mel":
+            m = torch.view_as_complex(m.reshape(b, n, t, -1, 2))
+            idx = self.freq_indices[None, None, None, :].expand(b, n, t, -1)
+            summed = torch.zeros(b, n, t, f * s, dtype=m.dtype, device=m.device).scatter_add_(3, idx, m)
+            denom = torch.repeat_interleave(self.num_bands_per_freq, s).clamp(min=1e-8)
+            return (summed / denom).view(b, n, t, f, s)
+        return torch.view_as_complex(m.reshape(b, n, t, f, s, 2))

@@ -1,0 +1,244 @@
+"""``Separator`` -- duck type of ``audio_separator.separator.Separator`` as AudioLab uses it.
+
+Callee surface the reference's orchestrator expects (call sites
+/root/reference/modules/separator/stem_separator.py:102-107 ctor, :124 download_model_files,
+:394 load_model, :281-282 separate -> file names relative to output_dir, :399-400 output_dir /
+model_instance.output_dir; /root/reference/handlers/reverb.py:382 ``output_dir=`` ctor kwarg).
+Output names carry ``(Vocals)`` / ``(Instrumental)`` (stem_separator.py:325-329) or the 4/6 stem
+names (:491-500).
+
+Underneath there is an in-memory path ``separate_tensor`` (device tensors in and out), which is what
+bench.py and the orchestrator use; ``separate(path)`` wraps it with WAV I/O.
+There is no CPU path: constructing a Separator without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import replace
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import spectral as sp
+from .configs import HTDemucsConfig, MdxConfig, RoformerConfig
+from .demix import HTDemucsDemixer, MdxDemixer, RoformerDemixer
+from .wavio import read_wav, write_wav
+
+DEMUCS_4 = ["Drums", "Bass", "Other", "Vocals"]
+DEMUCS_6 = ["Drums", "Bass", "Other", "Vocals", "Guitar", "Piano"]
+
+
+def _arch_of(model_filename: str) -> str:
+    name = model_filename.lower()
+    if name.endswith(".onnx"):
+        return "mdx"
+    if "roformer" in name:
+        return "mel_roformer" if ("mel_band" in name or "melband" in name) else "bs_roformer"
+    if name.startswith("htdemucs") or name.startswith("hdemucs"):
+        return "htdemucs"
+    if name.endswith(".pth"):
+        return "vr"
+    if "mdx23c" in name:
+        return "mdx23c"
+    raise ValueError(f"cannot infer the architecture of {model_filename!r}")
+
+
+class _ModelInstance:
+    """What ``separator.model_instance`` exposes to the orchestrator and to patch_separate.py."""
+
+    def __init__(self, arch: str, model_path: str, device, logger, output_dir):
+        self.arch = arch
+        self.model_path = model_path
+        self.torch_device = device
+        self.logger = logger
+        self.output_dir = output_dir
+        self.model_run: Optional[Callable] = None
+        self.segment_size = None
+        self.dim_t = None
+        self.demixer = None
+        self.primary_stem = "Vocals"
+        self.secondary_stem = "Instrumental"
+        self.stem_names: List[str] = []
+
+
+class Separator:
+    def __init__(self, log_level=logging.INFO, model_file_dir: str = "/tmp/audio-separator-models/",
+                 output_dir: Optional[str] = None, output_format: str = "WAV", normalization_threshold: float = 0.9,
+                 invert_using_spec: bool = False, sample_rate: int = 44100, use_autocast: bool = False,
+                 mdx_params: Optional[dict] = None, mdxc_params: Optional[dict] = None,
+                 demucs_params: Optional[dict] = None, allow_random_init: bool = False, device: str = "cuda:0",
+                 model_overrides: Optional[dict] = None):
+        self.logger = logging.getLogger(__name__)
+        self.logger.setLevel(log_level)
+        if not torch.cuda.is_available():
+            raise RuntimeError("audiolab_b200.Separator needs a CUDA device (B200); there is no CPU fallback")
+        self.torch_device = torch.device(device)
+        self.model_file_dir = model_file_dir
+        self.output_dir = output_dir or os.getcwd()
+        self.output_format = output_format
+        self.normalization_threshold = normalization_threshold
+        self.invert_using_spec = invert_using_spec
+        self.sample_rate = sample_rate
+        self.use_autocast = use_autocast
+        self.mdx_params = {"hop_length": 1024, "segment_size": 256, "overlap": 0.25, "batch_size": 1,
+                           "enable_denoise": False, **(mdx_params or {})}
+        self.mdxc_params = {"segment_size": 256, "override_model_segment_size": False, "batch_size": 4,
+                            "overlap": 4, "pitch_shift": 0, **(mdxc_params or {})}
+        self.demucs_params = {"segment_size": "Default", "shifts": 2, "overlap": 0.25, "segments_enabled": True,
+                              **(demucs_params or {})}
+        self.allow_random_init = allow_random_init or os.environ.get("AUDIOLAB_B200_RANDOM_INIT") == "1"
+        self.model_overrides = model_overrides or {}
+        self.model_instance: Optional[_ModelInstance] = None
+        self.model_name: Optional[str] = None
+        self._resample_taps = {}
+
+    # ------------------------------------------------------------------------------------------
+    def download_model_files(self, model_filename: str):
+        """The reference downloads weights here (stem_separator.py:123-124).  No network in this build:
+        report whether the file is already under model_file_dir."""
+        path = os.path.join(self.model_file_dir, model_filename)
+        if not os.path.exists(path):
+            self.logger.debug("model file %s not present (no download in this environment)", path)
+        return path
+
+    def _state_dict_or_none(self, path: str):
+        if os.path.exists(path) and not path.endswith((".onnx", ".yaml")):
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            return sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+        if not self.allow_random_init:
+            raise FileNotFoundError(
+                f"{path} not found and allow_random_init is False (set allow_random_init=True or "
+                "AUDIOLAB_B200_RANDOM_INIT=1 to run with seeded random weights)")
+        return None
+
+    def load_model(self, model_filename: str = "model_bs_roformer_ep_368_sdr_12.9628.ckpt"):
+        arch = _arch_of(model_filename)
+        path = os.path.join(self.model_file_dir, model_filename)
+        inst = _ModelInstance(arch, path, self.torch_device, self.logger, self.output_dir)
+        ov = dict(self.model_overrides.get(model_filename, self.model_overrides.get(arch, {})))
+        net = ov.pop("net", None)
+        if arch in ("bs_roformer", "mel_roformer"):
+            from .nets.roformer import RoformerMaskNet
+            cfg = RoformerConfig(kind="mel" if arch == "mel_roformer" else "bs",
+                                 num_overlap=int(self.mdxc_params["overlap"]))
+            cfg = replace(cfg, **ov)
+            if net is None:
+                sd = self._state_dict_or_none(path)
+                torch.manual_seed(4321)
+                net = RoformerMaskNet(cfg)
+                if sd is not None:
+                    net.load_state_dict(sd, strict=True)
+            net = net.to(self.torch_device).eval()
+            net.set_compute_dtype(torch.bfloat16 if self.use_autocast else torch.float32)
+            inst.demixer = RoformerDemixer(cfg, net, batch_size=int(self.mdxc_params["batch_size"]))
+            inst.stem_names = ["Vocals"] if cfg.num_stems == 1 else [f"Stem{i}" for i in range(cfg.num_stems)]
+            inst.run = lambda mix: inst.demixer.demix(mix)
+        elif arch == "mdx":
+            from .nets.tfc_tdf import TfcTdfNet
+            seg = int(self.mdx_params["segment_size"])
+            cfg = MdxConfig(hop=int(self.mdx_params["hop_length"]), dim_t_log2=int(np.log2(seg)),
+                            overlap=float(self.mdx_params["overlap"]), denoise=bool(self.mdx_params["enable_denoise"]),
+                            zero_low_bins=3)
+            cfg = replace(cfg, **ov)
+            if net is None:
+                if not self.allow_random_init:
+                    raise FileNotFoundError(f"{path}: ONNX import is out of scope; pass model_overrides[...]['net'] "
+                                            "or allow_random_init=True")
+                torch.manual_seed(4321)
+                net = TfcTdfNet(cfg.dim_f)
+            net = net.to(self.torch_device).eval()
+            inst.segment_size, inst.dim_t = seg, cfg.dim_t
+            autocast = self.use_autocast
+
+            def model_run(spek, _net=net):
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return _net(spek)
+
+            inst.model_run = model_run
+            inst.demixer = MdxDemixer(cfg, lambda s: inst.model_run(s), batch_size=max(1, int(self.mdx_params["batch_size"])))
+            inst.stem_names = ["Vocals"]
+            inst.run = lambda mix: inst.demixer.demix_windowed(mix)[None]
+        elif arch == "htdemucs":
+            from .nets.htdemucs import HTDemucsCore
+            six = "6s" in model_filename
+            shifts = int(self.demucs_params["shifts"])
+            cfg = HTDemucsConfig(num_sources=6 if six else 4, shifts=shifts, overlap=float(self.demucs_params["overlap"]))
+            cfg = replace(cfg, **ov)
+            if net is None:
+                self._state_dict_or_none(path)
+                torch.manual_seed(4321)
+                net = HTDemucsCore(num_sources=cfg.num_sources)
+            net = net.to(self.torch_device).eval()
+            autocast = self.use_autocast
+
+            def core(x, xt, _net=net):
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return _net(x, xt)
+
+            inst.demixer = HTDemucsDemixer(cfg, core)
+            inst.stem_names = DEMUCS_6 if six else DEMUCS_4
+            inst.run = lambda mix: inst.demixer.demix(mix)
+        else:
+            raise NotImplementedError(
+                f"{model_filename}: the {arch} architecture is outside this engine's scope "
+                "(north star: MDX-Net, BS/Mel-RoFormer, HTDemucs)")
+        self.model_instance = inst
+        self.model_name = os.path.splitext(model_filename)[0]
+        return inst
+
+    # ------------------------------------------------------------------------------------------
+    def _taps(self, up: int, down: int) -> torch.Tensor:
+        key = (up, down)
+        if key not in self._resample_taps:
+            self._resample_taps[key] = torch.from_numpy(sp.resample_taps(up, down)).to(self.torch_device)
+        return self._resample_taps[key]
+
+    def prepare_mix(self, audio: torch.Tensor, sr: int) -> torch.Tensor:
+        """[channels, n] at `sr` -> stereo fp32 device tensor at self.sample_rate (K3 polyphase resampler)."""
+        x = audio.to(self.torch_device, dtype=torch.float32, non_blocking=True)
+        if x.dim() == 1:
+            x = x[None]
+        if x.shape[0] == 1:
+            x = x.repeat(2, 1)
+        x = x[:2].contiguous()
+        if sr != self.sample_rate:
+            g = int(np.gcd(self.sample_rate, sr))
+            up, down = self.sample_rate // g, sr // g
+            x = sp.resample_poly(x, up, down, taps=self._taps(up, down))
+        return x
+
+    @torch.no_grad()
+    def separate_tensor(self, mix: torch.Tensor, sr: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """In-memory fast path: mix [2, n] -> {stem name: [2, n]} on the device."""
+        if self.model_instance is None:
+            raise RuntimeError("load_model() first")
+        inst = self.model_instance
+        mix = self.prepare_mix(mix, sr or self.sample_rate)
+        stems = inst.run(mix)                                  # [S, 2, n]
+        out = {name: stems[i] for i, name in enumerate(inst.stem_names)}
+        if len(inst.stem_names) == 1:
+            out[inst.secondary_stem] = sp.sub(mix, stems[0])   # `mix - primary`
+        return out
+
+    def separate(self, audio_file_path: str) -> List[str]:
+        """WAV in -> WAV stems in output_dir; returns file names relative to output_dir
+        (stem_separator.py:281-282)."""
+        if self.model_instance is None:
+            raise RuntimeError("load_model() first")
+        audio, sr = read_wav(audio_file_path)
+        x = torch.from_numpy(audio)
+        peak = float(x.abs().max()) if x.numel() else 0.0
+        if peak > self.normalization_threshold:                # upstream spec_utils.normalize
+            x = x * (self.normalization_threshold / peak)
+        stems = self.separate_tensor(x, sr)
+        base = os.path.splitext(os.path.basename(audio_file_path))[0]
+        out_dir = self.model_instance.output_dir or self.output_dir
+        os.makedirs(out_dir, exist_ok=True)
+        names = []
+        for stem, wav in stems.items():
+            fname = f"{base}_({stem})_{self.model_name}.wav"
+            write_wav(os.path.join(out_dir, fname), wav.cpu().numpy(), self.sample_rate, subtype="FLOAT")
+            names.append(fname)
+        return names

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-FRAME_MAJOR, BIN_MAJOR, CAC = 0, 1, 2
+FRAME_MAJOR, BIN_MAJOR, CAC, FRAME_INTERLEAVED = 0, 1, 2, 3
 
 
 def _stream() -> int:
@@ -63,6 +63,8 @@ class StftPlan:
             return (n_chunks * channels, n_frames, n_bins_out), torch.complex64
         if layout == BIN_MAJOR:
             return (n_chunks * channels, n_bins_out, n_frames), torch.complex64
+        if layout == FRAME_INTERLEAVED:
+            return (n_chunks, n_frames, n_bins_out, channels), torch.complex64
         return (n_chunks, channels * 2, n_bins_out, n_frames), torch.float32
 
     def stft(self, track: torch.Tensor, *, chunk_len: int, n_chunks: int = 1,
@@ -115,6 +117,8 @@ class StftPlan:
                 raise ValueError("complex layouts need complex64")
             if layout == FRAME_MAJOR:
                 n_frames_in, n_bins_in = spec.shape[-2], spec.shape[-1]
+            elif layout == FRAME_INTERLEAVED:
+                n_frames_in, n_bins_in = spec.shape[-3], spec.shape[-2]
             else:
                 n_bins_in, n_frames_in = spec.shape[-2], spec.shape[-1]
         rows_spec = n_chunks * channels * (stems if spec_has_stems else 1)
@@ -151,12 +155,14 @@ def ola_gather(chunks: torch.Tensor, offsets: torch.Tensor, n_total: int, *,
                mult: Optional[torch.Tensor] = None, wtab: Optional[torch.Tensor] = None,
                tab_id: Optional[torch.Tensor] = None, p0: int = 0, p1: Optional[int] = None,
                halo_in: Optional[torch.Tensor] = None, raw_out: bool = False, eps: float = 1e-10,
+               data_chunk0: int = 0,
                scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """chunks [n_chunks, rows, chunk_len] -> track [rows, n_total] (positions [p0, p1) written)."""
+    """chunks [n_chunks - data_chunk0, rows, chunk_len] -> track [rows, n_total] (positions [p0, p1) written)."""
     _need_cuda(chunks, offsets, mult, wtab, tab_id, halo_in, out)
     if chunks.dtype != torch.float32 or chunks.dim() != 3 or not chunks.is_contiguous():
         raise ValueError("chunks must be contiguous fp32 [n_chunks, rows, chunk_len]")
-    n_chunks, rows, chunk_len = chunks.shape
+    n_data, rows, chunk_len = chunks.shape
+    n_chunks = n_data + int(data_chunk0)
     p1 = n_total if p1 is None else int(p1)
     if offsets.dtype != torch.int64 or offsets.numel() != n_chunks:
         raise ValueError("offsets must be int64 [n_chunks]")
@@ -169,14 +175,19 @@ def ola_gather(chunks: torch.Tensor, offsets: torch.Tensor, n_total: int, *,
     if halo_in is not None and (halo_in.dtype != torch.float32 or halo_in.numel() != rows * (p1 - p0)
                                 or not halo_in.is_contiguous()):
         raise ValueError("halo_in must be contiguous fp32 [rows, p1-p0]")
+    shift = 0
+    if out is not None and hasattr(out, "buf"):          # sharding._ShiftedOut: [rows, p1-p0] window of the track
+        shift, out = int(out.shift), out.buf
+        if out.shape[1] < p1 - shift:
+            raise ValueError("shifted out buffer too small")
     if out is None:
         out = torch.zeros((rows, n_total), dtype=torch.float32, device=chunks.device)
     elif out.dtype != torch.float32 or out.dim() != 2 or out.shape[0] != rows or out.stride(1) != 1:
         raise ValueError("out must be fp32 [rows, >= p1]")
-    _lib.check(_lib.lib().al_ola_gather(chunks.data_ptr(), n_chunks, rows, chunk_len, offsets.data_ptr(),
+    _lib.check(_lib.lib().al_ola_gather(chunks.data_ptr(), n_chunks, int(data_chunk0), rows, chunk_len, offsets.data_ptr(),
                                         _ptr(mult), _ptr(wtab), _ptr(tab_id), int(n_total), int(p0), p1,
                                         _ptr(halo_in), int(bool(raw_out)), float(eps), float(scale),
-                                        out.data_ptr(), out.stride(0), _stream()), "al_ola_gather")
+                                        out.data_ptr() - 4 * shift, out.stride(0), _stream()), "al_ola_gather")
     return out
 
 

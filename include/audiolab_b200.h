@@ -21,6 +21,9 @@
  *       AL_LAYOUT_BIN_MAJOR   1   complex64 [rows, Fo, T]          == torch.stft(return_complex=True)
  *       AL_LAYOUT_CAC         2   float32   [chunks, channels*2, Fo, T]   "complex as channels",
  *                                 channel order (L.re, L.im, R.re, R.im)  == mdxnet.py:51-56
+ *       AL_LAYOUT_FRAME_INTERLEAVED 3 complex64 [groups, T, Fo, channels]  (group = chunk, or
+ *                                 chunk*stems + stem) == upstream BSRoformer 'b t (f s c)': the band-split
+ *                                 input and the mask-estimator output with no permute copy
  */
 #ifndef AUDIOLAB_B200_H_
 #define AUDIOLAB_B200_H_
@@ -39,6 +42,7 @@ extern "C" {
 #define AL_LAYOUT_FRAME_MAJOR 0
 #define AL_LAYOUT_BIN_MAJOR 1
 #define AL_LAYOUT_CAC 2
+#define AL_LAYOUT_FRAME_INTERLEAVED 3
 
 typedef struct al_plan al_plan;
 
@@ -94,7 +98,7 @@ int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch
  * spec          `layout`, T = n_frames_in, Fo = n_bins_in, rows = chunk*channels + ch; bins >= n_bins_in
  *               are zero (mdxnet.py:34-36,59-64 freq_pad).  When spec_has_stems != 0 the spectrogram
  *               carries the stem axis itself: rows = (chunk*stems + stem)*channels + ch (HTDemucs).
- * mask          NULL, or complex64 FRAME_MAJOR/BIN_MAJOR (same `layout`) with rows
+ * mask          NULL, or complex64 in the same complex `layout` (0, 1 or 3) with rows
  *               (chunk*stems + stem)*channels + ch: out = istft(spec * mask) (complex multiply).
  * frame_pad     zero frames virtually added before and after (HTDemucs._ispec pads 2): frame index
  *               t of the padded sequence reads spec frame t - frame_pad.
@@ -123,7 +127,9 @@ int al_istft(const al_plan* plan, const float* spec, const float* mask, int layo
  *   A.1-A.3; stem_separator.py never sees it because it happens inside `separator.separate`,
  *   modules/separator/stem_separator.py:281).
  *
- * chunks        [n_chunks, rows, chunk_len] fp32 dense chunk waves (al_istft dense output).
+ * chunks        [n_chunks - data_chunk0, rows, chunk_len] fp32 dense chunk waves (al_istft dense output)
+ *               of chunks data_chunk0 .. n_chunks-1.  Chunks before data_chunk0 are weight-only: they belong
+ *               to the left neighbour rank, whose partial sums arrive in halo_in.
  * offsets       device int64 [n_chunks], ascending; len_c = min(chunk_len, n_total - off_c).
  * mult          device int32 [n_chunks] or NULL (all 1): tail-aligned chunks the reference evaluates
  *               several times.
@@ -134,7 +140,7 @@ int al_istft(const al_plan* plan, const float* spec, const float* mask, int layo
  *               received from the left neighbour; when raw_out != 0 the un-normalised running sum
  *               is written instead (the partial sums a rank sends to its right neighbour).
  */
-int al_ola_gather(const float* chunks, int n_chunks, int rows, int chunk_len, const int64_t* offsets,
+int al_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len, const int64_t* offsets,
                   const int32_t* mult, const float* wtab, const int32_t* tab_id, int64_t n_total,
                   int64_t p0, int64_t p1, const float* halo_in, int raw_out, float eps, float scale,
                   float* track, int64_t track_stride, void* stream);

@@ -203,11 +203,9 @@ def test_ola_gather_matches_numpy_and_is_bitwise_shardable(cuda):
                          mult=d(mult[:k], torch.int32), wtab=args["wtab"])
     halo = sp.ola_gather(d(chunks[:k], torch.float32), d(offs[:k], torch.int64), n, p0=cut, p1=n, raw_out=True,
                          mult=d(mult[:k], torch.int32), wtab=args["wtab"])[:, cut:].contiguous()
-    # the right rank needs the weight sums of the left chunks too: they are analytic, so it passes
-    # zero-valued stand-ins for the left chunks?  No -- it recomputes: give it ALL offsets but only its data.
-    # (host logic in audiolab_b200.sharding does exactly this; here we check the arithmetic.)
-    full_right = sp.ola_gather(d(np.concatenate([np.zeros_like(chunks[:k]), chunks[k:]]), torch.float32),
-                               d(offs, torch.int64), n, p0=cut, p1=n, halo_in=halo, **args)
+    # the right rank counts the left chunks' weights (all offsets) but holds only its own chunk data
+    full_right = sp.ola_gather(d(chunks[k:], torch.float32), d(offs, torch.int64), n, p0=cut, p1=n,
+                               halo_in=halo, data_chunk0=k, **args)
     stitched = torch.cat([left[:, :cut], full_right[:, cut:]], dim=1)
     assert torch.equal(stitched, got)
 
