@@ -192,8 +192,11 @@ def roformer_schedule(n: int, chunk: int, step: int) -> Tuple[List[int], List[in
             offs.append(i)
             mult.append(1)
     if tail:
-        offs.append(n - chunk)
-        mult.append(tail)
+        if offs and offs[-1] == n - chunk:      # the tail coincides with the last regular chunk
+            mult[-1] += tail
+        else:
+            offs.append(n - chunk)
+            mult.append(tail)
     return offs, mult
 
 

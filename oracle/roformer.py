@@ -402,7 +402,10 @@ def chunk_schedule(n: int, chunk: int, step: int) -> List[Tuple[int, int]]:
         else:
             sched.append((i, 1))
     if tail:
-        sched.append((n - chunk, tail))
+        if sched and sched[-1][0] == n - chunk:
+            sched[-1] = (n - chunk, sched[-1][1] + tail)
+        else:
+            sched.append((n - chunk, tail))
     return sched
 
 
