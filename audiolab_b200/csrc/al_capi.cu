@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -46,6 +47,7 @@ struct al_plan {
     float* d_win_raw = nullptr;   // window as given (for the OLA envelope)
     float2* d_tw = nullptr;       // [32*32]
     float2* d_ctw = nullptr;      // [(D-1)*513]
+    float2* d_ctw_half = nullptr; // n_fft 2048 only: [544] 0.5 * exp(-2 pi i k / 2048) (packed stereo fast path)
     std::mutex mu;
     std::map<int, float*> env;    // n_frames_total -> inv_env table
 };
@@ -103,6 +105,14 @@ int al_plan_create(int n_fft, int hop, const float* window_host, int normalized,
     AL_UP(p->d_win_raw, raw.data(), N * sizeof(float));
     AL_UP(p->d_tw, tw.data(), tw.size() * sizeof(float2));
     AL_UP(p->d_ctw, ctw.data(), ctw.size() * sizeof(float2));
+    if (D == 2) {
+        std::vector<float2> half(544, make_float2(0.f, 0.f));
+        for (int k = 0; k <= 512; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)N;
+            half[k] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
+        }
+        AL_UP(p->d_ctw_half, half.data(), half.size() * sizeof(float2));
+    }
 #undef AL_UP
     *out = p;
     return AL_OK;
@@ -115,6 +125,7 @@ int al_plan_destroy(al_plan* p) {
     cudaFree(p->d_win_raw);
     cudaFree(p->d_tw);
     cudaFree(p->d_ctw);
+    cudaFree(p->d_ctw_half);
     for (auto& kv : p->env) cudaFree(kv.second);
     delete p;
     return AL_OK;
@@ -138,6 +149,33 @@ int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch
     if (last > 2LL * (chunk_len - 1))
         return fail(AL_E_ARG, "al_stft: frames reach %lld, beyond a single reflection of chunk_len %d", last, chunk_len);
     if ((reinterpret_cast<uintptr_t>(spec) & 7) != 0) return fail(AL_E_ARG, "al_stft: spec must be 8-byte aligned");
+    static const bool force_generic = getenv("AL_FORCE_GENERIC") != nullptr;
+    if (!force_generic && plan->D == 2 && channels == 2 && (layout == 0 || layout == 3) &&
+        (layout == 0 || (reinterpret_cast<uintptr_t>(spec) & 15) == 0)) {
+        al::StftPkParams q{};
+        q.track = track;
+        q.n_valid = n_valid;
+        q.ch_stride = ch_stride;
+        q.chunk_offsets = reinterpret_cast<const long long*>(chunk_offsets);
+        q.off0 = off0;
+        q.off_step = off_step;
+        q.n_chunks = n_chunks;
+        q.chunk_len = chunk_len;
+        q.center = center_pad;
+        q.hop = plan->hop;
+        q.n_frames = n_frames;
+        q.window = plan->d_win_a;
+        q.tw = plan->d_tw;
+        q.ctw_half = plan->d_ctw_half;
+        q.spec = spec;
+        q.layout = layout;
+        q.n_bins_out = n_bins_out;
+        q.zero_low_bins = zero_low_bins;
+        q.aligned = ((reinterpret_cast<uintptr_t>(track) & 15) == 0 && (ch_stride & 3) == 0) ? 1 : 0;
+        cudaError_t e = al::launch_stft_pk(q, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "al_stft (packed stereo path)");
+        return AL_OK;
+    }
     al::StftParams p{};
     p.track = track;
     p.n_valid = n_valid;

@@ -1,0 +1,118 @@
+// Channel-packed warp FFT building blocks for the stereo fast-path STFT / iSTFT kernels (sm_100a).
+//
+// Every value is a float2 = (left, right) sample of the SAME FFT element, so each FADD2 / FMUL2 /
+// FFMA2 advances both channels' transforms and twiddles / window values are scalar broadcast
+// operands.  One warp owns one 1024-point complex FFT per channel (element 32*r + lane in register r):
+// two in-register radix-32 butterflies around one shared-memory transposition, done as two half
+// passes (re, then im) through an 8.25 KB per-warp scratch.
+//
+// Also here: the mbarrier helpers of the producer / consumer stage ring.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft32p_gen.cuh"
+
+namespace al {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+constexpr int kScrF2 = 33 * 32;   // float2 per warp scratch: [32][33] transposition tile
+
+// (re, im) *= (w.x + i w.y), or its conjugate when CONJ
+template <bool CONJ>
+__device__ __forceinline__ void pcmul(float2& re, float2& im, float2 w) {
+    const float s = CONJ ? -w.y : w.y;
+    const float2 r = pfma(im, -s, pscale(re, w.x));
+    const float2 i = pfma(im, w.x, pscale(re, s));
+    re = r;
+    im = i;
+}
+
+// in : re/im[r] = z[32*r + lane];  out: re/im[r] = Z[32*r + lane],
+// Z[k] = sum_n z[n] exp(-+2 pi i n k / 1024) (unnormalised).  tw[k1*32 + n2] = exp(-2 pi i k1 n2 / 1024).
+template <bool INV>
+__device__ __forceinline__ void warp_fft1024p(float2 (&re)[32], float2 (&im)[32], float2* scr,
+                                              const float2* tw, int lane) {
+    if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) pcmul<INV>(re[k1], im[k1], tw[k1 * 32 + lane]);
+    float2* wr = scr + lane * 33;
+    const float2* rd = scr + lane;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) wr[k1] = re[k1];
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) re[n2] = rd[n2 * 33];
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) wr[k1] = im[k1];
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) im[n2] = rd[n2 * 33];
+    __syncwarp();
+    if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+}
+
+// Same transform with a single transposition pass through a 16-byte-element scratch
+// (float4 = (re.L, re.R, im.L, im.R), [32][33] float4 = 16.5 KB per warp): half the LDS/STS
+// instructions and two warp barriers instead of four.
+constexpr int kScrF4 = 33 * 32;
+template <bool INV>
+__device__ __forceinline__ void warp_fft1024p_wide(float2 (&re)[32], float2 (&im)[32], float4* scr,
+                                                   const float2* tw, int lane) {
+    if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+    float4* wr = scr + lane * 33;
+    const float4* rd = scr + lane;
+    wr[0] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) {
+        pcmul<INV>(re[k1], im[k1], tw[k1 * 32 + lane]);
+        wr[k1] = make_float4(re[k1].x, re[k1].y, im[k1].x, im[k1].y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+        const float4 v = rd[n2 * 33];
+        re[n2] = make_float2(v.x, v.y);
+        im[n2] = make_float2(v.z, v.w);
+    }
+    __syncwarp();
+    if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+}
+
+// ---- bulk asynchronous shared -> global store (TMA engine, no tensor map) ------------------------
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier helpers (shared::cta) ----------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+}  // namespace al

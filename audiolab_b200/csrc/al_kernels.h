@@ -62,7 +62,36 @@ struct IstftParams {
     int segs;
 };
 
+// stereo / n_fft 2048 / bin-innermost fast path (al_stft_pk.cu)
+struct StftPkParams {
+    const float* track;
+    long long n_valid;
+    long long ch_stride;
+    const long long* chunk_offsets;
+    long long off0, off_step;
+    int n_chunks;
+    int chunk_len;
+    int center;
+    int hop;
+    int n_frames;
+    const float* window;      // [2048] analysis window (already scaled)
+    const float2* tw;         // [32*32]
+    const float2* ctw_half;   // [544] 0.5 * exp(-2 pi i k / 2048), zero padded beyond 512
+    float* spec;
+    int layout;               // 0 or 3
+    int n_bins_out;
+    int zero_low_bins;
+    int aligned;              // track and ch_stride allow 128-bit loads
+    // filled by the launcher
+    int sp;
+    int n_stages;
+    int tiles_per_chunk;
+    int total_tiles;
+    long long* prof;          // AL_PK_PROF builds only: per-warp phase cycle counters
+};
+
 cudaError_t launch_stft(const StftParams& p, int n_fft, int rows, cudaStream_t stream);
+cudaError_t launch_stft_pk(const StftPkParams& p, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_fft, int n_chunks, cudaStream_t stream);
 
 cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,

@@ -31,18 +31,25 @@ def hbm_peak() -> float:
     return 6650.0
 
 
+REPS = 8   # launches per event pair: a lone ~50 us kernel would otherwise be timed together with the ~20 us the
+           # host needs to enqueue it after the start event (the GPU sits idle in between)
+
+
 def time_it(fn, iters, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    reps = 1 if iters == 1 else REPS
     ms = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()                      # keeps the queue non-empty when the start event is reached
         e0.record()
-        fn()
+        for _ in range(reps):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ms.append(e0.elapsed_time(e1))
+        ms.append(e0.elapsed_time(e1) / reps)
     return ms
 
 
