@@ -38,10 +38,12 @@ SIGNATURES = {
     "al_resample_poly": (C.c_int, [c_f32p, c_i64, c_f32p, c_i64, C.c_int, c_i64, c_i64, C.c_int, C.c_int, c_f32p,
                                    C.c_int, C.c_void_p]),
     "al_sub": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64, C.c_void_p]),
-    "al_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                               C.c_int, C.c_void_p]),
+    "al_rmsnorm_bf16": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, c_i64, C.c_int, C.c_float, C.c_float,
+                                  C.c_void_p]),
+    "al_rotary_bf16": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_int, C.c_int, c_i64, C.c_int, C.c_void_p]),
+    "al_gate_sigmoid_bf16": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_int, C.c_int, C.c_void_p]),
 }
-OPTIONAL = {"al_gemm_bf16"}
+OPTIONAL = set()
 
 
 def lib() -> C.CDLL:

@@ -47,6 +47,7 @@ struct al_plan {
     float* d_win_raw = nullptr;   // window as given (for the OLA envelope)
     float2* d_tw = nullptr;       // [32*32]
     float2* d_ctw = nullptr;      // [(D-1)*513]
+    float2* d_ctw_full = nullptr; // n_fft 2048 only: [1024] exp(-2 pi i k / 2048) (packed stereo fast path of K2)
     float2* d_ctw_half = nullptr; // n_fft 2048 only: [544] 0.5 * exp(-2 pi i k / 2048) (packed stereo fast path)
     std::mutex mu;
     std::map<int, float*> env;    // n_frames_total -> inv_env table
@@ -112,6 +113,12 @@ int al_plan_create(int n_fft, int hop, const float* window_host, int normalized,
             half[k] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
         }
         AL_UP(p->d_ctw_half, half.data(), half.size() * sizeof(float2));
+        std::vector<float2> full(1024);
+        for (int k = 0; k < 1024; ++k) {
+            const double a = -2.0 * kPi * (double)k / (double)N;
+            full[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        AL_UP(p->d_ctw_full, full.data(), full.size() * sizeof(float2));
     }
 #undef AL_UP
     *out = p;
@@ -126,6 +133,7 @@ int al_plan_destroy(al_plan* p) {
     cudaFree(p->d_tw);
     cudaFree(p->d_ctw);
     cudaFree(p->d_ctw_half);
+    cudaFree(p->d_ctw_full);
     for (auto& kv : p->env) cudaFree(kv.second);
     delete p;
     return AL_OK;
@@ -238,6 +246,34 @@ int al_istft(const al_plan* plan_c, const float* spec, const float* mask, int la
     const float* inv_env = nullptr;
     int rc = get_env(plan, T, (cudaStream_t)stream, &inv_env);
     if (rc != AL_OK) return rc;
+    static const bool force_generic = getenv("AL_FORCE_GENERIC") != nullptr;
+    if (!force_generic && plan->D == 2 && channels == 2 && layout == 3 && n_bins_in == 1025 && zero_low_bins == 0 &&
+        frame_pad == 0 && (reinterpret_cast<uintptr_t>(spec) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+        al::IstftPkParams q{};
+        q.spec = reinterpret_cast<const float4*>(spec);
+        q.mask = reinterpret_cast<const float4*>(mask);
+        q.n_frames = n_frames_in;
+        q.stems = stems;
+        q.spec_has_stems = spec_has_stems;
+        q.hop = plan->hop;
+        q.window = plan->d_win_s;
+        q.tw = plan->d_tw;
+        q.ctw = plan->d_ctw_full;
+        q.inv_env = inv_env;
+        q.out_start = out_start;
+        q.out_len = out_len;
+        q.weight = weight;
+        q.dst = dst;
+        q.dst_ch_stride = dst_ch_stride;
+        q.dst_chunk_stride = dst_chunk_stride;
+        q.dst_offsets = reinterpret_cast<const long long*>(dst_offsets);
+        q.dst_off0 = dst_off0;
+        q.dst_off_step = dst_off_step;
+        q.dst_limit = dst_limit;
+        cudaError_t e = al::launch_istft_pk(q, n_chunks, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "al_istft (packed stereo path)");
+        return AL_OK;
+    }
     al::IstftParams p{};
     p.spec = spec;
     p.mask = mask;
@@ -303,6 +339,44 @@ int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream) 
     if (!a || !b || !out) return fail(AL_E_ARG, "al_sub: NULL argument");
     cudaError_t e = al::launch_sub(a, b, out, n, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_sub");
+    return AL_OK;
+}
+
+int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, int64_t n_rows, int dim, float scale,
+                    float eps, void* stream) {
+    if (!x || !gamma || !out) return fail(AL_E_ARG, "al_rmsnorm_bf16: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || dim <= 0 || (dim & 7) != 0 || dim > 2048)
+        return fail(AL_E_ARG, "al_rmsnorm_bf16: dim %d must be a multiple of 8, <= 2048", dim);
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gamma) |
+          reinterpret_cast<uintptr_t>(bias)) & 15) != 0)
+        return fail(AL_E_ARG, "al_rmsnorm_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = al::launch_rmsnorm_bf16(x, gamma, bias, out, n_rows, dim, scale, eps, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_rmsnorm_bf16");
+    return AL_OK;
+}
+
+int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int heads, int dim_head, int64_t pos_div,
+                   int pos_mod, void* stream) {
+    if (!q || !k || !cos_sin) return fail(AL_E_ARG, "al_rotary_bf16: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0 || pos_div <= 0 || pos_mod <= 0)
+        return fail(AL_E_ARG, "al_rotary_bf16: bad sizes (dim_head must be a multiple of 8)");
+    if (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(cos_sin)) & 15) != 0)
+        return fail(AL_E_ARG, "al_rotary_bf16: pointers must be 16-byte aligned");
+    cudaError_t e = al::launch_rotary_bf16(q, k, cos_sin, n_rows, heads, dim_head, pos_div, pos_mod, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_rotary_bf16");
+    return AL_OK;
+}
+
+int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream) {
+    if (!o || !gates) return fail(AL_E_ARG, "al_gate_sigmoid_bf16: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0)
+        return fail(AL_E_ARG, "al_gate_sigmoid_bf16: bad sizes (dim_head must be a multiple of 8)");
+    if ((reinterpret_cast<uintptr_t>(o) & 15) != 0) return fail(AL_E_ARG, "al_gate_sigmoid_bf16: o must be 16-byte aligned");
+    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_gate_sigmoid_bf16");
     return AL_OK;
 }
 

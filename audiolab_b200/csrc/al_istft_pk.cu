@@ -1,0 +1,263 @@
+// K2 fast path: stereo, n_fft = 2048, FRAME_INTERLEAVED spectrum (and mask) -- the RoFormer shape.
+// Fused complex mask (.) spec + Hermitian extension + C2R iFFT + synthesis window + overlap-add over
+// frames + / sum(window^2) + centre trim (+ chunk weight, + placement), like istft_kernel<2>
+// (reference: modules/rvc/infer/modules/uvr5/mdxnet.py:58-75; upstream BSRoformer.forward
+// "stft_repr * mask -> torch.istft"), restructured like the K1 fast path:
+//
+//  * both channels ride in one packed-fp32 inverse FFT (al_fftp.cuh): a spectrum / mask element of
+//    layout 3 is one 16-byte (L.re, L.im, R.re, R.im) load;
+//  * one warp owns one frame from the HBM row to the windowed time-domain frame.  The packed
+//    1024-point input  Z[k] = A[k] + i B[k],  A = Y[k] + conj(Y[1024-k]),
+//    B = (Y[k] - conj(Y[1024-k])) conj(W^k)  (Y = mask (.) spec, W = exp(-2 pi i / 2048)) is built
+//    straight from global memory: the lane that owns Z[k] loads Y[k] and Y[1024-k] itself (the two
+//    loads of a register pair (r, 31-r) fall on the same 128-byte lines and are issued back to
+//    back), so there is no shuffle, no lane-0 special case and no spectrum staging in shared memory;
+//  * HBM latency is covered by bulk L2 prefetches (cp.async.bulk.prefetch.L2) of the rows of the next
+//    round, issued before the current round's loads, and by a two-deep register pipeline of loads;
+//  * the windowed frame is parked in the warp's own transposition scratch; after one CTA barrier all
+//    threads gather-sum the round's 8 frames (+ the carry of earlier rounds) in ascending frame
+//    order -- the deterministic order of istft_kernel -- and emit both channels.
+//
+// Algorithmic bytes per frame (both channels): 2 * (1025*8 [+ 1025*8 mask] + hop*4).
+#include "al_fftp.cuh"
+#include "al_kernels.h"
+
+namespace al {
+
+constexpr int kIpWarps = 8;               // frames per round
+constexpr int kIpThreads = kIpWarps * 32;
+constexpr int kIpN = 2048;
+constexpr int kIpBins = 1025;
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
+
+// Y = x * m per channel; returns packed (L, R) real and imaginary parts
+template <bool MASK>
+__device__ __forceinline__ void ip_product(const float4 x, const float4 m, float2& yr, float2& yi) {
+    if (MASK) {
+        yr = make_float2(fmaf(-x.y, m.y, x.x * m.x), fmaf(-x.w, m.w, x.z * m.z));
+        yi = make_float2(fmaf(x.y, m.x, x.x * m.y), fmaf(x.w, m.z, x.z * m.w));
+    } else {
+        yr = make_float2(x.x, x.z);
+        yi = make_float2(x.y, x.w);
+    }
+}
+
+// Z[k] from P = Y[k], Q = Y[1024 - k], w = W^k
+__device__ __forceinline__ void ip_combine(float2 pr, float2 pi, float2 qr, float2 qi, float2 w, float2& zr,
+                                           float2& zi) {
+    const float2 ar = padd(pr, qr), ai = psub(pi, qi);     // A = P + conj(Q)
+    const float2 dr = psub(pr, qr), di = padd(pi, qi);     // D = P - conj(Q)
+    zr = pfma(dr, w.y, pfma(di, -w.x, ar));                 // A.re - Im(D conj(w))
+    zi = pfma(di, w.y, pfma(dr, w.x, ai));                  // A.im + Re(D conj(w))
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(kIpThreads, 1)
+istft_pk2_kernel(const IstftPkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);           // [1024]
+    float2* s_win = s_tw + 1024;                                   // [1024] (w[2k], w[2k+1])
+    float2* s_ctw = s_win + 1024;                                  // [1024] W^k
+    float4* s_scr = reinterpret_cast<float4*>(s_ctw + 1024);       // [kIpWarps][kScrF4]
+    float2* s_carry = reinterpret_cast<float2*>(s_scr + kIpWarps * kScrF4);   // [2][2048 - hop] (L, R)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
+    const int chunk = g / p.stems, stem = g - chunk * p.stems;
+    const int hop = p.hop, T = p.n_frames;
+    const int carry_len = kIpN - hop;
+
+    // owned untrimmed overlap-add positions [Pa, Pb)
+    const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
+    const long long Pend = (long long)p.out_start + p.out_len;
+    const long long Pb = min(Pa + (long long)p.hops_per_cta * hop, Pend);
+    if (Pa >= Pb) return;
+    int ta = (int)((Pa - kIpN) / hop) + 1;              // first frame touching Pa
+    if (Pa < kIpN) ta = 0;
+    ta = max(ta, 0);
+    const int tb = min((int)((Pb - 1) / hop), T - 1);   // last frame touching Pb - 1
+    const int t_last = (int)((Pb - 1) / hop);           // rounds run until the carry is flushed up to Pb
+
+    const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
+    float* __restrict__ dst0 = p.dst + ((long long)stem * 2) * p.dst_ch_stride + (long long)chunk * p.dst_chunk_stride + place;
+    float* __restrict__ dst1 = dst0 + p.dst_ch_stride;
+
+    const float4* __restrict__ X = p.spec + (long long)(p.spec_has_stems ? g : chunk) * T * kIpBins;
+    const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
+
+    if (lane == 0 && ta + warp <= tb) {   // the first round's rows: start them towards L2 right away
+        prefetch_l2_bulk(X + (long long)(ta + warp) * kIpBins, kIpBins * 16);
+        if (MASK) prefetch_l2_bulk(M + (long long)(ta + warp) * kIpBins, kIpBins * 16);
+    }
+    for (int i = tid; i < 1024; i += kIpThreads) {
+        s_tw[i] = p.tw[i];
+        s_win[i] = reinterpret_cast<const float2*>(p.window)[i];
+        s_ctw[i] = p.ctw[i];
+    }
+    for (int i = tid; i < 2 * carry_len; i += kIpThreads) s_carry[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    float4* scr = s_scr + warp * kScrF4;
+    int cbuf = 0;
+    for (int tr = ta; tr <= t_last; tr += kIpWarps, cbuf ^= 1) {
+        const int nf = max(0, min(kIpWarps, tb - tr + 1));   // live frames of this round (CTA-uniform)
+        const int t = tr + warp;
+        const bool live = warp < nf;                          // warp-uniform
+        float2 re[32], im[32];
+        if (live) {
+            if (lane == 0 && t + kIpWarps <= tb) {
+                prefetch_l2_bulk(X + (long long)(t + kIpWarps) * kIpBins, kIpBins * 16);
+                if (MASK) prefetch_l2_bulk(M + (long long)(t + kIpWarps) * kIpBins, kIpBins * 16);
+            }
+            // ---- build Z from the spectrum (and mask) rows: register pairs (r, 31 - r) --------------
+            const float4* __restrict__ xrow = X + (long long)t * kIpBins;
+            const float4* __restrict__ mrow = MASK ? M + (long long)t * kIpBins : nullptr;
+            // pair r: k1 = 32 r + lane (reg r), k2 = 32 (31 - r) + lane (reg 31 - r); mirrors q = 1024 - k
+            float4 bx[2][4], bm[2][4];
+#define IP_ISSUE(r_, b_)                                                         \
+    do {                                                                          \
+        const int k1_ = 32 * (r_) + lane, k2_ = 32 * (31 - (r_)) + lane;          \
+        bx[b_][0] = __ldg(xrow + k1_);                                            \
+        bx[b_][1] = __ldg(xrow + (1024 - k2_));                                   \
+        bx[b_][2] = __ldg(xrow + k2_);                                            \
+        bx[b_][3] = __ldg(xrow + (1024 - k1_));                                   \
+        if (MASK) {                                                               \
+            bm[b_][0] = __ldg(mrow + k1_);                                        \
+            bm[b_][1] = __ldg(mrow + (1024 - k2_));                               \
+            bm[b_][2] = __ldg(mrow + k2_);                                        \
+            bm[b_][3] = __ldg(mrow + (1024 - k1_));                               \
+        }                                                                         \
+    } while (0)
+            IP_ISSUE(0, 0);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int b = r & 1;
+                if (r + 1 < 16) IP_ISSUE(r + 1, b ^ 1);
+                float2 p1r, p1i, q2r, q2i, p2r, p2i, q1r, q1i;
+                ip_product<MASK>(bx[b][0], bm[b][0], p1r, p1i);
+                ip_product<MASK>(bx[b][1], bm[b][1], q2r, q2i);
+                ip_product<MASK>(bx[b][2], bm[b][2], p2r, p2i);
+                ip_product<MASK>(bx[b][3], bm[b][3], q1r, q1i);
+                if (r == 0 && lane == 0) {   // k1 = 0: C2R ignores Im of the DC and Nyquist bins
+                    p1i = make_float2(0.f, 0.f);
+                    q1i = make_float2(0.f, 0.f);
+                }
+                const float2 w1 = s_ctw[32 * r + lane], w2 = s_ctw[32 * (31 - r) + lane];
+                ip_combine(p1r, p1i, q1r, q1i, w1, re[r], im[r]);
+                ip_combine(p2r, p2i, q2r, q2i, w2, re[31 - r], im[31 - r]);
+            }
+#undef IP_ISSUE
+        }
+        __syncthreads();   // the previous round's overlap-add has finished reading the scratches
+        if (live) {
+            warp_fft1024p_wide<true>(re, im, scr, s_tw, lane);
+            // z[k] = (x[2k], x[2k+1]) * n_fft; window (carries 1 / n_fft) and park the frame: scr[k] = samples 2k, 2k+1
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 w = s_win[32 * r + lane];
+                const float2 ev = pscale(re[r], w.x), od = pscale(im[r], w.y);
+                scr[32 * r + lane] = make_float4(ev.x, ev.y, od.x, od.y);
+            }
+        }
+        __syncthreads();   // all frames of the round are parked
+
+        // ---- overlap-add: span [S, S + 8 hop + carry_len), ascending frame order ------------------------
+        const long long S = (long long)tr * hop;
+        const float2* cin = s_carry + cbuf * carry_len;
+        float2* cout = s_carry + (cbuf ^ 1) * carry_len;
+        const int emit = kIpWarps * hop;
+        const int span = emit + carry_len;
+        for (int i = tid; i < span; i += kIpThreads) {
+            float2 acc = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+            int f_lo = (i - kIpN) / hop + 1;
+            if (i < kIpN) f_lo = 0;
+            const int f_hi = min(nf - 1, i / hop);
+            for (int f = f_lo; f <= f_hi; ++f) {
+                const float2 v = reinterpret_cast<const float2*>(s_scr + f * kScrF4)[i - f * hop];
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            if (i < emit) {
+                const long long P = S + i;
+                if (P >= Pa && P < Pb) {
+                    const long long pp = P - p.out_start;
+                    const float e = __ldg(p.inv_env + P);
+                    float v0 = acc.x * e, v1 = acc.y * e;
+                    if (p.weight) {
+                        const float wgt = __ldg(p.weight + pp);
+                        v0 *= wgt;
+                        v1 *= wgt;
+                    }
+                    const long long q = place + pp;
+                    if (q >= 0 && q < p.dst_limit) {
+                        dst0[pp] = v0;
+                        dst1[pp] = v1;
+                    }
+                }
+            } else {
+                cout[i - emit] = acc;
+            }
+        }
+    }
+}
+
+// segments per row: minimise waves * rounds per segment (a round = 8 frames; each segment re-computes the
+// ceil((2048 - hop) / hop) frames that precede its first owned sample)
+static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int* hpc_out, int* segs_out) {
+    const int halo = (kIpN - hop + hop - 1) / hop;
+    long long best = -1;
+    int best_segs = 1;
+    const int max_segs = total_hops / kIpWarps > 1 ? total_hops / kIpWarps : 1;
+    for (int segs = 1; segs <= max_segs; ++segs) {
+        const int hpc = (total_hops + segs - 1) / segs;
+        const int real_segs = (total_hops + hpc - 1) / hpc;
+        const long long waves = ((long long)rows * real_segs + n_sm - 1) / n_sm;
+        const long long rounds = (hpc + halo + kIpWarps - 1) / kIpWarps + 1;
+        const long long cost = waves * rounds;
+        if (best < 0 || cost < best) {
+            best = cost;
+            best_segs = segs;
+        }
+    }
+    const int hpc = (total_hops + best_segs - 1) / best_segs;
+    *hpc_out = hpc;
+    *segs_out = (total_hops + hpc - 1) / hpc;
+}
+
+cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
+    IstftPkParams p = p0;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int rows = n_chunks * p.stems;
+    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
+    ip_tiling(rows, total_hops, p.hop, n_sm, &p.hops_per_cta, &p.segs);
+    const size_t smem = (size_t)3 * 1024 * sizeof(float2) + (size_t)kIpWarps * kScrF4 * sizeof(float4) +
+                        2 * (size_t)(kIpN - p.hop) * sizeof(float2);
+    const size_t cap = 227 * 1024;
+    if (smem > cap) return cudaErrorInvalidValue;
+#define AL_IP_LAUNCH(MSK)                                                                                     \
+    do {                                                                                                      \
+        static bool attr = false;                                                                             \
+        if (!attr) {                                                                                          \
+            cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 (int)cap);                                                   \
+            if (e != cudaSuccess) return e;                                                                   \
+            attr = true;                                                                                      \
+        }                                                                                                     \
+        istft_pk2_kernel<MSK><<<(unsigned)(rows * p.segs), kIpThreads, smem, stream>>>(p);                   \
+    } while (0)
+    if (p.mask) AL_IP_LAUNCH(true); else AL_IP_LAUNCH(false);
+#undef AL_IP_LAUNCH
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace al

@@ -90,7 +90,33 @@ struct StftPkParams {
     long long* prof;          // AL_PK_PROF builds only: per-warp phase cycle counters
 };
 
+// stereo / n_fft 2048 / FRAME_INTERLEAVED fast path of K2 (al_istft_pk.cu)
+struct IstftPkParams {
+    const float4* spec;       // [chunks (* stems)][T][1025] (L.re, L.im, R.re, R.im)
+    const float4* mask;       // [chunks * stems][T][1025] or NULL
+    int n_frames;             // T (no frame padding on this path)
+    int stems;
+    int spec_has_stems;
+    int hop;
+    const float* window;      // [2048] synthesis window * 1/N
+    const float2* tw;         // [32*32]
+    const float2* ctw;        // [1024] exp(-2 pi i k / 2048)
+    const float* inv_env;     // [(T-1)*hop + 2048]
+    int out_start;
+    int out_len;
+    const float* weight;
+    float* dst;
+    long long dst_ch_stride, dst_chunk_stride;
+    const long long* dst_offsets;
+    long long dst_off0, dst_off_step;
+    long long dst_limit;
+    // filled by the launcher
+    int hops_per_cta;
+    int segs;
+};
+
 cudaError_t launch_stft(const StftParams& p, int n_fft, int rows, cudaStream_t stream);
+cudaError_t launch_istft_pk(const IstftPkParams& p, int n_chunks, cudaStream_t stream);
 cudaError_t launch_stft_pk(const StftPkParams& p, cudaStream_t stream);
 cudaError_t launch_istft(const IstftParams& p, int n_fft, int n_chunks, cudaStream_t stream);
 
@@ -105,6 +131,13 @@ cudaError_t launch_resample(const float* in, long long in_stride, float* out, lo
                             const float* taps, int n_taps, cudaStream_t stream);
 
 cudaError_t launch_sub(const float* a, const float* b, float* out, long long n, cudaStream_t stream);
+
+cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, long long n_rows, int dim,
+                                float scale, float eps, cudaStream_t stream);
+cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head,
+                               long long pos_div, int pos_mod, cudaStream_t stream);
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
+                             cudaStream_t stream);
 
 cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
                        cudaStream_t stream);

@@ -1,0 +1,164 @@
+// Fused row-wise operators of the RoFormer mask network's bf16 inference path (sm_100a).
+//
+// The dense contractions of the network go to the tensor cores through cuBLAS / cuDNN (library calls);
+// everything between two contractions is HBM-bound row-wise work that the reference runs as chains
+// of 5-12 elementwise PyTorch kernels under autocast (upstream bs_roformer RMSNorm / rotary /
+// gated attention).  Each chain is ONE kernel here: bf16 in, fp32 arithmetic, bf16
+// out, one 16-byte access per 8 elements.
+//
+//   rmsnorm_bf16  : [x += bias;] out = x / max(||x||_2, eps) * sqrt(dim) * gamma      (4 B / element)
+//   rotary_bf16   : q, k rotated in place by the position of their token                (8 B / element)
+//   gate_bf16     : attention output *= sigmoid(gate of its (token, head)), in place   (4 B / element)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "al_kernels.h"
+
+namespace al {
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+
+// One warp per row; the row stays in registers between the reduction and the scaling pass.
+template <int MAXC>   // chunks of 256 elements held in registers (dim <= 256 * MAXC)
+__global__ void __launch_bounds__(256)
+rmsnorm_bf16_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ bias,
+                    __nv_bfloat16* __restrict__ out, long long n_rows, int dim, float scale, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    uint4* xr = reinterpret_cast<uint4*>(x + row * dim);
+    uint4* orow = reinterpret_cast<uint4*>(out + row * dim);
+    float v[MAXC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int e = c * 256 + lane * 8;
+        if (e < dim) {
+            bf16x8_to_f32(xr[e >> 3], v[c]);
+            if (bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + e));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + e) + 1);
+                v[c][0] += b0.x; v[c][1] += b0.y; v[c][2] += b0.z; v[c][3] += b0.w;
+                v[c][4] += b1.x; v[c][5] += b1.y; v[c][6] += b1.z; v[c][7] += b1.w;
+                const uint4 u = f32_to_bf16x8(v[c]);     // the residual stream is bf16: norm what is stored
+                xr[e >> 3] = u;
+                bf16x8_to_f32(u, v[c]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(v[c][i], v[c][i], ss);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = scale / fmaxf(sqrtf(ss), eps);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int e = c * 256 + lane * 8;
+        if (e < dim) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e) + 1);
+            float r[8];
+            r[0] = v[c][0] * inv * g0.x; r[1] = v[c][1] * inv * g0.y; r[2] = v[c][2] * inv * g0.z; r[3] = v[c][3] * inv * g0.w;
+            r[4] = v[c][4] * inv * g1.x; r[5] = v[c][5] * inv * g1.y; r[6] = v[c][6] * inv * g1.z; r[7] = v[c][7] * inv * g1.w;
+            orow[e >> 3] = f32_to_bf16x8(r);
+        }
+    }
+}
+
+cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, long long n_rows, int dim,
+                                float scale, float eps, cudaStream_t stream) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
+    auto* xb = reinterpret_cast<__nv_bfloat16*>(x);
+    auto* ob = reinterpret_cast<__nv_bfloat16*>(out);
+    if (dim <= 512) rmsnorm_bf16_kernel<2><<<grid, wpb * 32, 0, stream>>>(xb, gamma, bias, ob, n_rows, dim, scale, eps);
+    else if (dim <= 1024) rmsnorm_bf16_kernel<4><<<grid, wpb * 32, 0, stream>>>(xb, gamma, bias, ob, n_rows, dim, scale, eps);
+    else rmsnorm_bf16_kernel<8><<<grid, wpb * 32, 0, stream>>>(xb, gamma, bias, ob, n_rows, dim, scale, eps);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// q, k: [n_rows, heads * dim_head] bf16, rotated in place.  Element pair (2i, 2i+1) of every head turns by
+// the angle pos * freq_i, pos = (row / pos_div) % pos_mod;  cs[pos][i] = (cos, sin).
+__global__ void __launch_bounds__(256)
+rotary_bf16_kernel(uint4* __restrict__ q, uint4* __restrict__ k, const float2* __restrict__ cs, long long n_vec,
+                   int vec_per_row, int dim_head, long long pos_div, int pos_mod) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec) return;
+    const long long row = i / vec_per_row;
+    const int col = (int)(i - row * vec_per_row) * 8;
+    const int pos = (int)((row / pos_div) % pos_mod);
+    const int half = dim_head >> 1;
+    const float4* t = reinterpret_cast<const float4*>(cs + (long long)pos * half + ((col % dim_head) >> 1));
+    const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+    const float c[4] = {t0.x, t0.z, t1.x, t1.z}, s[4] = {t0.y, t0.w, t1.y, t1.w};
+    float a[8], b[8], ra[8], rb[8];
+    bf16x8_to_f32(q[i], a);
+    bf16x8_to_f32(k[i], b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ra[2 * j] = a[2 * j] * c[j] - a[2 * j + 1] * s[j];
+        ra[2 * j + 1] = a[2 * j + 1] * c[j] + a[2 * j] * s[j];
+        rb[2 * j] = b[2 * j] * c[j] - b[2 * j + 1] * s[j];
+        rb[2 * j + 1] = b[2 * j + 1] * c[j] + b[2 * j] * s[j];
+    }
+    q[i] = f32_to_bf16x8(ra);
+    k[i] = f32_to_bf16x8(rb);
+}
+
+cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head,
+                               long long pos_div, int pos_mod, cudaStream_t stream) {
+    const int vec_per_row = heads * dim_head / 8;
+    const long long n_vec = n_rows * vec_per_row;
+    rotary_bf16_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<uint4*>(q), reinterpret_cast<uint4*>(k), reinterpret_cast<const float2*>(cs), n_vec, vec_per_row,
+        dim_head, pos_div, pos_mod);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// o: [n_rows, heads * dim_head] bf16, gates: [n_rows, heads] bf16;  o[row, h, :] *= sigmoid(gates[row, h])
+__global__ void __launch_bounds__(256)
+gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates, long long n_vec, int vec_per_row,
+                 int heads, int dim_head) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vec) return;
+    const long long row = i / vec_per_row;
+    const int h = ((int)(i - row * vec_per_row) * 8) / dim_head;
+    const float g = __bfloat162float(gates[row * heads + h]);
+    const float sg = 1.f / (1.f + __expf(-g));
+    float a[8];
+    bf16x8_to_f32(o[i], a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= sg;
+    o[i] = f32_to_bf16x8(a);
+}
+
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
+                             cudaStream_t stream) {
+    const int vec_per_row = heads * dim_head / 8;
+    const long long n_vec = n_rows * vec_per_row;
+    gate_bf16_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace al

@@ -1,0 +1,60 @@
+"""Host wrappers of the fused row-wise bf16 operators (csrc/al_netops.cu) used by the RoFormer mask
+network's inference path.  CUDA tensors only; every call enqueues on torch's current stream."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_bf16_rows(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != torch.bfloat16 or t.dim() != 2 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous bf16 [rows, cols] tensor")
+
+
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = F.normalize(x, dim=-1) * sqrt(dim) * gamma; with `bias`, x += bias happens (in place) first."""
+    _check_bf16_rows(x, "x")
+    n, d = x.shape
+    if gamma.dtype != torch.float32 or gamma.numel() != d or (bias is not None and
+                                                              (bias.dtype != torch.float32 or bias.numel() != d)):
+        raise ValueError("gamma / bias must be fp32 [dim]")
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _check_bf16_rows(out, "out")
+    _lib.check(_lib.lib().al_rmsnorm_bf16(x.data_ptr(), gamma.data_ptr(), None if bias is None else bias.data_ptr(),
+                                          out.data_ptr(), n, d, float(d) ** 0.5, 1e-12, _stream()), "al_rmsnorm_bf16")
+    return out
+
+
+def rotary_(q: torch.Tensor, k: torch.Tensor, cos_sin: torch.Tensor, heads: int, dim_head: int, pos_div: int,
+            pos_mod: int) -> None:
+    """Rotate q and k [rows, heads*dim_head] in place; row position = (row // pos_div) % pos_mod."""
+    _check_bf16_rows(q, "q")
+    _check_bf16_rows(k, "k")
+    if q.shape != k.shape or q.shape[1] != heads * dim_head:
+        raise ValueError("q, k must be [rows, heads*dim_head]")
+    if cos_sin.dtype != torch.float32 or tuple(cos_sin.shape) != (pos_mod, dim_head // 2, 2) or not cos_sin.is_contiguous():
+        raise ValueError("cos_sin must be contiguous fp32 [pos_mod, dim_head/2, 2]")
+    _lib.check(_lib.lib().al_rotary_bf16(q.data_ptr(), k.data_ptr(), cos_sin.data_ptr(), q.shape[0], heads, dim_head,
+                                         int(pos_div), int(pos_mod), _stream()), "al_rotary_bf16")
+
+
+def gate_sigmoid_(o: torch.Tensor, gates: torch.Tensor, heads: int, dim_head: int) -> None:
+    """o[row, h, :] *= sigmoid(gates[row, h]) in place."""
+    _check_bf16_rows(o, "o")
+    _check_bf16_rows(gates, "gates")
+    if o.shape[1] != heads * dim_head or tuple(gates.shape) != (o.shape[0], heads):
+        raise ValueError("o must be [rows, heads*dim_head] and gates [rows, heads]")
+    _lib.check(_lib.lib().al_gate_sigmoid_bf16(o.data_ptr(), gates.data_ptr(), o.shape[0], heads, dim_head, _stream()),
+               "al_gate_sigmoid_bf16")

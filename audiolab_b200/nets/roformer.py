@@ -210,6 +210,83 @@ class RoformerMaskNet(nn.Module):
             MaskEstimator(c.dim, dims, c.mask_estimator_depth, c.mlp_expansion_factor) for _ in range(c.num_stems)
         ])
         self.compute_dtype = torch.float32
+        self._bf16_cache = {}
+        self._rot_cache = {}
+        self._fused_dtype = torch.bfloat16      # the kernels are bf16-only; tests of the host logic may override
+
+    # ---- bf16 inference path: fused row-wise kernels (csrc/al_netops.cu) between the contractions -------
+    def _bf16(self, p: torch.Tensor) -> torch.Tensor:
+        """bf16 copy of a parameter, made once (autocast re-casts every weight on every call)."""
+        hit = self._bf16_cache.get(id(p))
+        if hit is None or hit[0] != p._version or hit[1].device != p.device:
+            hit = (p._version, p.detach().to(self._fused_dtype).contiguous())
+            self._bf16_cache[id(p)] = hit
+        return hit[1]
+
+    def _cos_sin(self, rot: RotaryEmbedding, n: int, device) -> torch.Tensor:
+        key = (id(rot), n, str(device))
+        hit = self._rot_cache.get(key)
+        if hit is None:
+            pos = torch.arange(n, device=device, dtype=torch.float32)
+            ang = pos[:, None] * rot.freqs.detach().to(device=device, dtype=torch.float32)[None, :]
+            hit = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()      # [n, dim_head/2, 2]
+            self._rot_cache[key] = hit
+        return hit
+
+    def _transformer_fused(self, x2, tr: Transformer, geom, time_axis: bool, pending):
+        """x2 [b*t*f, d] bf16 residual stream (token order b, t, f), updated in place.  `pending` is the
+        output-projection bias of the previous FeedForward, folded into the next RMSNorm kernel."""
+        from .. import netops
+        b, t, f = geom
+        for attn, ff in tr.layers:
+            h, dh = attn.heads, attn.to_qkv.weight.shape[0] // (3 * attn.heads)
+            inner = h * dh
+            xn = netops.rmsnorm(x2, attn.norm.gamma.detach(), pending)
+            pending = None
+            w = self._bf16(attn.to_qkv.weight)
+            q, k, v = F.linear(xn, w[:inner]), F.linear(xn, w[inner:2 * inner]), F.linear(xn, w[2 * inner:])
+            if attn.rotary_embed is not None:
+                if time_axis:
+                    netops.rotary_(q, k, self._cos_sin(attn.rotary_embed, t, x2.device), h, dh, f, t)
+                else:
+                    netops.rotary_(q, k, self._cos_sin(attn.rotary_embed, f, x2.device), h, dh, 1, f)
+            # attention over time: batch b, "heads" (band, head); over bands: batch (b, t).  Strided views of the
+            # token-major buffers -- no transposition copies around the attention.
+            shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
+            o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
+                                               v.view(shape).transpose(1, 2))
+            o = o.transpose(1, 2)
+            if not o.is_contiguous():
+                o = o.contiguous()
+            o2 = o.view(-1, inner)
+            gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
+            netops.gate_sigmoid_(o2, gates, h, dh)
+            x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
+            lin1, lin2 = ff.net[1], ff.net[4]
+            xn = netops.rmsnorm(x2, ff.net[0].gamma.detach())
+            hid = F.gelu(F.linear(xn, self._bf16(lin1.weight), self._bf16(lin1.bias)))
+            x2.addmm_(hid, self._bf16(lin2.weight).t())
+            pending = lin2.bias.detach()
+        if isinstance(tr.norm, RMSNorm):
+            x2 = netops.rmsnorm(x2, tr.norm.gamma.detach(), pending)
+            pending = None
+        return x2, pending
+
+    def _axial_fused(self, x):
+        """bf16 twin of `_axial` (+ BS-RoFormer's final norm): same parameters, same arithmetic order, fp32 inside
+        each fused kernel."""
+        from .. import netops
+        b, t, f, d = x.shape
+        x2 = x.to(self._fused_dtype).contiguous().view(-1, d)
+        pending = None
+        for time_transformer, freq_transformer in self.layers:
+            x2, pending = self._transformer_fused(x2, time_transformer, (b, t, f), True, pending)
+            x2, pending = self._transformer_fused(x2, freq_transformer, (b, t, f), False, pending)
+        if self.cfg.kind != "mel":
+            x2 = netops.rmsnorm(x2, self.final_norm.gamma.detach(), pending)
+        elif pending is not None:
+            x2 = x2 + pending.to(x2.dtype)
+        return x2.view(b, t, f, d)
 
     def set_compute_dtype(self, dtype: torch.dtype) -> "RoformerMaskNet":
         self.compute_dtype = dtype
@@ -236,9 +313,13 @@ class RoformerMaskNet(nn.Module):
             else:
                 x = feats
             x = self.band_split(x)
-            x = self._axial(x)
-            if c.kind != "mel":
-                x = self.final_norm(x)
+            if ac and x.is_cuda and self.compute_dtype == torch.bfloat16:
+                with torch.autocast("cuda", enabled=False):
+                    x = self._axial_fused(x)
+            else:
+                x = self._axial(x)
+                if c.kind != "mel":
+                    x = self.final_norm(x)
             m = torch.stack([fn(x) for fn in self.mask_estimators], dim=1)  # b n t (f' s c)
         n = m.shape[1]
         m = m.float()

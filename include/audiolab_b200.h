@@ -164,6 +164,27 @@ int al_resample_poly(const float* in, int64_t in_stride, float* out, int64_t out
  */
 int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream);
 
+/*
+ * Row-wise operators of the RoFormer mask network's bf16 inference path.  Each replaces a chain of
+ * elementwise PyTorch kernels that upstream bs_roformer / mel_band_roformer run between two dense
+ * contractions (driven by MDXCSeparator.demix, reference call site
+ * modules/separator/stem_separator.py:281).  All tensors are DEVICE bf16, row-major, 16-byte aligned.
+ *
+ * al_rmsnorm_bf16 -- upstream RMSNorm.forward: F.normalize(x, dim=-1) * sqrt(dim) * gamma.
+ *   x [n_rows, dim]; if bias != NULL, x += bias is applied (and stored) first -- the deferred bias
+ *   of the previous FeedForward's output projection.  out may alias x.  scale = sqrt(dim), eps 1e-12.
+ * al_rotary_bf16 -- upstream rotary_embed.rotate_queries_or_keys on q and k, in place.
+ *   q, k [n_rows, heads*dim_head]; cos_sin [pos_mod, dim_head/2, 2] fp32; the position of a row is
+ *   (row / pos_div) % pos_mod (rows are tokens of a [batch, time, band] grid).
+ * al_gate_sigmoid_bf16 -- upstream Attention: out * to_gates(x).sigmoid(), in place.
+ *   o [n_rows, heads*dim_head], gates [n_rows, heads].
+ */
+int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, int64_t n_rows, int dim, float scale,
+                    float eps, void* stream);
+int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int heads, int dim_head, int64_t pos_div,
+                   int pos_mod, void* stream);
+int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

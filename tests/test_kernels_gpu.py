@@ -143,6 +143,63 @@ def test_istft_fused_complex_mask_and_stems(cuda):
     assert torch.equal(got, got_fm)
 
 
+@pytest.mark.parametrize("hop,T,stems,use_mask", [(441, 301, 2, True), (441, 61, 1, False), (512, 130, 1, True),
+                                                  (300, 97, 3, True)])
+def test_istft_frame_interleaved_packed_path_matches_torch(cuda, hop, T, stems, use_mask):
+    """Layout 3 (RoFormer 'b t (f c)'), stereo, n_fft 2048 -> the packed fast path of K2 (al_istft_pk.cu).
+    Arbitrary spectrum incl. Im(DC) / Im(Nyquist) != 0, fused mask, stems, ragged out_len, several segments."""
+    from audiolab_b200 import spectral as sp
+    n_fft, F, nch = 2048, 1025, 2
+    L = (T - 1) * hop - 37                                                       # out_len not a multiple of hop
+    X = torch.view_as_complex(torch.tensor(synth_noise((nch, 2, F, T, 2), seed=hop + T)))        # [c, ch, F, T]
+    if use_mask:
+        M = torch.view_as_complex(torch.tensor(synth_noise((nch, stems, 2, F, T, 2), seed=T)))   # [c, s, ch, F, T]
+        Y = X[:, None] * M
+    else:
+        stems, M = 1, None
+        Y = X[:, None]
+    ref = torch.istft(Y.reshape(-1, F, T), n_fft, hop, window=torch.hann_window(n_fft), center=True, length=L)
+    ref = ref.reshape(nch, stems, 2, L)
+    plan = _plan(n_fft, hop)
+    Xi = X.permute(0, 3, 2, 1).contiguous().to(cuda)                             # [c, T, F, ch]
+    Mi = None if M is None else M.permute(0, 1, 4, 3, 2).contiguous().to(cuda)   # [c, s, T, F, ch]
+    got = plan.istft(Xi, mask=Mi, n_chunks=nch, channels=2, stems=stems, layout=sp.FRAME_INTERLEAVED, out_len=L)
+    tol = WAVE_ATOL * max(1.0, float(ref.abs().max()))
+    assert max_abs_err(got.cpu(), ref) <= tol
+    # tiling independence: one chunk alone is segmented differently, yet must give the same bits
+    one = plan.istft(Xi[:1].contiguous(), mask=None if Mi is None else Mi[:1].contiguous(), n_chunks=1, channels=2,
+                     stems=stems, layout=sp.FRAME_INTERLEAVED, out_len=L)
+    assert torch.equal(one[0], got[0])
+    # the generic kernel (bin-major layout) agrees within rounding
+    gen = plan.istft(X.reshape(-1, F, T).contiguous().to(cuda),
+                     mask=None if M is None else M.reshape(-1, F, T).contiguous().to(cuda),
+                     n_chunks=nch, channels=2, stems=stems, layout=sp.BIN_MAJOR, out_len=L)
+    assert max_abs_err(got.cpu(), gen.cpu()) <= tol
+
+
+def test_istft_frame_interleaved_weight_and_placement(cuda):
+    """Packed K2 path with the chunk weight, per-chunk placement into a track and the dst_limit clip."""
+    from audiolab_b200 import spectral as sp
+    n_fft, hop, T, F, nch = 2048, 441, 41, 1025, 3
+    L = (T - 1) * hop
+    X = torch.view_as_complex(torch.tensor(synth_noise((nch, 2, F, T, 2), seed=77)))
+    ref = torch.istft(X.reshape(-1, F, T), n_fft, hop, window=torch.hann_window(n_fft), center=True, length=L)
+    ref = ref.reshape(nch, 2, L)
+    w = torch.tensor(synth_noise((L,), seed=5)).abs() + 0.1
+    plan = _plan(n_fft, hop)
+    n_track = 3 * L - 200
+    track = torch.zeros((2, n_track), device=cuda)
+    offs = torch.tensor([0, L + 100, 2 * L + 300], dtype=torch.int64, device=cuda)  # last chunk clipped by dst_limit
+    plan.istft(X.permute(0, 3, 2, 1).contiguous().to(cuda), n_chunks=nch, channels=2, layout=sp.FRAME_INTERLEAVED,
+               out_len=L, weight=w.to(cuda), dst=track, dst_ch_stride=n_track, dst_chunk_stride=0, dst_offsets=offs,
+               dst_limit=n_track)
+    exp = torch.zeros((2, n_track))
+    exp[:, :L] = ref[0] * w
+    exp[:, L + 100:2 * L + 100] = ref[1] * w
+    exp[:, 2 * L + 300:] = (ref[2] * w)[:, : n_track - (2 * L + 300)]
+    assert max_abs_err(track.cpu(), exp) <= WAVE_ATOL * max(1.0, float(exp.abs().max()))
+
+
 def test_istft_cac_freq_pad_and_trim_concat_placement(cuda):
     """mdxnet.py:58-75 (zero freq-pad) + :178-183 (trim, concat, drop pad) fused into one launch."""
     from audiolab_b200 import spectral as sp

@@ -1,0 +1,168 @@
+"""Fused row-wise bf16 operators of the RoFormer inference path (csrc/al_netops.cu, audiolab_b200/netops.py).
+
+CPU: the host logic of `RoformerMaskNet._axial_fused` (token-major residual stream, strided attention
+views, deferred FeedForward bias) against the upstream-shaped module path, with the three kernels replaced
+by their PyTorch definitions below.  GPU: each kernel against the same definitions, and the fused bf16
+mask against the module path under bf16 autocast.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from audiolab_b200.configs import RoformerConfig
+from audiolab_b200.nets.roformer import RoformerMaskNet
+
+
+# ---- PyTorch definitions of the three operators (upstream RMSNorm / rotary / gated attention) ----
+def ref_rmsnorm(x, gamma, bias=None, out=None):
+    if bias is not None:
+        x.copy_((x.float() + bias).to(x.dtype))
+    y = (F.normalize(x.float(), dim=-1) * (x.shape[-1] ** 0.5) * gamma).to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def ref_rotary_(q, k, cs, heads, dh, pos_div, pos_mod):
+    n = q.shape[0]
+    pos = (torch.arange(n, device=q.device) // pos_div) % pos_mod
+    c, s = cs[pos][:, None, :, 0], cs[pos][:, None, :, 1]       # [n, 1, dh/2]
+    for t in (q, k):
+        v = t.view(n, heads, dh // 2, 2).float()
+        a, b = v[..., 0], v[..., 1]
+        t.copy_(torch.stack((a * c - b * s, b * c + a * s), dim=-1).view(n, -1).to(t.dtype))
+
+
+def ref_gate_(o, gates, heads, dh):
+    n = o.shape[0]
+    o.copy_((o.view(n, heads, dh).float() * torch.sigmoid(gates.float())[:, :, None]).view(n, -1).to(o.dtype))
+
+
+def _small_net(kind):
+    torch.manual_seed(0)
+    if kind == "bs":
+        cfg = RoformerConfig(dim=32, depth=2, heads=2, dim_head=16, chunk_size=441 * 12)
+    else:
+        cfg = RoformerConfig(kind="mel", dim=32, depth=2, heads=2, dim_head=16, chunk_size=441 * 12, num_bands=20)
+    net = RoformerMaskNet(cfg).eval()
+    with torch.no_grad():
+        for p in net.parameters():          # default init leaves gammas at 1 and biases near 0
+            p.add_(0.05 * torch.randn_like(p))
+    return cfg, net
+
+
+@pytest.mark.parametrize("kind", ["bs", "mel"])
+def test_fused_axial_host_logic_matches_module_path(kind, monkeypatch):
+    import audiolab_b200.netops as netops
+    cfg, net = _small_net(kind)
+    monkeypatch.setattr(netops, "rmsnorm", ref_rmsnorm)
+    monkeypatch.setattr(netops, "rotary_", ref_rotary_)
+    monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    net._fused_dtype = torch.float32
+    b, t, f = 2, 13, len(net.band_split.dim_inputs)
+    x = torch.randn(b, t, f, cfg.dim)
+    with torch.no_grad():
+        ref = net._axial(x.clone())
+        if kind != "mel":
+            ref = net.final_norm(ref)
+        got = net._axial_fused(x.clone())
+    assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_netops_refuse_cpu_tensors():
+    import audiolab_b200.netops as netops
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        netops.rmsnorm(x, torch.ones(64))
+    with pytest.raises(RuntimeError):
+        netops.gate_sigmoid_(x, torch.zeros(4, 4, dtype=torch.bfloat16), 4, 16)
+
+
+# ---- GPU: kernels vs definitions -----------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d,with_bias", [(1000, 512, False), (777, 512, True), (65, 1024, True), (33, 2048, False),
+                                           (50, 136, True)])
+def test_rmsnorm_kernel(cuda, n, d, with_bias):
+    import audiolab_b200.netops as netops
+    g = torch.Generator().manual_seed(n + d)
+    x = (torch.randn(n, d, generator=g) * 3).to(torch.bfloat16).to(cuda)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).to(cuda)
+    bias = (0.2 * torch.randn(d, generator=g)).to(cuda) if with_bias else None
+    x_ref = x.clone()
+    ref = ref_rmsnorm(x_ref, gamma, bias)
+    x_k = x.clone()
+    got = netops.rmsnorm(x_k, gamma, bias)
+    assert torch.equal(x_k, x_ref)                                  # the stored residual (x + bias, bf16)
+    assert float((got.float() - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())   # 1 bf16 ulp
+    # in place
+    x_i = x.clone()
+    netops.rmsnorm(x_i, gamma, bias, out=x_i)
+    assert torch.equal(x_i, got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pos_div,pos_mod", [(7, 11), (1, 7)])
+def test_rotary_kernel(cuda, pos_div, pos_mod):
+    import audiolab_b200.netops as netops
+    heads, dh, n = 8, 64, 3 * 7 * 11
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(n, heads * dh, generator=g).to(torch.bfloat16).to(cuda)
+    k = torch.randn(n, heads * dh, generator=g).to(torch.bfloat16).to(cuda)
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, dh, 2).float() / dh))
+    ang = torch.arange(pos_mod).float()[:, None] * freqs[None]
+    cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().to(cuda)
+    qr, kr = q.clone(), k.clone()
+    ref_rotary_(qr, kr, cs, heads, dh, pos_div, pos_mod)
+    netops.rotary_(q, k, cs, heads, dh, pos_div, pos_mod)
+    assert float((q.float() - qr.float()).abs().max()) <= 2 ** -7 * float(qr.float().abs().max())
+    assert float((k.float() - kr.float()).abs().max()) <= 2 ** -7 * float(kr.float().abs().max())
+
+
+@pytest.mark.gpu
+def test_gate_kernel(cuda):
+    import audiolab_b200.netops as netops
+    heads, dh, n = 8, 64, 999
+    g = torch.Generator().manual_seed(6)
+    o = torch.randn(n, heads * dh, generator=g).to(torch.bfloat16).to(cuda)
+    gates = (2 * torch.randn(n, heads, generator=g)).to(torch.bfloat16).to(cuda)
+    ref = o.clone()
+    ref_gate_(ref, gates, heads, dh)
+    netops.gate_sigmoid_(o, gates, heads, dh)
+    assert float((o.float() - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["bs", "mel"])
+def test_fused_bf16_mask_matches_autocast_module_path(cuda, kind):
+    """The fused path must be at least as close to the fp32 network as the reference's autocast configuration."""
+    cfg, net = _small_net(kind)
+    net = net.to(cuda)
+    t, f = 1 + cfg.chunk_size // cfg.stft_hop_length, cfg.stft_n_fft // 2 + 1
+    g = torch.Generator().manual_seed(3)
+    spec = torch.view_as_complex(torch.randn(2, t, f, 2, 2, generator=g)).to(cuda)
+    m32 = net.set_compute_dtype(torch.float32).mask(spec)
+    net.set_compute_dtype(torch.bfloat16)
+    fused = net.mask(spec)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):     # the module path under autocast
+        x = net.band_split(torch.view_as_real(spec).reshape(2, t, -1) if kind == "bs" else
+                           torch.view_as_real(spec).reshape(2, t, f * 2, 2)[:, :, net.freq_indices].reshape(2, t, -1))
+        x = net._axial(x)
+        if kind != "mel":
+            x = net.final_norm(x)
+    x_fused = None
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        xb = net.band_split(torch.view_as_real(spec).reshape(2, t, -1) if kind == "bs" else
+                            torch.view_as_real(spec).reshape(2, t, f * 2, 2)[:, :, net.freq_indices].reshape(2, t, -1))
+    with torch.no_grad():
+        x_fused = net._axial_fused(xb)
+        x32 = net._axial(xb.float())
+        if kind != "mel":
+            x32 = net.final_norm(x32)
+    err_fused = float((x_fused.float() - x32).norm() / x32.norm())
+    err_autocast = float((x.float() - x32).norm() / x32.norm())
+    print(f"{kind}: relative error vs fp32 trunk: fused {err_fused:.3e}, autocast modules {err_autocast:.3e}")
+    assert err_fused <= 1.25 * err_autocast + 1e-3
+    assert fused.shape == m32.shape and torch.isfinite(torch.view_as_real(fused)).all()
+    rel = float((torch.view_as_real(fused) - torch.view_as_real(m32)).norm() / torch.view_as_real(m32).norm())
+    assert rel <= 0.05
