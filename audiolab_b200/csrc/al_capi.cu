@@ -380,4 +380,14 @@ int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, 
     return AL_OK;
 }
 
+int al_gelu_bf16(void* x, int64_t n, void* stream) {
+    if (!x) return fail(AL_E_ARG, "al_gelu_bf16: NULL argument");
+    if (n == 0) return AL_OK;
+    if (n < 0 || (n & 7) != 0) return fail(AL_E_ARG, "al_gelu_bf16: n must be a non-negative multiple of 8");
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(AL_E_ARG, "al_gelu_bf16: x must be 16-byte aligned");
+    cudaError_t e = al::launch_gelu_bf16(x, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_gelu_bf16");
+    return AL_OK;
+}
+
 }  // extern "C"

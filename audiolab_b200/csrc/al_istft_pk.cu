@@ -13,21 +13,29 @@
 //    loads of a register pair (r, 31-r) fall on the same 128-byte lines and are issued back to
 //    back), so there is no shuffle, no lane-0 special case and no spectrum staging in shared memory;
 //  * HBM latency is covered by bulk L2 prefetches (cp.async.bulk.prefetch.L2) of the rows of the next
-//    round, issued before the current round's loads, and by a two-deep register pipeline of loads;
+//    round, issued before the current round's loads, and by a four-deep register pipeline of loads
+//    (the FFT registers are still empty while the first stages are in flight);
 //  * the windowed frame is parked in the warp's own transposition scratch; after one CTA barrier all
-//    threads gather-sum the round's 8 frames (+ the carry of earlier rounds) in ascending frame
+//    threads gather-sum the round's frames (+ the carry of earlier rounds) in ascending frame
 //    order -- the deterministic order of istft_kernel -- and emit both channels.
 //
 // Algorithmic bytes per frame (both channels): 2 * (1025*8 [+ 1025*8 mask] + hop*4).
+#include <stdlib.h>
+
 #include "al_fftp.cuh"
 #include "al_kernels.h"
 
 namespace al {
 
-constexpr int kIpWarps = 8;               // frames per round
-constexpr int kIpThreads = kIpWarps * 32;
+// W = warps = frames per round.  W = 4 (default): two CTAs share an SM, so one's row loads overlap the
+// other's FFT / overlap-add; W = 8: one CTA per SM, half the halo recomputation (AL_IP_WARPS=8 selects it).
+constexpr int kIpSmWarps = 8;             // 255 registers per thread: 8 warps fill the register file
 constexpr int kIpN = 2048;
 constexpr int kIpBins = 1025;
+#ifndef AL_IP_DEPTH
+#define AL_IP_DEPTH 4
+#endif
+constexpr int kIpDepth = AL_IP_DEPTH;    // register pipeline depth of the row loads (stages of 4 + 4 x 16 B per lane)
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
@@ -54,21 +62,23 @@ __device__ __forceinline__ void ip_combine(float2 pr, float2 pi, float2 qr, floa
     zi = pfma(di, w.y, pfma(dr, w.x, ai));                  // A.im + Re(D conj(w))
 }
 
-template <bool MASK>
-__global__ void __launch_bounds__(kIpThreads, 1)
+template <bool MASK, int W>
+__global__ void __launch_bounds__(W * 32, kIpSmWarps / W)
 istft_pk2_kernel(const IstftPkParams p) {
+    constexpr int kIpWarps = W, kIpThreads = W * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);           // [1024]
     float2* s_win = s_tw + 1024;                                   // [1024] (w[2k], w[2k+1])
     float2* s_ctw = s_win + 1024;                                  // [1024] W^k
     float4* s_scr = reinterpret_cast<float4*>(s_ctw + 1024);       // [kIpWarps][kScrF4]
-    float2* s_carry = reinterpret_cast<float2*>(s_scr + kIpWarps * kScrF4);   // [2][2048 - hop] (L, R)
+    float2* s_carry = reinterpret_cast<float2*>(s_scr + kIpWarps * kScrF4);   // [2048 - hop] (L, R), updated in place
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
     const int chunk = g / p.stems, stem = g - chunk * p.stems;
     const int hop = p.hop, T = p.n_frames;
     const int carry_len = kIpN - hop;
+    const int kOla_K = (kIpN + hop - 1) / hop;          // frames that can cover one position
 
     // owned untrimmed overlap-add positions [Pa, Pb)
     const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
@@ -97,12 +107,11 @@ istft_pk2_kernel(const IstftPkParams p) {
         s_win[i] = reinterpret_cast<const float2*>(p.window)[i];
         s_ctw[i] = p.ctw[i];
     }
-    for (int i = tid; i < 2 * carry_len; i += kIpThreads) s_carry[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < carry_len; i += kIpThreads) s_carry[i] = make_float2(0.f, 0.f);
     __syncthreads();
 
     float4* scr = s_scr + warp * kScrF4;
-    int cbuf = 0;
-    for (int tr = ta; tr <= t_last; tr += kIpWarps, cbuf ^= 1) {
+    for (int tr = ta; tr <= t_last; tr += kIpWarps) {
         const int nf = max(0, min(kIpWarps, tb - tr + 1));   // live frames of this round (CTA-uniform)
         const int t = tr + warp;
         const bool live = warp < nf;                          // warp-uniform
@@ -116,7 +125,7 @@ istft_pk2_kernel(const IstftPkParams p) {
             const float4* __restrict__ xrow = X + (long long)t * kIpBins;
             const float4* __restrict__ mrow = MASK ? M + (long long)t * kIpBins : nullptr;
             // pair r: k1 = 32 r + lane (reg r), k2 = 32 (31 - r) + lane (reg 31 - r); mirrors q = 1024 - k
-            float4 bx[2][4], bm[2][4];
+            float4 bx[kIpDepth][4], bm[kIpDepth][4];
 #define IP_ISSUE(r_, b_)                                                         \
     do {                                                                          \
         const int k1_ = 32 * (r_) + lane, k2_ = 32 * (31 - (r_)) + lane;          \
@@ -131,11 +140,12 @@ istft_pk2_kernel(const IstftPkParams p) {
             bm[b_][3] = __ldg(mrow + (1024 - k1_));                               \
         }                                                                         \
     } while (0)
-            IP_ISSUE(0, 0);
+#pragma unroll
+            for (int r = 0; r < kIpDepth - 1; ++r) IP_ISSUE(r, r);
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const int b = r & 1;
-                if (r + 1 < 16) IP_ISSUE(r + 1, b ^ 1);
+                const int b = r % kIpDepth;
+                if (r + kIpDepth - 1 < 16) IP_ISSUE(r + kIpDepth - 1, (r + kIpDepth - 1) % kIpDepth);
                 float2 p1r, p1i, q2r, q2i, p2r, p2i, q1r, q1i;
                 ip_product<MASK>(bx[b][0], bm[b][0], p1r, p1i);
                 ip_product<MASK>(bx[b][1], bm[b][1], q2r, q2i);
@@ -164,49 +174,59 @@ istft_pk2_kernel(const IstftPkParams p) {
         }
         __syncthreads();   // all frames of the round are parked
 
-        // ---- overlap-add: span [S, S + 8 hop + carry_len), ascending frame order ------------------------
+        // ---- overlap-add: span [S, S + kIpWarps hop + carry_len), ascending frame order ------------------------
+        // A thread owns offsets j (< hop) and walks the hop-blocks h of the span: position i = h hop + j
+        // receives frame f at sample (h - f) hop + j, f = max(0, h - kj) .. min(nf - 1, h), where
+        // kj = (2047 - j) / hop is fixed per thread -- no per-sample division, unit-stride LDS.64.
         const long long S = (long long)tr * hop;
-        const float2* cin = s_carry + cbuf * carry_len;
-        float2* cout = s_carry + (cbuf ^ 1) * carry_len;
+        // the carry is updated in place: a thread writes carry[(h - kIpWarps) hop + j] only after it has
+        // read that same element (at hop-block h - kIpWarps), and no other thread touches offsets = j mod hop
+        const float2* cin = s_carry;
+        float2* cout = s_carry;
         const int emit = kIpWarps * hop;
         const int span = emit + carry_len;
-        for (int i = tid; i < span; i += kIpThreads) {
-            float2 acc = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
-            int f_lo = (i - kIpN) / hop + 1;
-            if (i < kIpN) f_lo = 0;
-            const int f_hi = min(nf - 1, i / hop);
-            for (int f = f_lo; f <= f_hi; ++f) {
-                const float2 v = reinterpret_cast<const float2*>(s_scr + f * kScrF4)[i - f * hop];
-                acc.x += v.x;
-                acc.y += v.y;
-            }
-            if (i < emit) {
-                const long long P = S + i;
-                if (P >= Pa && P < Pb) {
-                    const long long pp = P - p.out_start;
-                    const float e = __ldg(p.inv_env + P);
-                    float v0 = acc.x * e, v1 = acc.y * e;
-                    if (p.weight) {
-                        const float wgt = __ldg(p.weight + pp);
-                        v0 *= wgt;
-                        v1 *= wgt;
-                    }
-                    const long long q = place + pp;
-                    if (q >= 0 && q < p.dst_limit) {
-                        dst0[pp] = v0;
-                        dst1[pp] = v1;
-                    }
+        const int fstride = 2 * kScrF4 - hop;                       // float2 step from (f, h) to (f + 1, h)
+        for (int j = tid; j < hop; j += kIpThreads) {
+            const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
+            const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
+            for (int h = 0, i = j; i < span; ++h, i += hop) {
+                float2 acc = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+                const int f_lo = max(0, h - kj);
+                const int f_hi = min(nf - 1, h);
+                const float2* __restrict__ q = sj + f_lo * fstride + h * hop;   // = scr_f [(h - f) hop + j]
+                for (int f = f_lo; f <= f_hi; ++f, q += fstride) {
+                    const float2 v = *q;
+                    acc.x += v.x;
+                    acc.y += v.y;
                 }
-            } else {
-                cout[i - emit] = acc;
+                if (i < emit) {
+                    const long long P = S + i;
+                    if (P >= Pa && P < Pb) {
+                        const long long pp = P - p.out_start;
+                        const float e = __ldg(p.inv_env + P);
+                        float v0 = acc.x * e, v1 = acc.y * e;
+                        if (p.weight) {
+                            const float wgt = __ldg(p.weight + pp);
+                            v0 *= wgt;
+                            v1 *= wgt;
+                        }
+                        const long long qd = place + pp;
+                        if (qd >= 0 && qd < p.dst_limit) {
+                            dst0[pp] = v0;
+                            dst1[pp] = v1;
+                        }
+                    }
+                } else {
+                    cout[i - emit] = acc;
+                }
             }
         }
     }
 }
 
-// segments per row: minimise waves * rounds per segment (a round = 8 frames; each segment re-computes the
+// segments per row: minimise waves * rounds per segment (a round = kIpWarps frames; each segment re-computes the
 // ceil((2048 - hop) / hop) frames that precede its first owned sample)
-static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int* hpc_out, int* segs_out) {
+static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int kIpWarps, int* hpc_out, int* segs_out) {
     const int halo = (kIpN - hop + hop - 1) / hop;
     long long best = -1;
     int best_segs = 1;
@@ -238,23 +258,28 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     }
     const int rows = n_chunks * p.stems;
     const int total_hops = (p.out_len + p.hop - 1) / p.hop;
-    ip_tiling(rows, total_hops, p.hop, n_sm, &p.hops_per_cta, &p.segs);
-    const size_t smem = (size_t)3 * 1024 * sizeof(float2) + (size_t)kIpWarps * kScrF4 * sizeof(float4) +
-                        2 * (size_t)(kIpN - p.hop) * sizeof(float2);
+    static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
+    ip_tiling(rows, total_hops, p.hop, n_sm * (kIpSmWarps / W), W, &p.hops_per_cta, &p.segs);
+    const size_t smem = (size_t)3 * 1024 * sizeof(float2) + (size_t)W * kScrF4 * sizeof(float4) +
+                        (size_t)(kIpN - p.hop) * sizeof(float2);
     const size_t cap = 227 * 1024;
     if (smem > cap) return cudaErrorInvalidValue;
-#define AL_IP_LAUNCH(MSK)                                                                                     \
+#define AL_IP_LAUNCH(MSK, WW)                                                                                    \
     do {                                                                                                      \
         static bool attr = false;                                                                             \
         if (!attr) {                                                                                          \
-            cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)cap);                                                   \
+            if (e != cudaSuccess) return e;                                                                   \
+            e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+                                     cudaSharedmemCarveoutMaxShared);                                         \
             if (e != cudaSuccess) return e;                                                                   \
             attr = true;                                                                                      \
         }                                                                                                     \
-        istft_pk2_kernel<MSK><<<(unsigned)(rows * p.segs), kIpThreads, smem, stream>>>(p);                   \
+        istft_pk2_kernel<MSK, WW><<<(unsigned)(rows * p.segs), WW * 32, smem, stream>>>(p);                 \
     } while (0)
-    if (p.mask) AL_IP_LAUNCH(true); else AL_IP_LAUNCH(false);
+    if (W == 8) { if (p.mask) AL_IP_LAUNCH(true, 8); else AL_IP_LAUNCH(false, 8); }
+    else { if (p.mask) AL_IP_LAUNCH(true, 4); else AL_IP_LAUNCH(false, 4); }
 #undef AL_IP_LAUNCH
     count_launch();
     return cudaGetLastError();

@@ -139,6 +139,8 @@ cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_ro
 cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
                              cudaStream_t stream);
 
+cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream);
+
 cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
                        cudaStream_t stream);
 

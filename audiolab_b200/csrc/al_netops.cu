@@ -161,4 +161,33 @@ cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int h
     return cudaGetLastError();
 }
 
+// x: [n] bf16, exact (erf) GELU in place -- upstream FeedForward's nn.GELU() between its two Linear layers
+// (SURVEY.md A.4); fp32 inside, like torch's bf16 gelu.  Two 16-byte vectors per thread.
+__global__ void __launch_bounds__(256)
+gelu_bf16_kernel(uint4* __restrict__ x, long long n_vec) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= n_vec) return;
+    const bool two = i + 1 < n_vec;
+    const uint4 v0 = x[i];
+    const uint4 v1 = two ? x[i + 1] : make_uint4(0u, 0u, 0u, 0u);
+    float a[8], b[8];
+    bf16x8_to_f32(v0, a);
+    bf16x8_to_f32(v1, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = a[j] * 0.5f * (1.f + erff(a[j] * 0.70710678118654752440f));
+        b[j] = b[j] * 0.5f * (1.f + erff(b[j] * 0.70710678118654752440f));
+    }
+    x[i] = f32_to_bf16x8(a);
+    if (two) x[i + 1] = f32_to_bf16x8(b);
+}
+
+cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream) {
+    const long long n_vec = n / 8;
+    if (n_vec <= 0) return cudaSuccess;
+    gelu_bf16_kernel<<<(unsigned)((n_vec + 511) / 512), 256, 0, stream>>>(reinterpret_cast<uint4*>(x), n_vec);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace al

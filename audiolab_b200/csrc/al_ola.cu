@@ -3,12 +3,32 @@
 // loops of upstream MDXSeparator.demix / MDXCSeparator.demix / demucs.apply.
 //
 // HBM-bound: reads every chunk sample once (4 B) and writes every track sample once.
-// One thread owns one (row, position); it adds the covering chunks in ascending chunk order, so the
-// sum is bit-identical however the chunks were batched or sharded.  The weight sum ("counter") is
+// One thread owns four consecutive positions of a row (128-bit loads and stores where the addresses
+// allow it); every position adds its covering chunks in ascending chunk order, so the sum is
+// bit-identical however the chunks were batched or sharded.  The loads of up to four covering chunks
+// are issued before the first dependent add to keep enough bytes in flight per SM.  The weight sum ("counter") is
 // recomputed from the same tables instead of being stored.
 #include "al_kernels.h"
 
 namespace al {
+
+// [emul-begin]
+constexpr int kOlaVec = 4;      // consecutive positions per thread
+constexpr int kOlaGroup = 4;    // chunks whose loads are issued together
+
+__device__ __forceinline__ bool al_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Loads v[e] = src[e] for the elements selected by `m` (bit e), 128-bit when all four are wanted and
+// the address allows it; unselected elements read as 0.
+__device__ __forceinline__ void ola_load4(const float* __restrict__ src, unsigned m, float (&v)[kOlaVec]) {
+    if (m == 0xFu && al_aligned16(src)) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < kOlaVec; ++e) v[e] = ((m >> e) & 1u) ? __ldg(src + e) : 0.f;
+    }
+}
 
 __global__ void __launch_bounds__(256)
 ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
@@ -16,41 +36,92 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk
                   const float* __restrict__ wtab, const int* __restrict__ tab_id, long long n_total,
                   long long p0, long long p1, const float* __restrict__ halo_in, int raw_out, float eps,
                   float scale, float* __restrict__ track, long long track_stride) {
-    const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // the CTA's first position decides where the chunk walk starts (uniform loads, one search per CTA
+    // instead of one per sample); chunks that end before a thread's own positions are masked out below
+    const long long pb = p0 + (long long)blockIdx.x * blockDim.x * kOlaVec;
+    const long long p = pb + (long long)threadIdx.x * kOlaVec;
     if (p >= p1) return;
-    // first chunk whose end is beyond p: offsets ascending, so binary search on off_c + chunk_len > p
     int lo = 0, hi = n_chunks;
-    while (lo < hi) {
+    while (lo < hi) {   // offsets ascending: first chunk with off_c + chunk_len > pb
         const int mid = (lo + hi) >> 1;
-        if (__ldg(offsets + mid) + chunk_len > p) hi = mid; else lo = mid + 1;
+        if (__ldg(offsets + mid) + chunk_len > pb) hi = mid; else lo = mid + 1;
     }
     const int c_first = lo;
+    const unsigned own = p + kOlaVec <= p1 ? 0xFu : ((1u << (int)(p1 - p)) - 1u);   // positions inside [p0, p1)
     for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-        float acc = halo_in ? __ldg(halo_in + (long long)r * (p1 - p0) + (p - p0)) : 0.f;
-        float wsum = 0.f;
-        for (int c = c_first; c < n_chunks; ++c) {
-            const long long off = __ldg(offsets + c);
-            if (off > p) break;
-            const long long j = p - off;
-            const long long len = min((long long)chunk_len, n_total - off);
-            if (j >= len) continue;
-            float w = 1.f;
-            if (wtab) w = __ldg(wtab + (long long)(tab_id ? __ldg(tab_id + c) : 0) * chunk_len + j);
-            const int m = mult ? __ldg(mult + c) : 1;
-            // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive through
-            // halo_in, only their weights are counted here
-            const float x = c >= data_chunk0 ? __ldg(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j) : 0.f;
-            for (int k = 0; k < m; ++k) {   // the reference re-adds a tail chunk m times; keep its rounding
-                acc += x * w;
-                wsum += w;
+        float acc[kOlaVec], wsum[kOlaVec];
+        if (halo_in) ola_load4(halo_in + (long long)r * (p1 - p0) + (p - p0), own, acc);
+        else {
+#pragma unroll
+            for (int e = 0; e < kOlaVec; ++e) acc[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < kOlaVec; ++e) wsum[e] = 0.f;
+        for (int c0 = c_first; c0 < n_chunks; c0 += kOlaGroup) {
+            if (__ldg(offsets + c0) > p + (kOlaVec - 1)) break;     // ascending: nothing further covers us
+            float x[kOlaGroup][kOlaVec], w[kOlaGroup][kOlaVec];
+            unsigned msk[kOlaGroup];
+            int mm[kOlaGroup];
+            // issue every load of the group before the first dependent add
+#pragma unroll
+            for (int g = 0; g < kOlaGroup; ++g) {
+                const int c = c0 + g;
+                msk[g] = 0;
+                mm[g] = 0;
+                if (c < n_chunks) {
+                    const long long off = __ldg(offsets + c);
+                    const long long j = p - off;                                  // may be negative
+                    const long long len = min((long long)chunk_len, n_total - off);
+#pragma unroll
+                    for (int e = 0; e < kOlaVec; ++e)
+                        if (j + e >= 0 && j + e < len) msk[g] |= 1u << e;
+                    msk[g] &= own;
+                    mm[g] = mult ? __ldg(mult + c) : 1;
+                }
+                if (msk[g]) {
+                    const int c = c0 + g;
+                    const long long j = p - __ldg(offsets + c);
+                    if (wtab) ola_load4(wtab + (long long)(tab_id ? __ldg(tab_id + c) : 0) * chunk_len + j, msk[g], w[g]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < kOlaVec; ++e) w[g][e] = 1.f;
+                    }
+                    // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive
+                    // through halo_in, only their weights are counted here
+                    if (c >= data_chunk0) ola_load4(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j, msk[g], x[g]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < kOlaVec; ++e) x[g][e] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kOlaGroup; ++g) {
+                if (!msk[g]) continue;
+                for (int k = 0; k < mm[g]; ++k) {   // the reference re-adds a tail chunk m times; keep its rounding
+#pragma unroll
+                    for (int e = 0; e < kOlaVec; ++e) {
+                        if ((msk[g] >> e) & 1u) {
+                            acc[e] += x[g][e] * w[g][e];
+                            wsum[e] += w[g][e];
+                        }
+                    }
+                }
             }
         }
-        float v;
-        if (raw_out) v = acc;
-        else v = scale * acc / fmaxf(wsum, eps);
-        track[(long long)r * track_stride + p] = v;
+        float v[kOlaVec];
+#pragma unroll
+        for (int e = 0; e < kOlaVec; ++e) v[e] = raw_out ? acc[e] : scale * acc[e] / fmaxf(wsum[e], eps);
+        float* dst = track + (long long)r * track_stride + p;
+        if (own == 0xFu && al_aligned16(dst)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int e = 0; e < kOlaVec; ++e)
+                if ((own >> e) & 1u) dst[e] = v[e];
+        }
     }
 }
+// [emul-end]
 
 cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                               const long long* offsets, const int* mult, const float* wtab,
@@ -59,7 +130,8 @@ cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0
                               long long track_stride, cudaStream_t stream) {
     if (p1 <= p0) return cudaSuccess;
     const long long n = p1 - p0;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)min(rows, 8));
+    const long long per_cta = 256LL * kOlaVec;
+    dim3 grid((unsigned)((n + per_cta - 1) / per_cta), (unsigned)min(rows, 8));
     ola_gather_kernel<<<grid, 256, 0, stream>>>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id,
                                                 n_total, p0, p1, halo_in, raw_out, eps, scale, track,
                                                 track_stride);

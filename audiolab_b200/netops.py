@@ -58,3 +58,13 @@ def gate_sigmoid_(o: torch.Tensor, gates: torch.Tensor, heads: int, dim_head: in
         raise ValueError("o must be [rows, heads*dim_head] and gates [rows, heads]")
     _lib.check(_lib.lib().al_gate_sigmoid_bf16(o.data_ptr(), gates.data_ptr(), o.shape[0], heads, dim_head, _stream()),
                "al_gate_sigmoid_bf16")
+
+
+def gelu_(x: torch.Tensor) -> torch.Tensor:
+    """Exact (erf) GELU of a contiguous bf16 tensor, in place."""
+    if not x.is_cuda:
+        raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.numel() % 8 != 0:
+        raise ValueError("x must be a contiguous bf16 tensor with a multiple of 8 elements")
+    _lib.check(_lib.lib().al_gelu_bf16(x.data_ptr(), x.numel(), _stream()), "al_gelu_bf16")
+    return x

@@ -264,7 +264,7 @@ class RoformerMaskNet(nn.Module):
             x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
             lin1, lin2 = ff.net[1], ff.net[4]
             xn = netops.rmsnorm(x2, ff.net[0].gamma.detach())
-            hid = F.gelu(F.linear(xn, self._bf16(lin1.weight), self._bf16(lin1.bias)))
+            hid = netops.gelu_(F.linear(xn, self._bf16(lin1.weight), self._bf16(lin1.bias)))
             x2.addmm_(hid, self._bf16(lin2.weight).t())
             pending = lin2.bias.detach()
         if isinstance(tr.norm, RMSNorm):

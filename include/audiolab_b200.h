@@ -178,12 +178,15 @@ int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream);
  *   (row / pos_div) % pos_mod (rows are tokens of a [batch, time, band] grid).
  * al_gate_sigmoid_bf16 -- upstream Attention: out * to_gates(x).sigmoid(), in place.
  *   o [n_rows, heads*dim_head], gates [n_rows, heads].
+ * al_gelu_bf16 -- upstream FeedForward's nn.GELU() (exact, erf form) between its two Linear layers, in place.
+ *   x [n] bf16, n a multiple of 8.
  */
 int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, int64_t n_rows, int dim, float scale,
                     float eps, void* stream);
 int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int heads, int dim_head, int64_t pos_div,
                    int pos_mod, void* stream);
 int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream);
+int al_gelu_bf16(void* x, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

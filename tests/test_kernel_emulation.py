@@ -1,0 +1,104 @@
+"""Host emulation of the index-logic CUDA kernels (tools/cpu_emul): the same source text as
+audiolab_b200/csrc/al_ola.cu / al_resample.cu between the [emul-begin]/[emul-end] markers, compiled
+for the host with one std::thread per CUDA thread.  Checks addressing, masking, tiling and the
+accumulation order on a box without a GPU; the GPU parity tests (tests/test_kernels_gpu.py) remain
+the parity gate."""
+import ctypes
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle.resample import resample_poly_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    spec = importlib.util.spec_from_file_location("build_emul", os.path.join(ROOT, "tools", "cpu_emul", "build_emul.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = ctypes.CDLL(mod.build())
+    P, LL, I, F = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+    lib.emul_ola_gather.argtypes = [P, I, I, I, I, P, P, P, P, LL, LL, LL, P, I, F, F, P, LL, I]
+    lib.emul_ola_gather.restype = None
+    lib.emul_resample.argtypes = [P, LL, P, LL, I, LL, LL, I, I, P, I, I]
+    lib.emul_resample.restype = I
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ola(lib, chunks, offs, n, mult=None, wtab=None, p0=0, p1=None, halo_in=None, raw_out=False, data_chunk0=0,
+         shift_elems=0):
+    n_data, rows, C = chunks.shape
+    p1 = n if p1 is None else p1
+    offs = np.ascontiguousarray(offs, np.int64)
+    mult = None if mult is None else np.ascontiguousarray(mult, np.int32)
+    buf = np.zeros(rows * n + 8, np.float32)                       # shift_elems moves the track off 16-byte alignment
+    track = buf[shift_elems:shift_elems + rows * n].reshape(rows, n)
+    lib.emul_ola_gather(_p(chunks), n_data + data_chunk0, data_chunk0, rows, C, _p(offs), _p(mult), _p(wtab), None, n,
+                        p0, p1, _p(halo_in), int(raw_out), 1e-10, 1.0, _p(track), n, 64)
+    return track.copy()
+
+
+@pytest.mark.parametrize("C,step,n,shift", [(4000, 1000, 13337, 0), (4000, 1000, 13337, 1), (1021, 255, 5003, 0),
+                                           (64, 64, 640, 0)])
+def test_ola_gather_emulated_matches_numpy_and_shards_bitwise(emul, C, step, n, shift):
+    rs = np.random.RandomState(0)
+    rows = 3
+    offs = list(range(0, n - C + 1, step)) + [n - C]
+    mult = [1] * (len(offs) - 1) + [3]
+    chunks = rs.standard_normal((len(offs), rows, C)).astype(np.float32)
+    w = np.hamming(C).astype(np.float32)
+    res = np.zeros((rows, n), np.float64)
+    cnt = np.zeros((rows, n), np.float64)
+    for c, (o, m) in enumerate(zip(offs, mult)):
+        for _ in range(m):
+            res[:, o:o + C] += chunks[c].astype(np.float64) * w
+            cnt[:, o:o + C] += w
+    ref = res / np.maximum(cnt, 1e-10)
+    got = _ola(emul, chunks, offs, n, mult=mult, wtab=w, shift_elems=shift)
+    assert np.abs(got - ref).max() <= 2e-6
+    cut = (n // 2) | 1 if shift else (n // 2) & ~3
+    k = sum(1 for o in offs if o < cut)
+    left = _ola(emul, chunks[:k], offs[:k], n, mult=mult[:k], wtab=w, p0=0, p1=cut)
+    halo = _ola(emul, chunks[:k], offs[:k], n, mult=mult[:k], wtab=w, p0=cut, p1=n, raw_out=True)[:, cut:].copy()
+    right = _ola(emul, chunks[k:], offs, n, mult=mult, wtab=w, p0=cut, p1=n, halo_in=halo, data_chunk0=k)
+    stitched = np.concatenate([left[:, :cut], right[:, cut:]], axis=1)
+    assert np.array_equal(stitched, got)
+    assert not left[:, cut:].any() and not right[:, :cut].any()     # nothing written outside [p0, p1)
+
+
+def _taps(up, down):
+    from audiolab_b200.spectral import resample_taps
+    return resample_taps(up, down)
+
+
+@pytest.mark.parametrize("up,down,n_in,rows,grid", [(147, 160, 48000, 2, 3), (147, 160, 12345, 1, 1), (147, 160, 160, 2, 4),
+                                                   (147, 160, 7, 1, 2), (160, 147, 30000, 2, 2), (147, 160, 9001, 3, 7)])
+def test_resample_rb_emulated_matches_scipy(emul, up, down, n_in, rows, grid):
+    rs = np.random.RandomState(n_in)
+    x = rs.uniform(-1, 1, size=(rows, n_in)).astype(np.float32)
+    ref = resample_poly_ref(x, up, down)
+    taps = _taps(up, down)
+    n_out = (n_in * up + down - 1) // down
+    assert ref.shape == (rows, n_out)
+    # unaligned variant: odd row stride disables the 128-bit paths
+    for pad in (0, 1) if n_in < 20000 else (0,):
+        in_stride = (n_in + 3) // 4 * 4 + pad
+        out_stride = (n_out + 3) // 4 * 4 + pad
+        xin = np.zeros((rows, in_stride), np.float32)
+        xin[:, :n_in] = x
+        xin[:, n_in:] = np.nan                                      # reads past n_in must be masked
+        out = np.full((rows, out_stride), -77.0, np.float32)
+        rc = emul.emul_resample(_p(xin), in_stride, _p(out), out_stride, rows, n_in, n_out, up, down, _p(taps),
+                                taps.size, grid)
+        assert rc >= 0, "register-blocked plan rejected this ratio"
+        assert rc == (3 if pad == 0 else 0)
+        assert np.abs(out[:, :n_out] - ref).max() <= 2e-6
+        assert (out[:, n_out:] == -77.0).all()                       # nothing written past n_out

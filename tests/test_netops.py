@@ -39,6 +39,11 @@ def ref_gate_(o, gates, heads, dh):
     o.copy_((o.view(n, heads, dh).float() * torch.sigmoid(gates.float())[:, :, None]).view(n, -1).to(o.dtype))
 
 
+def ref_gelu_(x):
+    x.copy_(F.gelu(x.float()).to(x.dtype))
+    return x
+
+
 def _small_net(kind):
     torch.manual_seed(0)
     if kind == "bs":
@@ -59,6 +64,7 @@ def test_fused_axial_host_logic_matches_module_path(kind, monkeypatch):
     monkeypatch.setattr(netops, "rmsnorm", ref_rmsnorm)
     monkeypatch.setattr(netops, "rotary_", ref_rotary_)
     monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    monkeypatch.setattr(netops, "gelu_", ref_gelu_)
     net._fused_dtype = torch.float32
     b, t, f = 2, 13, len(net.band_split.dim_inputs)
     x = torch.randn(b, t, f, cfg.dim)
@@ -130,6 +136,20 @@ def test_gate_kernel(cuda):
     ref_gate_(ref, gates, heads, dh)
     netops.gate_sigmoid_(o, gates, heads, dh)
     assert float((o.float() - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [8, 8 * 1001, 16 * 4096 + 8])
+def test_gelu_kernel_is_torch_gelu(cuda, n):
+    import audiolab_b200.netops as netops
+    g = torch.Generator().manual_seed(n)
+    x = (3 * torch.randn(n, generator=g)).to(torch.bfloat16).to(cuda)
+    ref = F.gelu(x)                                     # torch: fp32 inside, erf form, rounded to bf16
+    got = netops.gelu_(x.clone())
+    assert float((got.float() - ref.float()).abs().max()) <= 2 ** -8 * float(ref.float().abs().max())
+    assert float((got.float() - ref.float()).abs().mean()) <= 1e-4
+    with pytest.raises(ValueError):
+        netops.gelu_(torch.zeros(12, dtype=torch.bfloat16, device=cuda))
 
 
 @pytest.mark.gpu
