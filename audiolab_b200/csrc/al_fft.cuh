@@ -114,7 +114,7 @@ template <bool INV> struct SmallDft<6, INV> {
 // per-D launch shape of the generic kernels: G frames per round, UW = G*D/2 unit warps per CTA
 template <int D> struct Cfg;
 template <> struct Cfg<2> { static constexpr int G = 8, UW = 8; };
-template <> struct Cfg<4> { static constexpr int G = 4, UW = 8; };
+template <> struct Cfg<4> { static constexpr int G = 8, UW = 16; };   // 8 frames = one 32-byte sector of a T-innermost row
 template <> struct Cfg<6> { static constexpr int G = 4, UW = 12; };
 
 // ---- spectrogram addressing --------------------------------------------------------------------

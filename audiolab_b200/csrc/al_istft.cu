@@ -14,6 +14,8 @@
 
 namespace al {
 
+constexpr int kOlaKMax = 6;   // frames covering one position in the register form of the overlap-add (n_fft <= 6 hop)
+
 template <int D>
 __global__ void __launch_bounds__(Cfg<D>::UW * 32)
 istft_kernel(const IstftParams p) {
@@ -21,7 +23,7 @@ istft_kernel(const IstftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);     // [1024]
     float2* s_slot = s_tw + 1024;                            // [UW][kSlotF2]
-    float* s_carry = reinterpret_cast<float*>(s_slot + UW * kSlotF2);   // [2][N - hop]
+    float* s_carry = reinterpret_cast<float*>(s_slot + UW * kSlotF2);   // [N - hop], updated in place
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int orow = blockIdx.x / p.segs, seg = blockIdx.x - orow * p.segs;   // orow = (chunk*stems + s)*channels + c
@@ -31,6 +33,7 @@ istft_kernel(const IstftParams p) {
     const long long srow = p.spec_has_stems ? orow : (long long)chunk * p.channels + ch;
     const int hop = p.hop;
     const int carry_len = N - hop;
+    const int ola_k = (N + hop - 1) / hop;              // frames that can cover one position
 
     const SpecView sview{const_cast<float*>(p.spec), p.layout, p.n_frames_in, p.n_bins_in, p.channels};
     const SpecView mview{const_cast<float*>(p.mask), p.layout, p.n_frames_in, N / 2 + 1, p.channels};
@@ -50,26 +53,25 @@ istft_kernel(const IstftParams p) {
                               (long long)chunk * p.dst_chunk_stride + place;
 
     for (int i = tid; i < 1024; i += NT) s_tw[i] = p.tw[i];
-    for (int i = tid; i < 2 * carry_len; i += NT) s_carry[i] = 0.f;
+    for (int i = tid; i < carry_len; i += NT) s_carry[i] = 0.f;
 
     // rounds run past the last frame until the carry has been flushed up to Pb
     const int t_last = (int)((Pb - 1) / hop);
-    int cbuf = 0;
-    for (int tr = ta; tr <= t_last; tr += G, cbuf ^= 1) {
+    for (int tr = ta; tr <= t_last; tr += G) {
         __syncthreads();   // slots free (previous OLA finished), tables visible
         const int nf = max(0, min(G, tb - tr + 1));   // live frames in this round (CTA-uniform)
         if (nf > 0) {
 
         // ---- stage A: load (x mask), Hermitian extension, inverse radix-D -> X_r[kappa] -------------
         const bool t_fast = (p.layout == 1 || p.layout == 2);
-        for (int it = tid; it < G * 513; it += NT) {
-            int f, kappa;
+        // two (frame, kappa) items per iteration: the 2 x D (x 2 planes, x 2 with a mask) loads of both are in
+        // flight before the first butterfly
+        auto sa_load = [&](int it, float2 (&y)[D], int& f, int& kappa) {
             if (t_fast) { kappa = it / G; f = it - kappa * G; }
             else        { f = it / 513;  kappa = it - f * 513; }
             const int t = tr + f;
             const int ts = t - p.frame_pad;
             const bool live = (t <= tb) && ts >= 0 && ts < p.n_frames_in;
-            float2 y[D];
 #pragma unroll
             for (int q = 0; q < D; ++q) {
                 const int k = kappa + 1024 * q;
@@ -83,12 +85,29 @@ istft_kernel(const IstftParams p) {
                 if (k > N / 2) v.y = -v.y;
                 y[q] = v;
             }
+        };
+        auto sa_finish = [&](float2 (&y)[D], int f, int kappa) {
             SmallDft<D, true>::run(y);
             float2* xs = s_slot + (f * HW) * kSlotF2 + kappa;
             xs[0] = y[0];
 #pragma unroll
             for (int r = 1; r < D; ++r)
                 xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
+        };
+        int it = tid;
+        for (; it + NT < G * 513; it += 2 * NT) {
+            float2 ya[D], yb[D];
+            int fa, ka, fb, kb;
+            sa_load(it, ya, fa, ka);
+            sa_load(it + NT, yb, fb, kb);
+            sa_finish(ya, fa, ka);
+            sa_finish(yb, fb, kb);
+        }
+        if (it < G * 513) {
+            float2 ya[D];
+            int fa, ka;
+            sa_load(it, ya, fa, ka);
+            sa_finish(ya, fa, ka);
         }
         __syncthreads();
 
@@ -125,32 +144,98 @@ istft_kernel(const IstftParams p) {
         }  // nf > 0
 
         // ---- overlap-add: span [S, S + G*hop + carry_len), ascending frame order ---------------------
+        // A thread owns offsets j (< hop) and walks the hop-blocks h of the span: position i = h hop + j
+        // receives frame f at sample (h - f) hop + j, f = max(0, h - kj) .. min(nf - 1, h), with
+        // kj = (N - 1 - j) / hop fixed per thread (no per-sample division by the run-time hop).  The
+        // carry is updated in place: carry[(h - G) hop + j] is written after the same thread read it.
         const long long S = (long long)tr * hop;
-        const float* cin = s_carry + cbuf * carry_len;
-        float* cout = s_carry + (cbuf ^ 1) * carry_len;
         const float* frames = reinterpret_cast<const float*>(s_slot);
-        const int span = G * hop + carry_len;
-        for (int i = tid; i < span; i += NT) {
-            float acc = (i < carry_len) ? cin[i] : 0.f;
-            int f_lo = (i - N) / hop + 1;
-            if (i < N) f_lo = 0;
-            const int f_hi = min(nf - 1, i / hop);
-            for (int f = f_lo; f <= f_hi; ++f) {
-                const int j = i - f * hop;   // 0 <= j < N
-                const int w = (j % D) >> 1, n = j / D, c = j & 1;
-                acc += frames[((f * HW + w) * kSlotF2 + n) * 2 + c];
+        const int emit = G * hop;
+        const int span = emit + carry_len;
+        for (int j = tid; j < hop; j += NT) {
+            const int kj = (ola_k - 1) * hop + j < N ? ola_k - 1 : ola_k - 2;
+            // 1 / envelope and chunk weight of the emitted positions: loads issued before their first use
+            float ev[G], wg[G];
+#pragma unroll
+            for (int h = 0; h < G; ++h) {
+                const long long P = S + h * hop + j;
+                const bool mine = P >= Pa && P < Pb;
+                ev[h] = mine ? __ldg(p.inv_env + P) : 0.f;
+                wg[h] = (mine && p.weight) ? __ldg(p.weight + (P - p.out_start)) : 1.f;
             }
-            if (i < G * hop) {
+            if (ola_k <= kOlaKMax) {
+                // Register form (CTA-uniform branch): the thread's G + K - 1 hop-blocks are accumulators; frames are
+                // added in ascending order, frame f feeding blocks f .. f + kj from the same K slot offsets.
+                constexpr int NH = G + kOlaKMax - 1;
+                int idx[kOlaKMax];
+#pragma unroll
+                for (int k = 0; k < kOlaKMax; ++k) {
+                    const int o = k * hop + j;                // sample of the frame that lands on block f + k
+                    idx[k] = (k <= kj) ? ((((o % D) >> 1) * kSlotF2 + o / D) * 2 + (o & 1)) : -1;
+                }
+                float out[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    out[h] = (i < carry_len) ? s_carry[i] : 0.f;
+                }
+#pragma unroll
+                for (int f = 0; f < G; ++f) {
+                    if (f < nf) {
+                        const float* __restrict__ fr = frames + f * (HW * kSlotF2 * 2);
+#pragma unroll
+                        for (int k = 0; k < kOlaKMax; ++k)
+                            if (idx[k] >= 0) out[f + k] += fr[idx[k]];
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    const long long P = S + h * hop + j;
+                    if (P >= Pa && P < Pb) {
+                        const long long pp = P - p.out_start;
+                        float v = out[h] * ev[h];
+                        if (p.weight) v *= wg[h];
+                        const long long q = place + pp;
+                        if (q >= 0 && q < p.dst_limit) dst[pp] = v;
+                    }
+                }
+#pragma unroll
+                for (int h = G; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    if (i < span) s_carry[i - emit] = out[h];
+                }
+                continue;
+            }
+#pragma unroll
+            for (int h = 0; h < G; ++h) {                     // emitted hop-blocks
+                const int i = h * hop + j;
+                float acc = (i < carry_len) ? s_carry[i] : 0.f;
+                const int f_lo = max(0, h - kj);
+                const int f_hi = min(nf - 1, h);
+                int o = (h - f_lo) * hop + j;                 // sample of frame f_lo, 0 <= o < N
+                for (int f = f_lo; f <= f_hi; ++f, o -= hop) {
+                    const int w = (o % D) >> 1, n = o / D, c = o & 1;
+                    acc += frames[((f * HW + w) * kSlotF2 + n) * 2 + c];
+                }
                 const long long P = S + i;
                 if (P >= Pa && P < Pb) {
                     const long long pp = P - p.out_start;
-                    float v = acc * __ldg(p.inv_env + P);
-                    if (p.weight) v *= __ldg(p.weight + pp);
+                    float v = acc * ev[h];
+                    if (p.weight) v *= wg[h];
                     const long long q = place + pp;
                     if (q >= 0 && q < p.dst_limit) dst[pp] = v;
                 }
-            } else {
-                cout[i - G * hop] = acc;
+            }
+            for (int h = G, i = emit + j; i < span; ++h, i += hop) {   // hop-blocks that stay in the carry
+                float acc = (i < carry_len) ? s_carry[i] : 0.f;
+                const int f_lo = max(0, h - kj);
+                const int f_hi = min(nf - 1, h);
+                int o = (h - f_lo) * hop + j;
+                for (int f = f_lo; f <= f_hi; ++f, o -= hop) {
+                    const int w = (o % D) >> 1, n = o / D, c = o & 1;
+                    acc += frames[((f * HW + w) * kSlotF2 + n) * 2 + c];
+                }
+                s_carry[i - emit] = acc;
             }
         }
     }
@@ -169,7 +254,7 @@ static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStrea
     p.hops_per_cta = hpc;
     p.segs = (total_hops + hpc - 1) / hpc;
     const size_t smem = 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) +
-                        2 * (size_t)(N - p.hop) * sizeof(float);
+                        (size_t)(N - p.hop) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -29,6 +29,7 @@ namespace al {
 
 // W = warps = frames per round.  W = 4 (default): two CTAs share an SM, so one's row loads overlap the
 // other's FFT / overlap-add; W = 8: one CTA per SM, half the halo recomputation (AL_IP_WARPS=8 selects it).
+constexpr int kIpKMax = 5;               // frames covering one position in the register form of the overlap-add (hop >= 410)
 constexpr int kIpSmWarps = 8;             // 255 registers per thread: 8 warps fill the register file
 constexpr int kIpN = 2048;
 constexpr int kIpBins = 1025;
@@ -189,7 +190,69 @@ istft_pk2_kernel(const IstftPkParams p) {
         for (int j = tid; j < hop; j += kIpThreads) {
             const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
             const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
-            for (int h = 0, i = j; i < span; ++h, i += hop) {
+            // 1 / envelope and chunk weight of the thread's emitted positions: all loads go out before the
+            // first dependent use (one L2 latency per j instead of one per position)
+            float ev[kIpWarps], wg[kIpWarps];
+#pragma unroll
+            for (int h = 0; h < kIpWarps; ++h) {
+                const long long P = S + h * hop + j;
+                const bool mine = P >= Pa && P < Pb;
+                ev[h] = mine ? __ldg(p.inv_env + P) : 0.f;
+                wg[h] = (mine && p.weight) ? __ldg(p.weight + (P - p.out_start)) : 1.f;
+            }
+            if (kOla_K <= kIpKMax) {
+                // Register form (CTA-uniform branch; hop >= 410): the thread's kIpWarps + K - 1 hop-blocks are
+                // accumulators, frames are added in ascending order f = 0 .. nf - 1, frame f feeding blocks
+                // f .. f + kj.  All indices are compile-time, the W x K loads are independent.
+                constexpr int NH = kIpWarps + kIpKMax - 1;
+                float2 out[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    out[h] = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int f = 0; f < kIpWarps; ++f) {
+                    if (f < nf) {
+                        const float2* __restrict__ sf = sj + f * (2 * kScrF4);
+#pragma unroll
+                        for (int k = 0; k < kIpKMax; ++k) {
+                            if (k <= kj) {
+                                const float2 v = sf[k * hop];
+                                out[f + k].x += v.x;
+                                out[f + k].y += v.y;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < kIpWarps; ++h) {
+                    const long long P = S + h * hop + j;
+                    if (P >= Pa && P < Pb) {
+                        const long long pp = P - p.out_start;
+                        float v0 = out[h].x * ev[h], v1 = out[h].y * ev[h];
+                        if (p.weight) {
+                            v0 *= wg[h];
+                            v1 *= wg[h];
+                        }
+                        const long long qd = place + pp;
+                        if (qd >= 0 && qd < p.dst_limit) {
+                            dst0[pp] = v0;
+                            dst1[pp] = v1;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = kIpWarps; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    if (i < span) cout[i - emit] = out[h];
+                }
+                continue;
+            }
+            // emitted hop-blocks
+#pragma unroll
+            for (int h = 0; h < kIpWarps; ++h) {
+                const int i = h * hop + j;
                 float2 acc = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
                 const int f_lo = max(0, h - kj);
                 const int f_hi = min(nf - 1, h);
@@ -199,26 +262,33 @@ istft_pk2_kernel(const IstftPkParams p) {
                     acc.x += v.x;
                     acc.y += v.y;
                 }
-                if (i < emit) {
-                    const long long P = S + i;
-                    if (P >= Pa && P < Pb) {
-                        const long long pp = P - p.out_start;
-                        const float e = __ldg(p.inv_env + P);
-                        float v0 = acc.x * e, v1 = acc.y * e;
-                        if (p.weight) {
-                            const float wgt = __ldg(p.weight + pp);
-                            v0 *= wgt;
-                            v1 *= wgt;
-                        }
-                        const long long qd = place + pp;
-                        if (qd >= 0 && qd < p.dst_limit) {
-                            dst0[pp] = v0;
-                            dst1[pp] = v1;
-                        }
+                const long long P = S + i;
+                if (P >= Pa && P < Pb) {
+                    const long long pp = P - p.out_start;
+                    float v0 = acc.x * ev[h], v1 = acc.y * ev[h];
+                    if (p.weight) {
+                        v0 *= wg[h];
+                        v1 *= wg[h];
                     }
-                } else {
-                    cout[i - emit] = acc;
+                    const long long qd = place + pp;
+                    if (qd >= 0 && qd < p.dst_limit) {
+                        dst0[pp] = v0;
+                        dst1[pp] = v1;
+                    }
                 }
+            }
+            // hop-blocks that stay in the carry
+            for (int h = kIpWarps, i = emit + j; i < span; ++h, i += hop) {
+                float2 acc = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+                const int f_lo = max(0, h - kj);
+                const int f_hi = min(nf - 1, h);
+                const float2* __restrict__ q = sj + f_lo * fstride + h * hop;
+                for (int f = f_lo; f <= f_hi; ++f, q += fstride) {
+                    const float2 v = *q;
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                cout[i - emit] = acc;
             }
         }
     }

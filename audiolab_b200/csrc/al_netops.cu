@@ -162,30 +162,76 @@ cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int h
 }
 
 // x: [n] bf16, exact (erf) GELU in place -- upstream FeedForward's nn.GELU() between its two Linear layers
-// (SURVEY.md A.4); fp32 inside, like torch's bf16 gelu.  Two 16-byte vectors per thread.
-__global__ void __launch_bounds__(256)
-gelu_bf16_kernel(uint4* __restrict__ x, long long n_vec) {
-    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (i >= n_vec) return;
-    const bool two = i + 1 < n_vec;
-    const uint4 v0 = x[i];
-    const uint4 v1 = two ? x[i + 1] : make_uint4(0u, 0u, 0u, 0u);
-    float a[8], b[8];
-    bf16x8_to_f32(v0, a);
-    bf16x8_to_f32(v1, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a[j] = a[j] * 0.5f * (1.f + erff(a[j] * 0.70710678118654752440f));
-        b[j] = b[j] * 0.5f * (1.f + erff(b[j] * 0.70710678118654752440f));
+// (SURVEY.md A.4).  erff costs ~30 issue slots per element, which makes the straightforward kernel
+// issue-bound at half the HBM rate (profiles/r01d).  A bf16 -> bf16 function has only 65536 inputs: the
+// kernel keeps the whole function as a 128 KB table in shared memory (built once per process with the
+// fp32 formula torch uses, x * 0.5 * (1 + erff(x / sqrt 2)), rounded to bf16), so one element costs one
+// LDS.U16 and the result is the exact formula's for every bit pattern.
+constexpr int kGeluThreads = 1024;
+constexpr int kGeluLutBytes = 65536 * 2;
+
+__global__ void gelu_lut_init_kernel(unsigned short* __restrict__ lut) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536) return;
+    const float x = __uint_as_float((unsigned)i << 16);
+    const float y = x * 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    lut[i] = __bfloat16_as_ushort(__float2bfloat16_rn(y));
+}
+
+__device__ __forceinline__ unsigned gelu_lut2(const unsigned short* __restrict__ t, unsigned v) {
+    return (unsigned)t[v & 0xFFFFu] | ((unsigned)t[v >> 16] << 16);
+}
+
+__global__ void __launch_bounds__(kGeluThreads, 1)
+gelu_bf16_kernel(uint4* __restrict__ x, long long n_vec, const uint4* __restrict__ lut_g) {
+    extern __shared__ __align__(16) unsigned char gelu_smem[];
+    uint4* lut4 = reinterpret_cast<uint4*>(gelu_smem);
+    for (int i = threadIdx.x; i < kGeluLutBytes / 16; i += kGeluThreads) lut4[i] = __ldg(lut_g + i);
+    __syncthreads();
+    const unsigned short* __restrict__ t = reinterpret_cast<const unsigned short*>(gelu_smem);
+    const long long stride = (long long)gridDim.x * kGeluThreads;
+    long long i = (long long)blockIdx.x * kGeluThreads + threadIdx.x;
+    // two vectors per iteration: both loads are in flight before the first lookup
+    for (; i + stride < n_vec; i += 2 * stride) {
+        uint4 a = x[i], b = x[i + stride];
+        a.x = gelu_lut2(t, a.x); a.y = gelu_lut2(t, a.y); a.z = gelu_lut2(t, a.z); a.w = gelu_lut2(t, a.w);
+        b.x = gelu_lut2(t, b.x); b.y = gelu_lut2(t, b.y); b.z = gelu_lut2(t, b.z); b.w = gelu_lut2(t, b.w);
+        x[i] = a;
+        x[i + stride] = b;
     }
-    x[i] = f32_to_bf16x8(a);
-    if (two) x[i + 1] = f32_to_bf16x8(b);
+    if (i < n_vec) {
+        uint4 a = x[i];
+        a.x = gelu_lut2(t, a.x); a.y = gelu_lut2(t, a.y); a.z = gelu_lut2(t, a.z); a.w = gelu_lut2(t, a.w);
+        x[i] = a;
+    }
 }
 
 cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream) {
     const long long n_vec = n / 8;
     if (n_vec <= 0) return cudaSuccess;
-    gelu_bf16_kernel<<<(unsigned)((n_vec + 511) / 512), 256, 0, stream>>>(reinterpret_cast<uint4*>(x), n_vec);
+    static unsigned short* lut = nullptr;
+    static int lut_dev = -1, n_sm = 148;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!lut || lut_dev != dev) {   // once per process (one process per GPU)
+        unsigned short* d = nullptr;
+        e = cudaMalloc((void**)&d, kGeluLutBytes);
+        if (e != cudaSuccess) return e;
+        gelu_lut_init_kernel<<<256, 256, 0, stream>>>(d);
+        e = cudaStreamSynchronize(stream);               // other streams may use the table from now on
+        if (e != cudaSuccess) { cudaFree(d); return e; }
+        e = cudaFuncSetAttribute(gelu_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGeluLutBytes);
+        if (e != cudaSuccess) { cudaFree(d); return e; }
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+        lut = d;
+        lut_dev = dev;
+    }
+    const long long want = (n_vec + kGeluThreads - 1) / kGeluThreads;
+    const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
+    gelu_bf16_kernel<<<grid, kGeluThreads, kGeluLutBytes, stream>>>(reinterpret_cast<uint4*>(x), n_vec,
+                                                                     reinterpret_cast<const uint4*>(lut));
     count_launch();
     return cudaGetLastError();
 }

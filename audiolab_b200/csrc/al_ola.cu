@@ -5,8 +5,8 @@
 // HBM-bound: reads every chunk sample once (4 B) and writes every track sample once.
 // One thread owns four consecutive positions of a row (128-bit loads and stores where the addresses
 // allow it); every position adds its covering chunks in ascending chunk order, so the sum is
-// bit-identical however the chunks were batched or sharded.  The loads of up to four covering chunks
-// are issued before the first dependent add to keep enough bytes in flight per SM.  The weight sum ("counter") is
+// bit-identical however the chunks were batched or sharded.  The covering chunks are walked in groups of
+// four whose 128-bit loads (chunk + weight table) are all issued before the first dependent add.  The weight sum ("counter") is
 // recomputed from the same tables instead of being stored.
 #include "al_kernels.h"
 
@@ -30,14 +30,14 @@ __device__ __forceinline__ void ola_load4(const float* __restrict__ src, unsigne
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                   const long long* __restrict__ offsets, const int* __restrict__ mult,
                   const float* __restrict__ wtab, const int* __restrict__ tab_id, long long n_total,
                   long long p0, long long p1, const float* __restrict__ halo_in, int raw_out, float eps,
                   float scale, float* __restrict__ track, long long track_stride) {
     // the CTA's first position decides where the chunk walk starts (uniform loads, one search per CTA
-    // instead of one per sample); chunks that end before a thread's own positions are masked out below
+    // instead of one per sample); chunks that end before a thread's own positions are skipped below
     const long long pb = p0 + (long long)blockIdx.x * blockDim.x * kOlaVec;
     const long long p = pb + (long long)threadIdx.x * kOlaVec;
     if (p >= p1) return;
@@ -57,53 +57,62 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk
         }
 #pragma unroll
         for (int e = 0; e < kOlaVec; ++e) wsum[e] = 0.f;
+        // covering chunks are consecutive (offsets ascending): walk them in groups of kOlaGroup, issuing every
+        // load of a group before its first dependent add
         for (int c0 = c_first; c0 < n_chunks; c0 += kOlaGroup) {
-            if (__ldg(offsets + c0) > p + (kOlaVec - 1)) break;     // ascending: nothing further covers us
+            if (__ldg(offsets + c0) > p + (kOlaVec - 1)) break;      // ascending: nothing further covers us
             float x[kOlaGroup][kOlaVec], w[kOlaGroup][kOlaVec];
             unsigned msk[kOlaGroup];
             int mm[kOlaGroup];
-            // issue every load of the group before the first dependent add
 #pragma unroll
             for (int g = 0; g < kOlaGroup; ++g) {
                 const int c = c0 + g;
                 msk[g] = 0;
-                mm[g] = 0;
-                if (c < n_chunks) {
-                    const long long off = __ldg(offsets + c);
-                    const long long j = p - off;                                  // may be negative
-                    const long long len = min((long long)chunk_len, n_total - off);
+                mm[g] = 1;
+                if (c >= n_chunks) continue;
+                const long long off = __ldg(offsets + c);
+                const long long j = p - off;                         // may be negative (chunk starts inside the group)
+                const long long len = min((long long)chunk_len, n_total - off);
+                if (off > p + (kOlaVec - 1) || j >= len) continue;   // starts after / ends before this group
+                unsigned m4 = own;
+                if (j < 0 || j + kOlaVec > len) {
 #pragma unroll
                     for (int e = 0; e < kOlaVec; ++e)
-                        if (j + e >= 0 && j + e < len) msk[g] |= 1u << e;
-                    msk[g] &= own;
-                    mm[g] = mult ? __ldg(mult + c) : 1;
+                        if (j + e < 0 || j + e >= len) m4 &= ~(1u << e);
                 }
-                if (msk[g]) {
-                    const int c = c0 + g;
-                    const long long j = p - __ldg(offsets + c);
-                    if (wtab) ola_load4(wtab + (long long)(tab_id ? __ldg(tab_id + c) : 0) * chunk_len + j, msk[g], w[g]);
-                    else {
+                msk[g] = m4;
+                if (mult) mm[g] = __ldg(mult + c);                   // the reference re-adds a tail chunk m times
+                if (wtab) ola_load4(wtab + (long long)(tab_id ? __ldg(tab_id + c) : 0) * chunk_len + j, m4, w[g]);
+                else {
 #pragma unroll
-                        for (int e = 0; e < kOlaVec; ++e) w[g][e] = 1.f;
-                    }
-                    // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive
-                    // through halo_in, only their weights are counted here
-                    if (c >= data_chunk0) ola_load4(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j, msk[g], x[g]);
-                    else {
+                    for (int e = 0; e < kOlaVec; ++e) w[g][e] = 1.f;
+                }
+                // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive through
+                // halo_in, only their weights are counted here
+                if (c >= data_chunk0) ola_load4(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j, m4, x[g]);
+                else {
 #pragma unroll
-                        for (int e = 0; e < kOlaVec; ++e) x[g][e] = 0.f;
-                    }
+                    for (int e = 0; e < kOlaVec; ++e) x[g][e] = 0.f;
                 }
             }
 #pragma unroll
             for (int g = 0; g < kOlaGroup; ++g) {
-                if (!msk[g]) continue;
-                for (int k = 0; k < mm[g]; ++k) {   // the reference re-adds a tail chunk m times; keep its rounding
+                if (msk[g] == 0xFu) {
+                    for (int k = 0; k < mm[g]; ++k) {                // keep the reference's rounding: m separate adds
 #pragma unroll
-                    for (int e = 0; e < kOlaVec; ++e) {
-                        if ((msk[g] >> e) & 1u) {
+                        for (int e = 0; e < kOlaVec; ++e) {
                             acc[e] += x[g][e] * w[g][e];
                             wsum[e] += w[g][e];
+                        }
+                    }
+                } else if (msk[g]) {
+                    for (int k = 0; k < mm[g]; ++k) {
+#pragma unroll
+                        for (int e = 0; e < kOlaVec; ++e) {
+                            if ((msk[g] >> e) & 1u) {
+                                acc[e] += x[g][e] * w[g][e];
+                                wsum[e] += w[g][e];
+                            }
                         }
                     }
                 }

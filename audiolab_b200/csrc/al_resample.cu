@@ -97,13 +97,18 @@ __device__ __forceinline__ void rb_stage(const ResampleRbParams& p, long long ti
     const long long P0 = (tile - (long long)row * p.tiles_per_row) * p.QT;
     const long long x0 = (P0 * p.down + p.s_min) & ~3LL;       // floor to a multiple of 4 (also when negative)
     const float* __restrict__ src = p.in + (long long)row * p.in_stride;
-    for (int v = threadIdx.x * 4; v < p.span; v += kRbThreads * 4) {
-        const long long j = x0 + v;
-        if (p.vec_in && j >= 0 && j + 4 <= p.n_in) {
-            al_cp_async16(xs + v, src + j);
-        } else {
+    if (p.vec_in && x0 >= 0 && x0 + p.span <= p.n_in) {         // interior tile: no bounds checks (CTA-uniform)
+        const float* __restrict__ s4 = src + x0;
+        for (int v = threadIdx.x * 4; v < p.span; v += kRbThreads * 4) al_cp_async16(xs + v, s4 + v);
+    } else {
+        for (int v = threadIdx.x * 4; v < p.span; v += kRbThreads * 4) {
+            const long long j = x0 + v;
+            if (p.vec_in && j >= 0 && j + 4 <= p.n_in) {
+                al_cp_async16(xs + v, src + j);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xs[v + e] = (j + e >= 0 && j + e < p.n_in) ? __ldg(src + j + e) : 0.f;
+                for (int e = 0; e < 4; ++e) xs[v + e] = (j + e >= 0 && j + e < p.n_in) ? __ldg(src + j + e) : 0.f;
+            }
         }
     }
     al_cp_async_commit();
@@ -136,7 +141,16 @@ resample_rb_kernel(const ResampleRbParams p) {
         }
     }
     const int s_g = cb0 - (p.tpp - 1) - p.s_min;              // >= 0
+    // outputs leave through shared memory; round k stores element e_k = (k + rot) & 3 so that the 32 lanes of
+    // a warp hit 32 different banks.  The rotation is a two-stage select network on thread-constant bits.
     const int rot = (g >> 3) & 3;
+    const bool rot1 = rot & 1, rot2 = rot & 2;
+    int so[kRbR];                                              // outs offset of round k, -1 if that residue does not exist
+#pragma unroll
+    for (int k = 0; k < kRbR; ++k) {
+        const int e = (k + rot) & 3;
+        so[k] = (active && r0 + e < p.up) ? r0 + e : -1;
+    }
 
     long long tile = blockIdx.x;
     int buf = 0;
@@ -167,14 +181,13 @@ resample_rb_kernel(const ResampleRbParams p) {
 #pragma unroll
                     for (int e = 0; e < kRbR; ++e) acc[e] += t[e][w] * x[w];
                 }
-                // store element (k + rot) & 3 in round k: 32 lanes hit 32 banks
-                float* __restrict__ o = outs + q * p.up + r0;
+                float b0 = rot1 ? acc[1] : acc[0], b1 = rot1 ? acc[2] : acc[1], b2 = rot1 ? acc[3] : acc[2],
+                      b3 = rot1 ? acc[0] : acc[3];
+                const float c[kRbR] = {rot2 ? b2 : b0, rot2 ? b3 : b1, rot2 ? b0 : b2, rot2 ? b1 : b3};
+                float* __restrict__ o = outs + q * p.up;
 #pragma unroll
-                for (int k = 0; k < kRbR; ++k) {
-                    const int e = (k + rot) & 3;
-                    const float v = e == 0 ? acc[0] : e == 1 ? acc[1] : e == 2 ? acc[2] : acc[3];
-                    if (r0 + e < p.up) o[e] = v;
-                }
+                for (int k = 0; k < kRbR; ++k)
+                    if (so[k] >= 0) o[so[k]] = c[k];
             }
         }
         __syncthreads();
@@ -184,13 +197,10 @@ resample_rb_kernel(const ResampleRbParams p) {
         const int n_valid = (int)(left < (long long)p.QT * p.up ? (left > 0 ? left : 0) : (long long)p.QT * p.up);
         float* __restrict__ dst = p.out + (long long)row * p.out_stride + m0;
         if (p.vec_out) {
-            for (int f = tid * 4; f < n_valid; f += kRbThreads * 4) {
-                if (f + 4 <= n_valid) {
-                    *reinterpret_cast<float4*>(dst + f) = *reinterpret_cast<const float4*>(outs + f);
-                } else {
-                    for (int e = 0; f + e < n_valid; ++e) dst[f + e] = outs[f + e];
-                }
-            }
+            const int n4 = n_valid & ~3;
+            for (int f = tid * 4; f < n4; f += kRbThreads * 4)
+                *reinterpret_cast<float4*>(dst + f) = *reinterpret_cast<const float4*>(outs + f);
+            if (tid < n_valid - n4) dst[n4 + tid] = outs[n4 + tid];
         } else {
             for (int f = tid; f < n_valid; f += kRbThreads) dst[f] = outs[f];
         }

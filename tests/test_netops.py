@@ -139,7 +139,7 @@ def test_gate_kernel(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [8, 8 * 1001, 16 * 4096 + 8])
+@pytest.mark.parametrize("n", [8, 8 * 1001, 16 * 4096 + 8, 8 * 1024 * 148 * 2 + 8 * 77])
 def test_gelu_kernel_is_torch_gelu(cuda, n):
     import audiolab_b200.netops as netops
     g = torch.Generator().manual_seed(n)
@@ -148,6 +148,7 @@ def test_gelu_kernel_is_torch_gelu(cuda, n):
     got = netops.gelu_(x.clone())
     assert float((got.float() - ref.float()).abs().max()) <= 2 ** -8 * float(ref.float().abs().max())
     assert float((got.float() - ref.float()).abs().mean()) <= 1e-4
+    print(f"gelu n={n}: bit-identical to torch.nn.functional.gelu: {torch.equal(got, ref)}")
     with pytest.raises(ValueError):
         netops.gelu_(torch.zeros(12, dtype=torch.bfloat16, device=cuda))
 

@@ -82,6 +82,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--cases", default="")
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--gelu", action="store_true", help="also time the bf16 GELU kernel (RoFormer FeedForward hidden of 5 chunks)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = hbm_peak()
@@ -155,6 +156,17 @@ def main():
         ms = time_it(lambda: sp.resample_poly(x, 147, 160, taps=taps), iters, warm)
         b = x.numel() * 4 + y.numel() * 4
         report("al_resample_poly/48k_to_44k1", b, ms, peak)
+
+    if args.gelu or args.only == "gelu":
+        from audiolab_b200 import netops
+        # in place: refill from h0 before every launch (fresh activations, as in the network) and subtract the refill
+        h0 = torch.randn((5 * 801 * 62, 2048), device=dev, dtype=torch.bfloat16)
+        h = torch.empty_like(h0)
+        import statistics as st
+        ms_copy = st.median(time_it(lambda: h.copy_(h0), iters, warm))
+        ms_both = time_it(lambda: netops.gelu_(h.copy_(h0)), iters, warm)
+        ms = [max(m - ms_copy, 1e-6) for m in ms_both]
+        report("al_gelu_bf16/roformer_ff_hidden", h.numel() * 4, ms, peak, {"refill_ms_subtracted": round(ms_copy, 4)})
 
 
 if __name__ == "__main__":
