@@ -48,7 +48,7 @@ def workload_config(n_gpus: int, mode: str) -> dict:
                     f"{TRACK_SECONDS} s 44.1 kHz synthetic track per GPU (BASELINE.json configs[1])",
         "n_fft": 2048, "hop": 441, "chunk_samples": 352800, "overlap": 4, "track_seconds": TRACK_SECONDS,
         "sharding": ("track-per-GPU" if mode == "tracks" else "chunk-range + NCCL halo exchange") if n_gpus > 1 else "none",
-        "l2_policy": "inputs larger than L2: every step streams 28 chunks x (13 MB spectrum + 13 MB mask) plus "
+        "l2_policy": "inputs larger than L2: every step streams 27 chunks x (13 MB spectrum + 13 MB mask) plus "
                      "~GBs of network activations through the 126 MB L2 between two uses of any buffer",
     }
 
@@ -397,7 +397,11 @@ def run_ours(args) -> None:
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("al_istft_bytes_per_launch")
+            tj = json.load(open(tpath))     # ncu --set full capture of one al_istft launch inside a bench step
+            traffic = tj.get("al_istft_bytes_per_launch")
+            if traffic and k2 and tj.get("chunks_per_launch"):
+                ev = demixer.plan.events["istft"]
+                traffic = traffic / tj["chunks_per_launch"] * (sum(nc for _, _, nc in ev) / len(ev))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -439,7 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="tracks", choices=["tracks", "chunk-range"])
-    ap.add_argument("--batch", type=int, default=9, help="chunks per mask-net call")
+    ap.add_argument("--batch", type=int, default=27, help="chunks per mask-net call (27 = the whole 60 s track)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--track-seconds", type=int, default=0,
                     help="with --profile-mode only: length of the synthetic track (bounds the ncu launch list)")
