@@ -47,6 +47,13 @@ istft_kernel(const IstftParams p) {
     if (Pa < N) ta = 0;
     ta = max(ta, 0);
     const int tb = min((int)((Pb - 1) / hop), p.n_frames_total - 1);   // last frame touching Pb-1
+    // T-innermost planes (AL_LAYOUT_CAC): four consecutive frames of one bin are one aligned 16-byte load when the
+    // rounds start on a multiple of 4 frames of the stored spectrogram.  The first round may then start up to 3
+    // frames early (even below frame 0): those frames end before Pa or do not exist, so they add nothing to the
+    // owned samples and the ascending-frame order of every emitted sample is unchanged.
+    const bool vec4 = p.layout == 2 && !p.mask && (G % 4) == 0 && (p.n_frames_in & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.spec) & 15) == 0;
+    if (vec4) ta -= (((ta - p.frame_pad) % 4) + 4) % 4;
 
     const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
     float* __restrict__ dst = p.dst + ((long long)stem * p.channels + ch) * p.dst_ch_stride +
@@ -64,6 +71,53 @@ istft_kernel(const IstftParams p) {
 
         // ---- stage A: load (x mask), Hermitian extension, inverse radix-D -> X_r[kappa] -------------
         const bool t_fast = (p.layout == 1 || p.layout == 2);
+        if (vec4) {
+            // item = (kappa, 4 frames): 2 x D aligned 128-bit loads (re / im plane of each of the D bins), all in
+            // flight before the first butterfly; then one radix-D butterfly per frame
+            constexpr int GV = G / 4 > 0 ? G / 4 : 1;
+            const long long plane = (long long)p.n_bins_in * p.n_frames_in;
+            const float* __restrict__ rowp = p.spec + srow * 2 * plane;
+            for (int it = tid; it < GV * 513; it += NT) {
+                const int kappa = it / GV, gq = it - kappa * GV;
+                const int t0 = tr + 4 * gq, ts0 = t0 - p.frame_pad;          // ts0 is a multiple of 4
+                const bool any = t0 <= tb && ts0 >= 0 && ts0 < p.n_frames_in;
+                float4 re4[D], im4[D];
+#pragma unroll
+                for (int q = 0; q < D; ++q) {
+                    const int k = kappa + 1024 * q;
+                    const int bin = (k <= N / 2) ? k : N - k;
+                    re4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    im4[q] = re4[q];
+                    if (any && bin < p.n_bins_in && bin >= p.zero_low_bins) {
+                        const float* __restrict__ src = rowp + (long long)bin * p.n_frames_in + ts0;
+                        re4[q] = __ldg(reinterpret_cast<const float4*>(src));
+                        im4[q] = __ldg(reinterpret_cast<const float4*>(src + plane));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 y[D];
+#pragma unroll
+                    for (int q = 0; q < D; ++q) {
+                        const int k = kappa + 1024 * q;
+                        const int bin = (k <= N / 2) ? k : N - k;
+                        float2 v;
+                        v.x = e == 0 ? re4[q].x : e == 1 ? re4[q].y : e == 2 ? re4[q].z : re4[q].w;
+                        v.y = e == 0 ? im4[q].x : e == 1 ? im4[q].y : e == 2 ? im4[q].z : im4[q].w;
+                        if (t0 + e > tb) v = make_float2(0.f, 0.f);          // like the scalar path: frames past tb are empty
+                        if (bin == 0 || bin == N / 2) v.y = 0.f;             // C2R ignores Im of DC / Nyquist
+                        if (k > N / 2) v.y = -v.y;
+                        y[q] = v;
+                    }
+                    SmallDft<D, true>::run(y);
+                    float2* xs = s_slot + ((4 * gq + e) * HW) * kSlotF2 + kappa;
+                    xs[0] = y[0];
+#pragma unroll
+                    for (int r = 1; r < D; ++r)
+                        xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
+                }
+            }
+        } else {
         // two (frame, kappa) items per iteration: the 2 x D (x 2 planes, x 2 with a mask) loads of both are in
         // flight before the first butterfly
         auto sa_load = [&](int it, float2 (&y)[D], int& f, int& kappa) {
@@ -109,6 +163,7 @@ istft_kernel(const IstftParams p) {
             sa_load(it, ya, fa, ka);
             sa_finish(ya, fa, ka);
         }
+        }  // scalar stage A
         __syncthreads();
 
         // ---- unit inverse FFT: warp = (frame f, pair w) ----------------------------------------------

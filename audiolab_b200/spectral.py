@@ -158,6 +158,9 @@ def ola_gather(chunks: torch.Tensor, offsets: torch.Tensor, n_total: int, *,
                data_chunk0: int = 0,
                scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """chunks [n_chunks - data_chunk0, rows, chunk_len] -> track [rows, n_total] (positions [p0, p1) written)."""
+    shift, windowed = 0, False
+    if out is not None and hasattr(out, "buf"):          # sharding._ShiftedOut: [rows, p1-p0] window of the track
+        shift, out, windowed = int(out.shift), out.buf, True
     _need_cuda(chunks, offsets, mult, wtab, tab_id, halo_in, out)
     if chunks.dtype != torch.float32 or chunks.dim() != 3 or not chunks.is_contiguous():
         raise ValueError("chunks must be contiguous fp32 [n_chunks, rows, chunk_len]")
@@ -175,11 +178,8 @@ def ola_gather(chunks: torch.Tensor, offsets: torch.Tensor, n_total: int, *,
     if halo_in is not None and (halo_in.dtype != torch.float32 or halo_in.numel() != rows * (p1 - p0)
                                 or not halo_in.is_contiguous()):
         raise ValueError("halo_in must be contiguous fp32 [rows, p1-p0]")
-    shift = 0
-    if out is not None and hasattr(out, "buf"):          # sharding._ShiftedOut: [rows, p1-p0] window of the track
-        shift, out = int(out.shift), out.buf
-        if out.shape[1] < p1 - shift:
-            raise ValueError("shifted out buffer too small")
+    if windowed and out.shape[1] < p1 - shift:
+        raise ValueError("shifted out buffer too small")
     if out is None:
         out = torch.zeros((rows, n_total), dtype=torch.float32, device=chunks.device)
     elif out.dtype != torch.float32 or out.dim() != 2 or out.shape[0] != rows or out.stride(1) != 1:

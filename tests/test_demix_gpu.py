@@ -225,3 +225,15 @@ def test_separate_process_audio_end_to_end(cuda, tmp_path, monkeypatch):
     assert outs == ["track_(Instrumental).wav", "track_(Vocals).wav"]
     v, sr = read_wav(res[0].last_outputs[0])
     assert sr == 44100 and v.shape == (2, 88200) and np.isfinite(v).all() and np.abs(v).max() <= 1.0 + 1e-6
+
+
+def test_sharded_roformer_single_rank_equals_demix(cuda):
+    """ShardedRoformerDemixer at world_size 1 (no process group needed): the owned span is the whole track and goes
+    through the same windowed ola_gather call the multi-rank path uses (tools/nccl_shard_check.py is the NCCL twin)."""
+    from audiolab_b200.sharding import ShardedRoformerDemixer
+    oc, om, d = _roformer_pair("bs", cuda)
+    mix = torch.tensor(synth_mix(oc.chunk_size * 2 + 777, seed=5)).to(cuda)
+    span, cr = ShardedRoformerDemixer(d, 0, 1).demix_span(mix)
+    ref = d.demix(mix)
+    assert (cr.p0, cr.p1) == (0, mix.shape[1])
+    assert max_abs_err(span.cpu(), ref.reshape(span.shape).cpu()) <= 1e-6

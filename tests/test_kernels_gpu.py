@@ -234,6 +234,29 @@ def test_istft_frame_pad_and_crop_like_htdemucs(cuda):
     assert max_abs_err(got[0, 0], ref[0]) <= WAVE_ATOL
 
 
+@pytest.mark.parametrize("n_fft,hop,T,frame_pad", [(4096, 1024, 64, 0), (4096, 1024, 336, 2), (6144, 1024, 256, 0),
+                                                  (6144, 1024, 20, 2), (2048, 441, 80, 0), (2048, 512, 40, 1)])
+def test_istft_cac_vector_path_equals_bin_major_bitwise(cuda, n_fft, hop, T, frame_pad):
+    """AL_LAYOUT_CAC with T % 4 == 0 takes the 128-bit stage-A loads (rounds re-aligned to 4 stored frames); the
+    result must equal the c64 [rows, F, T] layout bit for bit -- same frames, same ascending sum order -- and
+    torch.istft within tolerance.  Several segments per row (16 hops each), cropped frequency rows."""
+    from audiolab_b200 import spectral as sp
+    F = n_fft // 2 + 1
+    Fo = F - 1 if frame_pad else F                                  # HTDemucs drops the Nyquist row
+    S = torch.view_as_complex(torch.tensor(synth_noise((2, Fo, T, 2), seed=n_fft + T)))
+    Sfull = torch.zeros((2, F, T + 2 * frame_pad), dtype=S.dtype)
+    Sfull[:, :Fo, frame_pad:frame_pad + T] = S
+    ref = torch.istft(Sfull, n_fft, hop, window=torch.hann_window(n_fft), center=True)
+    plan = _plan(n_fft, hop)
+    out_len = ref.shape[-1]
+    a = plan.istft(S.contiguous().to(cuda), n_chunks=1, channels=2, layout=sp.BIN_MAJOR, frame_pad=frame_pad,
+                   out_len=out_len).cpu()
+    cac = torch.stack((S.real, S.imag), dim=1).reshape(1, 4, Fo, T).contiguous()   # [chunks, (ch, re/im), F, T]
+    b = plan.istft(cac.to(cuda), n_chunks=1, channels=2, layout=sp.CAC, frame_pad=frame_pad, out_len=out_len).cpu()
+    assert max_abs_err(a[0, 0], ref) <= WAVE_ATOL * max(1.0, float(ref.abs().max()))
+    assert torch.equal(a, b)
+
+
 def test_ola_gather_matches_numpy_and_is_bitwise_shardable(cuda):
     from audiolab_b200 import spectral as sp
     rs = np.random.RandomState(0)

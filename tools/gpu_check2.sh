@@ -1,0 +1,8 @@
+#!/bin/bash
+# Short validation call: GPU tests, kernel roofline, default bench line.
+TAG=${1:-chk}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest -m gpu" ; timeout 300 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1 ; echo "rc=$?" ; tail -15 $OUT/pytest_gpu.log
+echo "== kernel_bench" ; timeout 150 python tools/kernel_bench.py > $OUT/kernel_bench.jsonl 2> $OUT/kernel_bench.err ; echo "rc=$?" ; cat $OUT/kernel_bench.jsonl ; tail -3 $OUT/kernel_bench.err
+echo "== bench" ; timeout 300 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; echo "rc=$?" ; cat $OUT/bench.json ; tail -5 $OUT/bench.err
