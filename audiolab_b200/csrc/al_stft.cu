@@ -85,6 +85,57 @@ stft_kernel(const StftParams p) {
 
         // ---- radix-D combine + store ----------------------------------------------------------------
         const bool t_fast = (p.layout == 1 || p.layout == 2);
+        // T-innermost planes (AL_LAYOUT_CAC): a thread combines 4 consecutive frames of one kappa and writes each of
+        // its 2 x D plane rows as one aligned 16-byte store (t0 is a multiple of G, rows are 16-byte aligned)
+        const bool vec4 = p.layout == 2 && (G % 4) == 0 && (p.n_frames & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.spec) & 15) == 0;
+        if (vec4) {
+            constexpr int GV = G / 4 > 0 ? G / 4 : 1;
+            const long long plane = (long long)p.n_bins_out * p.n_frames;
+            float* __restrict__ rowp = p.spec + (long long)row * 2 * plane;
+            for (int it = tid; it < GV * 513; it += NT) {
+                const int kappa = it / GV, gq = it - kappa * GV;
+                const int t = t0 + 4 * gq;
+                if (t >= p.n_frames) continue;                 // n_frames % 4 == 0: all four frames in or out
+                float re4[D][4], im4[D][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2* xs = s_slot + ((4 * gq + e) * HW) * kSlotF2 + kappa;
+                    float2 y[D];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) y[r] = xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf];
+#pragma unroll
+                    for (int r = 1; r < D; ++r) y[r] = cmul(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
+                    SmallDft<D, false>::run(y);
+#pragma unroll
+                    for (int q = 0; q < D; ++q) {
+                        re4[q][e] = y[q].x;
+                        im4[q][e] = y[q].y;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < D; ++q) {
+                    const int k = kappa + 1024 * q;
+                    int bin;
+                    float sgn = 1.f;
+                    if (k <= N / 2) {
+                        bin = k;
+                    } else {
+                        if (kappa == 0 || kappa == 512) continue;   // duplicates of directly produced bins
+                        bin = N - k;
+                        sgn = -1.f;
+                    }
+                    if (bin >= p.n_bins_out) continue;
+                    float4 vr = make_float4(re4[q][0], re4[q][1], re4[q][2], re4[q][3]);
+                    float4 vi = make_float4(sgn * im4[q][0], sgn * im4[q][1], sgn * im4[q][2], sgn * im4[q][3]);
+                    if (bin < p.zero_low_bins) vr = vi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* dstp = rowp + (long long)bin * p.n_frames + t;
+                    *reinterpret_cast<float4*>(dstp) = vr;
+                    *reinterpret_cast<float4*>(dstp + plane) = vi;
+                }
+            }
+            continue;
+        }
         for (int it = tid; it < G * 513; it += NT) {
             int f, kappa;
             if (t_fast) { kappa = it / G; f = it - kappa * G; }

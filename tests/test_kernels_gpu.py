@@ -234,6 +234,25 @@ def test_istft_frame_pad_and_crop_like_htdemucs(cuda):
     assert max_abs_err(got[0, 0], ref[0]) <= WAVE_ATOL
 
 
+@pytest.mark.parametrize("n_fft,hop,T,crop,low", [(4096, 1024, 24, 2048, 0), (6144, 1024, 16, 3072, 3), (2048, 441, 40, 1025, 0),
+                                                 (6144, 1024, 256, 3072, 0)])
+def test_stft_cac_vector_stores_equal_bin_major_bitwise(cuda, n_fft, hop, T, crop, low):
+    """AL_LAYOUT_CAC with n_frames % 4 == 0 writes 128-bit rows; the values must be those of the c64 [rows, F, T]
+    layout bit for bit (cropped frequency rows, zeroed low bins, two chunks)."""
+    from audiolab_b200 import spectral as sp
+    L = (T - 1) * hop
+    x = torch.tensor(synth_mix(2 * L, seed=T)).to(cuda)
+    kw = dict(chunk_len=L, n_chunks=2, off0=0, off_step=L, n_frames=T, n_bins_out=crop, zero_low_bins=low)
+    plan = _plan(n_fft, hop)
+    a = plan.stft(x, layout=sp.BIN_MAJOR, **kw)                       # c64 [chunks*2, crop, T]
+    b = plan.stft(x, layout=sp.CAC, **kw)                             # f32 [chunks, 4, crop, T]
+    a4 = torch.view_as_real(a).reshape(2, 2, crop, T, 2).permute(0, 1, 4, 2, 3).reshape(2, 4, crop, T)
+    assert torch.equal(a4, b.reshape(2, 4, crop, T))
+    ref = _torch_stft(x[:, :L].cpu(), n_fft, hop, False)[:, :crop]    # chunk 0 alone (reflect pad at both chunk ends)
+    ref[:, :low] = 0
+    assert rel_err(a.reshape(2, 2, crop, T)[0].cpu(), ref) <= SPEC_RTOL
+
+
 @pytest.mark.parametrize("n_fft,hop,T,frame_pad", [(4096, 1024, 64, 0), (4096, 1024, 336, 2), (6144, 1024, 256, 0),
                                                   (6144, 1024, 20, 2), (2048, 441, 80, 0), (2048, 512, 40, 1)])
 def test_istft_cac_vector_path_equals_bin_major_bitwise(cuda, n_fft, hop, T, frame_pad):
