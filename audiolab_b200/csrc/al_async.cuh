@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#define AL_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw[]; T* name = reinterpret_cast<T*>(name##_raw)
+#ifndef AL_DYN_SMEM
+#define AL_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* name = reinterpret_cast<T*>(name##_raw_)
+#endif
 
 namespace al {
 

@@ -14,13 +14,14 @@
 
 namespace al {
 
+// [emul-begin]
 constexpr int kOlaKMax = 6;   // frames covering one position in the register form of the overlap-add (n_fft <= 6 hop)
 
 template <int D>
 __global__ void __launch_bounds__(Cfg<D>::UW * 32)
 istft_kernel(const IstftParams p) {
     constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, NT = UW * 32, N = D * 1024, HW = D / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);     // [1024]
     float2* s_slot = s_tw + 1024;                            // [UW][kSlotF2]
     float* s_carry = reinterpret_cast<float*>(s_slot + UW * kSlotF2);   // [N - hop], updated in place
@@ -296,20 +297,27 @@ istft_kernel(const IstftParams p) {
     }
 }
 
+// launch shape of istft_kernel<D>: fills hops_per_cta / segs, returns the dynamic shared memory size
 template <int D>
-static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStream_t stream) {
+static size_t istft_tiling(IstftParams& p, int rows) {
     constexpr int UW = Cfg<D>::UW, N = D * 1024;
-    IstftParams p = p0;
-    const int rows = n_chunks * p.stems * p.channels;
     const int total_hops = (p.out_len + p.hop - 1) / p.hop;
     // enough CTAs for ~4 waves over 148 SMs, but segments no shorter than 16 hops (halo <= ~30 %)
     int segs = (4 * 148 + rows - 1) / rows;
     int hpc = (total_hops + segs - 1) / segs;
-    hpc = max(hpc, 16);
+    hpc = hpc > 16 ? hpc : 16;
     p.hops_per_cta = hpc;
     p.segs = (total_hops + hpc - 1) / hpc;
-    const size_t smem = 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) +
-                        (size_t)(N - p.hop) * sizeof(float);
+    return 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)(N - p.hop) * sizeof(float);
+}
+// [emul-end]
+
+template <int D>
+static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStream_t stream) {
+    constexpr int UW = Cfg<D>::UW;
+    IstftParams p = p0;
+    const int rows = n_chunks * p.stems * p.channels;
+    const size_t smem = istft_tiling<D>(p, rows);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -5,9 +5,13 @@
 
 #include "al_fft.cuh"
 
+#define AL_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* name = reinterpret_cast<T*>(name##_raw_)
+
 namespace al {
 
 void count_launch();
+
+// [emul-begin]
 
 struct StftParams {
     const float* track;
@@ -61,6 +65,8 @@ struct IstftParams {
     int hops_per_cta;
     int segs;
 };
+
+// [emul-end]
 
 // stereo / n_fft 2048 / bin-innermost fast path (al_stft_pk.cu)
 struct StftPkParams {

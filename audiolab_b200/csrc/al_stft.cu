@@ -11,11 +11,12 @@
 
 namespace al {
 
+// [emul-begin]
 template <int D>
 __global__ void __launch_bounds__(Cfg<D>::UW * 32)
 stft_kernel(const StftParams p) {
     constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, NT = UW * 32, N = D * 1024, HW = D / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);             // [1024]
     float2* s_slot = s_tw + 1024;                                    // [UW][kSlotF2]
     float* s_stage = reinterpret_cast<float*>(s_slot + UW * kSlotF2);  // [D][ps]
@@ -169,14 +170,24 @@ stft_kernel(const StftParams p) {
     }
 }
 
+// launch shape of stft_kernel<D>: fills ps / rounds_per_cta / tiles, returns the dynamic shared memory size
 template <int D>
-static cudaError_t launch_stft_d(const StftParams& p0, int rows, cudaStream_t stream) {
+static size_t stft_tiling(StftParams& p) {
     constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, N = D * 1024;
-    StftParams p = p0;
     const int span = (G - 1) * p.hop + N;
     p.ps = ((span + D - 1) / D + 31) / 32 * 32 + 32 / D;
     p.rounds_per_cta = (D == 2) ? 1 : 2;
-    const size_t smem = 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)D * p.ps * sizeof(float);
+    const int frames_per_cta = G * p.rounds_per_cta;
+    p.tiles = (p.n_frames + frames_per_cta - 1) / frames_per_cta;
+    return 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)D * p.ps * sizeof(float);
+}
+// [emul-end]
+
+template <int D>
+static cudaError_t launch_stft_d(const StftParams& p0, int rows, cudaStream_t stream) {
+    constexpr int UW = Cfg<D>::UW;
+    StftParams p = p0;
+    const size_t smem = stft_tiling<D>(p);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(stft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -184,8 +195,6 @@ static cudaError_t launch_stft_d(const StftParams& p0, int rows, cudaStream_t st
         attr_set = true;
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    const int frames_per_cta = G * p.rounds_per_cta;
-    p.tiles = (p.n_frames + frames_per_cta - 1) / frames_per_cta;
     stft_kernel<D><<<(unsigned)(rows * p.tiles), UW * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError();

@@ -282,6 +282,7 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     sep = Separator(log_level=40, allow_random_init=True, use_autocast=True, device=str(dev),
@@ -382,8 +383,8 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e2e_val = audio_s_total * args.steps / e2e_s
-        h2d = mix_host.numel() * 4
-        d2h = 2 * 2 * n * 4
+        h2d = mix_host.numel() * 4 * world          # whole job: every rank copies its own track in and both stems out
+        d2h = 2 * 2 * n * 4 * world
     else:
         e2e_val, h2d, d2h = None, 0, 0
 

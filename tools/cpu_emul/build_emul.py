@@ -1,6 +1,7 @@
-"""Builds tools/cpu_emul/_emul.so: the [emul-begin]..[emul-end] regions of the index-logic kernels
-(al_ola.cu, al_resample.cu) compiled for the host on top of cuda_emul.h, so their addressing, masking
-and tiling can be checked on a box without a GPU (tests/test_kernel_emulation.py).  Test infrastructure."""
+"""Builds tools/cpu_emul/_emul.so: the [emul-begin]..[emul-end] regions of the kernels that use only CTA / warp
+barriers and shuffles (al_ola.cu, al_resample.cu, and the generic al_stft.cu / al_istft.cu with al_fft.cuh and the
+generated 32-point FFT) compiled for the host on top of cuda_emul.h, so their addressing, masking, tiling and
+arithmetic can be checked on a box without a GPU (tests/test_kernel_emulation.py).  Test infrastructure."""
 import os
 import re
 import subprocess
@@ -10,6 +11,67 @@ CSRC = os.path.join(HERE, "..", "..", "audiolab_b200", "csrc")
 SO = os.path.join(HERE, "_emul.so")
 
 GLUE = r'''
+using namespace al;
+
+template <int D>
+static int emul_stft_d(StftParams p, int rows) {
+    const size_t smem = stft_tiling<D>(p);
+    if (smem > sizeof(g_smem)) return -2;
+    std::memset(g_smem, 0xFF, sizeof(g_smem));
+    emul_launch(dim3(rows * p.tiles), dim3(Cfg<D>::UW * 32), [&] { stft_kernel<D>(p); });
+    return 0;
+}
+
+extern "C" int emul_stft(int n_fft, int hop, const float* track, long long n_valid, long long ch_stride, int channels,
+                         long long off0, long long off_step, int n_chunks, int chunk_len, int center, int n_frames,
+                         const float* window, const float* tw, const float* ctw, float* spec, int layout,
+                         int n_bins_out, int zero_low_bins) {
+    StftParams p{};
+    p.track = track; p.n_valid = n_valid; p.ch_stride = ch_stride; p.channels = channels; p.chunk_offsets = nullptr;
+    p.off0 = off0; p.off_step = off_step; p.chunk_len = chunk_len; p.center = center; p.hop = hop; p.n_frames = n_frames;
+    p.window = window; p.tw = reinterpret_cast<const float2*>(tw); p.ctw = reinterpret_cast<const float2*>(ctw);
+    p.spec = spec; p.layout = layout; p.n_bins_out = n_bins_out; p.zero_low_bins = zero_low_bins;
+    const int rows = n_chunks * channels;
+    switch (n_fft) {
+        case 2048: return emul_stft_d<2>(p, rows);
+        case 4096: return emul_stft_d<4>(p, rows);
+        case 6144: return emul_stft_d<6>(p, rows);
+    }
+    return -1;
+}
+
+template <int D>
+static int emul_istft_d(IstftParams p, int n_chunks) {
+    const int rows = n_chunks * p.stems * p.channels;
+    const size_t smem = istft_tiling<D>(p, rows);
+    if (smem > sizeof(g_smem)) return -2;
+    std::memset(g_smem, 0xFF, sizeof(g_smem));
+    emul_launch(dim3(rows * p.segs), dim3(Cfg<D>::UW * 32), [&] { istft_kernel<D>(p); });
+    return p.segs;
+}
+
+extern "C" int emul_istft(int n_fft, int hop, const float* spec, const float* mask, int layout, int n_bins_in,
+                          int n_frames_in, int frame_pad, int n_chunks, int stems, int channels, int spec_has_stems,
+                          int zero_low_bins, const float* window, const float* tw, const float* ctw,
+                          const float* inv_env, int out_start, int out_len, const float* weight, float* dst,
+                          long long dst_ch_stride, long long dst_chunk_stride, long long dst_off0,
+                          long long dst_off_step, long long dst_limit) {
+    IstftParams p{};
+    p.spec = spec; p.mask = mask; p.layout = layout; p.n_bins_in = n_bins_in; p.n_frames_in = n_frames_in;
+    p.frame_pad = frame_pad; p.n_frames_total = n_frames_in + 2 * frame_pad; p.stems = stems; p.channels = channels;
+    p.spec_has_stems = spec_has_stems; p.zero_low_bins = zero_low_bins; p.hop = hop; p.window = window;
+    p.tw = reinterpret_cast<const float2*>(tw); p.ctw = reinterpret_cast<const float2*>(ctw); p.inv_env = inv_env;
+    p.out_start = out_start; p.out_len = out_len; p.weight = weight; p.dst = dst; p.dst_ch_stride = dst_ch_stride;
+    p.dst_chunk_stride = dst_chunk_stride; p.dst_offsets = nullptr; p.dst_off0 = dst_off0; p.dst_off_step = dst_off_step;
+    p.dst_limit = dst_limit;
+    switch (n_fft) {
+        case 2048: return emul_istft_d<2>(p, n_chunks);
+        case 4096: return emul_istft_d<4>(p, n_chunks);
+        case 6144: return emul_istft_d<6>(p, n_chunks);
+    }
+    return -1;
+}
+
 extern "C" void emul_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                                 const long long* offsets, const int* mult, const float* wtab, const int* tab_id,
                                 long long n_total, long long p0, long long p1, const float* halo_in, int raw_out,
@@ -45,15 +107,21 @@ def region(path):
 
 
 def build(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("al_ola.cu", "al_resample.cu")]
-    deps = srcs + [os.path.join(HERE, "cuda_emul.h"), __file__]
+    srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu")]
+    whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh")]       # no launch syntax: taken whole
+    deps = srcs + whole + [os.path.join(HERE, "cuda_emul.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):
         return SO
     gen = os.path.join(HERE, "_emul_gen.cpp")
     with open(gen, "w") as f:
         f.write('#include "cuda_emul.h"\n')
+        for w in whole:
+            body = re.sub(r'^#(pragma once|include .*)$', "", open(w).read(), flags=re.M)
+            f.write(f"// ---- {os.path.basename(w)}\n" + body + "\n")
+        f.write("namespace al {\n")
         for s in srcs:
             f.write(f"// ---- from {os.path.basename(s)}\n" + region(s) + "\n")
+        f.write("}  // namespace al\n")
         f.write(GLUE)
     subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread",
                     "-I", HERE, "-o", SO, gen], check=True)

@@ -1,4 +1,4 @@
-// Minimal host emulation of the CUDA execution model for the index-logic kernels (no warp intrinsics):
+// Minimal host emulation of the CUDA execution model (CTA barrier, warp barrier, warp shuffle; no tensor ops):
 // one std::thread per CUDA thread, CTAs run one after another, __syncthreads() = std::barrier.
 // Test infrastructure only (tests/test_kernel_emulation.py); never part of the product.
 #pragma once
@@ -14,7 +14,11 @@
 
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+typedef int cudaError_t;
+typedef void* cudaStream_t;
 static thread_local dim3 threadIdx, blockIdx;
 static dim3 blockDim, gridDim;
 #define __global__
@@ -27,6 +31,21 @@ using std::max;
 using std::min;
 static std::barrier<>* g_bar = nullptr;
 static inline void __syncthreads() { g_bar->arrive_and_wait(); }
+// warp-level primitives: one barrier and one 32-word exchange buffer per warp of the running CTA
+static std::vector<std::barrier<>*> g_warp_bar;
+static unsigned g_shfl[64][32];
+static inline void __syncwarp(unsigned = 0xffffffffu) { g_warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "4-byte shuffles only");
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    std::memcpy(&g_shfl[w][l], &v, 4);
+    g_warp_bar[w]->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &g_shfl[w][src & 31], 4);
+    g_warp_bar[w]->arrive_and_wait();
+    return r;
+}
 alignas(16) static unsigned char g_smem[228 * 1024];
 #define AL_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(g_smem)
 static inline void al_cp_async16(void* d, const void* s) { std::memcpy(d, s, 16); }
@@ -41,6 +60,10 @@ static void emul_launch(dim3 grid, dim3 block, F f) {
         for (unsigned bx = 0; bx < grid.x; ++bx) {
             std::barrier<> bar(block.x);
             g_bar = &bar;
+            for (auto* b : g_warp_bar) delete b;
+            g_warp_bar.clear();
+            for (unsigned w = 0; w * 32 < block.x; ++w)
+                g_warp_bar.push_back(new std::barrier<>(std::min(32u, block.x - w * 32)));
             std::vector<std::thread> th;
             for (unsigned t = 0; t < block.x; ++t)
                 th.emplace_back([=, &f] {
