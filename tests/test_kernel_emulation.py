@@ -102,3 +102,89 @@ def test_resample_rb_emulated_matches_scipy(emul, up, down, n_in, rows, grid):
         assert rc == (3 if pad == 0 else 0)
         assert np.abs(out[:, :n_out] - ref).max() <= 2e-6
         assert (out[:, n_out:] == -77.0).all()                       # nothing written past n_out
+
+
+# ---- generic STFT / iSTFT kernels (al_stft.cu / al_istft.cu + al_fft.cuh), emulated with warp barriers + shuffles ------
+def _plan_tables(n_fft, hop, T_total=None):
+    """The tables al_plan_create / env_kernel build (audiolab_b200/csrc/al_capi.cu:60-120, al_istft.cu env_kernel)."""
+    N, D = n_fft, n_fft // 1024
+    i = np.arange(N)
+    raw = (0.5 - 0.5 * np.cos(2.0 * np.pi * i / N)).astype(np.float32)
+    wa = raw.copy()
+    ws = (raw.astype(np.float64) / N).astype(np.float32)
+    k1, n2 = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
+    a = -2.0 * np.pi * (k1 * n2) / 1024.0
+    tw = np.stack((np.cos(a), np.sin(a)), axis=-1).astype(np.float32).reshape(1024, 2)
+    r, k = np.meshgrid(np.arange(1, D), np.arange(513), indexing="ij")
+    a = -2.0 * np.pi * r * k / N
+    ctw = np.stack((np.cos(a), np.sin(a)), axis=-1).astype(np.float32).reshape(-1, 2)
+    env = None
+    if T_total is not None:
+        total = (T_total - 1) * hop + N
+        acc = np.zeros(total, np.float64)
+        for t in range(T_total):
+            acc[t * hop:t * hop + N] += raw.astype(np.float64) ** 2
+        env = np.where(acc > 1e-11, 1.0 / np.maximum(acc, 1e-30), 0.0).astype(np.float32)
+    return wa, ws, np.ascontiguousarray(tw), np.ascontiguousarray(ctw), env
+
+
+def _bind_fft(lib):
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    lib.emul_stft.argtypes = [I, I, P, LL, LL, I, LL, LL, I, I, I, I, P, P, P, P, I, I, I]
+    lib.emul_stft.restype = I
+    lib.emul_istft.argtypes = [I, I, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL]
+    lib.emul_istft.restype = I
+
+
+@pytest.mark.parametrize("n_fft,hop,T,layout", [(2048, 441, 9, 1), (4096, 1024, 8, 2), (6144, 1024, 8, 2), (4096, 1024, 7, 2),
+                                               (6144, 1024, 5, 0)])
+def test_generic_stft_emulated_matches_torch(emul, n_fft, hop, T, layout):
+    """layout 0: c64 [rows, T, F]; 1: c64 [rows, F, T]; 2: CaC planes (T % 4 == 0 takes the 128-bit row stores)."""
+    import torch
+    _bind_fft(emul)
+    L = (T - 1) * hop
+    rs = np.random.RandomState(T + n_fft)
+    x = rs.uniform(-1, 1, size=(2, L)).astype(np.float32)
+    F = n_fft // 2 + 1
+    ref = torch.stft(torch.tensor(x), n_fft, hop, window=torch.hann_window(n_fft), center=True, return_complex=True)
+    ref = torch.view_as_real(ref).numpy()                                    # [2, F, T, 2]
+    wa, _, tw, ctw, _ = _plan_tables(n_fft, hop)
+    spec = np.full((2, F, T, 2), np.nan, np.float32).ravel()
+    rc = emul.emul_stft(n_fft, hop, _p(x), L, L, 2, 0, 0, 1, L, n_fft // 2, T, _p(wa), _p(tw), _p(ctw), _p(spec), layout, F, 0)
+    assert rc == 0
+    if layout == 0:
+        got = spec.reshape(2, T, F, 2).transpose(0, 2, 1, 3)
+    elif layout == 1:
+        got = spec.reshape(2, F, T, 2)
+    else:
+        got = spec.reshape(2, 2, F, T).transpose(0, 2, 3, 1)
+    assert np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n_fft,hop,T,frame_pad,layout", [(4096, 1024, 40, 0, 2), (4096, 1024, 36, 2, 2), (6144, 1024, 36, 0, 2),
+                                                         (2048, 441, 21, 0, 1), (6144, 1024, 19, 0, 2), (2048, 512, 40, 1, 2)])
+def test_generic_istft_emulated_matches_torch(emul, n_fft, hop, T, frame_pad, layout):
+    """Arbitrary (non-consistent) spectrum; several 16-hop segments per row, so the halo recomputation, the re-aligned
+    first round of the 128-bit CaC loads (T % 4 == 0) and the in-place carry all run."""
+    import torch
+    _bind_fft(emul)
+    F = n_fft // 2 + 1
+    Fo = F - 1 if frame_pad else F
+    rs = np.random.RandomState(T)
+    S = (rs.standard_normal((2, Fo, T)) + 1j * rs.standard_normal((2, Fo, T))).astype(np.complex64)
+    Sfull = np.zeros((2, F, T + 2 * frame_pad), np.complex64)
+    Sfull[:, :Fo, frame_pad:frame_pad + T] = S
+    ref = torch.istft(torch.tensor(Sfull), n_fft, hop, window=torch.hann_window(n_fft), center=True).numpy()
+    out_len = ref.shape[-1]
+    _, ws, tw, ctw, env = _plan_tables(n_fft, hop, T + 2 * frame_pad)
+    if layout == 2:
+        spec = np.ascontiguousarray(np.stack((S.real, S.imag), axis=1)).astype(np.float32)     # [2, (re, im), Fo, T]
+    else:
+        spec = np.ascontiguousarray(S).view(np.float32)                                        # c64 [2, Fo, T]
+    dst = np.full((2, out_len), np.nan, np.float32)
+    segs = emul.emul_istft(n_fft, hop, _p(spec), None, layout, Fo, T, frame_pad, 1, 1, 2, 0, 0, _p(ws), _p(tw), _p(ctw), _p(env),
+                           n_fft // 2, out_len, None, _p(dst), out_len, 2 * out_len, 0, 0, out_len)
+    assert segs >= 1
+    assert np.isfinite(dst).all()
+    assert np.abs(dst - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
