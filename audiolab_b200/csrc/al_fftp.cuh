@@ -15,9 +15,11 @@
 
 namespace al {
 
+#ifndef AL_CPU_EMUL
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+#endif
 
 constexpr int kScrF2 = 33 * 32;   // float2 per warp scratch: [32][33] transposition tile
 
@@ -83,6 +85,7 @@ __device__ __forceinline__ void warp_fft1024p_wide(float2 (&re)[32], float2 (&im
     if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
 }
 
+#ifndef AL_CPU_EMUL   // (tools/cpu_emul emulates the barrier / shuffle kernels only)
 // ---- bulk asynchronous shared -> global store (TMA engine, no tensor map) ------------------------
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
@@ -114,5 +117,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+#endif  // AL_CPU_EMUL
 
 }  // namespace al

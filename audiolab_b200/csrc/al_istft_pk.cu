@@ -27,6 +27,7 @@
 
 namespace al {
 
+// [emul-begin]
 // W = warps = frames per round.  W = 4 (default): two CTAs share an SM, so one's row loads overlap the
 // other's FFT / overlap-add; W = 8: one CTA per SM, half the halo recomputation (AL_IP_WARPS=8 selects it).
 constexpr int kIpKMax = 5;               // frames covering one position in the register form of the overlap-add (hop >= 410)
@@ -39,7 +40,11 @@ constexpr int kIpBins = 1025;
 constexpr int kIpDepth = AL_IP_DEPTH;    // register pipeline depth of the row loads (stages of 4 + 4 x 16 B per lane)
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
+#ifndef AL_CPU_EMUL
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+#else
+    (void)g; (void)bytes;
+#endif
 }
 
 // Y = x * m per channel; returns packed (L, R) real and imaginary parts
@@ -67,7 +72,7 @@ template <bool MASK, int W>
 __global__ void __launch_bounds__(W * 32, kIpSmWarps / W)
 istft_pk2_kernel(const IstftPkParams p) {
     constexpr int kIpWarps = W, kIpThreads = W * 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);           // [1024]
     float2* s_win = s_tw + 1024;                                   // [1024] (w[2k], w[2k+1])
     float2* s_ctw = s_win + 1024;                                  // [1024] W^k
@@ -317,6 +322,15 @@ static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int kIpWarps,
     *segs_out = (total_hops + hpc - 1) / hpc;
 }
 
+// launch shape of istft_pk2_kernel<., W>: fills hops_per_cta / segs, returns the dynamic shared memory size
+static size_t ip_launch_shape(IstftPkParams& p, int n_chunks, int n_sm, int W) {
+    const int rows = n_chunks * p.stems;
+    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
+    ip_tiling(rows, total_hops, p.hop, n_sm * (kIpSmWarps / W), W, &p.hops_per_cta, &p.segs);
+    return (size_t)3 * 1024 * sizeof(float2) + (size_t)W * kScrF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2);
+}
+// [emul-end]
+
 cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
     IstftPkParams p = p0;
     static int n_sm = 0;
@@ -327,11 +341,8 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
         if (n_sm <= 0) n_sm = 148;
     }
     const int rows = n_chunks * p.stems;
-    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
     static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
-    ip_tiling(rows, total_hops, p.hop, n_sm * (kIpSmWarps / W), W, &p.hops_per_cta, &p.segs);
-    const size_t smem = (size_t)3 * 1024 * sizeof(float2) + (size_t)W * kScrF4 * sizeof(float4) +
-                        (size_t)(kIpN - p.hop) * sizeof(float2);
+    const size_t smem = ip_launch_shape(p, n_chunks, n_sm, W);
     const size_t cap = 227 * 1024;
     if (smem > cap) return cudaErrorInvalidValue;
 #define AL_IP_LAUNCH(MSK, WW)                                                                                    \

@@ -66,8 +66,6 @@ struct IstftParams {
     int segs;
 };
 
-// [emul-end]
-
 // stereo / n_fft 2048 / bin-innermost fast path (al_stft_pk.cu)
 struct StftPkParams {
     const float* track;
@@ -120,6 +118,8 @@ struct IstftPkParams {
     int hops_per_cta;
     int segs;
 };
+
+// [emul-end]
 
 cudaError_t launch_stft(const StftParams& p, int n_fft, int rows, cudaStream_t stream);
 cudaError_t launch_istft_pk(const IstftPkParams& p, int n_chunks, cudaStream_t stream);

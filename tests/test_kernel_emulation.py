@@ -188,3 +188,37 @@ def test_generic_istft_emulated_matches_torch(emul, n_fft, hop, T, frame_pad, la
     assert segs >= 1
     assert np.isfinite(dst).all()
     assert np.abs(dst - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("hop,T,stems,use_mask,warps", [(441, 21, 1, True, 4), (441, 13, 2, True, 8), (512, 17, 1, False, 4),
+                                                       (1024, 9, 1, True, 4)])
+def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warps):
+    """istft_pk2_kernel (stereo, n_fft 2048, frame-interleaved spectrum and mask): fused complex mask, packed f32x2
+    inverse FFT, register-form overlap-add with the in-place carry, several segments per chunk (n_sm = 3 forces
+    ip_tiling to split), both warps-per-CTA variants."""
+    import torch
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emul.emul_istft_pk.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I]
+    emul.emul_istft_pk.restype = I
+    n_fft, F, n_chunks = 2048, 1025, 2
+    rs = np.random.RandomState(hop + T)
+    cplx = lambda *shape: (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+    spec = cplx(n_chunks, T, F, 2)                                         # [chunk, t, f, channel]
+    mask = cplx(n_chunks, stems, T, F, 2) if use_mask else None
+    out_len = (T - 1) * hop
+    _, ws, tw, _, env = _plan_tables(n_fft, hop, T)
+    k = np.arange(1024)
+    ctw_full = np.ascontiguousarray(np.stack((np.cos(-2 * np.pi * k / n_fft), np.sin(-2 * np.pi * k / n_fft)), -1).astype(np.float32))
+    weight = rs.uniform(0.5, 1.5, out_len).astype(np.float32)
+    dst = np.full((n_chunks, stems, 2, out_len), np.nan, np.float32)
+    segs = emul.emul_istft_pk(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), n_fft // 2, out_len,
+                              _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, n_chunks, warps, 3)
+    assert segs >= 1
+    assert np.isfinite(dst).all()
+    win = torch.hann_window(n_fft)
+    for c in range(n_chunks):
+        for s_ in range(stems):
+            y = spec[c] * (mask[c, s_] if use_mask else 1.0)               # [t, f, ch]
+            ref = torch.istft(torch.tensor(np.ascontiguousarray(y.transpose(2, 1, 0))), n_fft, hop, window=win, center=True)
+            ref = ref.numpy() * weight
+            assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())

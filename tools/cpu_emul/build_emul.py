@@ -72,6 +72,32 @@ extern "C" int emul_istft(int n_fft, int hop, const float* spec, const float* ma
     return -1;
 }
 
+extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames, int stems, int spec_has_stems, int hop,
+                             const float* window, const float* tw, const float* ctw_full, const float* inv_env,
+                             int out_start, int out_len, const float* weight, float* dst, long long dst_ch_stride,
+                             long long dst_chunk_stride, long long dst_off0, long long dst_off_step, long long dst_limit,
+                             int n_chunks, int warps, int n_sm) {
+    IstftPkParams p{};
+    p.spec = reinterpret_cast<const float4*>(spec); p.mask = reinterpret_cast<const float4*>(mask); p.n_frames = n_frames;
+    p.stems = stems; p.spec_has_stems = spec_has_stems; p.hop = hop; p.window = window;
+    p.tw = reinterpret_cast<const float2*>(tw); p.ctw = reinterpret_cast<const float2*>(ctw_full); p.inv_env = inv_env;
+    p.out_start = out_start; p.out_len = out_len; p.weight = weight; p.dst = dst; p.dst_ch_stride = dst_ch_stride;
+    p.dst_chunk_stride = dst_chunk_stride; p.dst_offsets = nullptr; p.dst_off0 = dst_off0; p.dst_off_step = dst_off_step;
+    p.dst_limit = dst_limit;
+    const size_t smem = ip_launch_shape(p, n_chunks, n_sm, warps);
+    if (smem > sizeof(g_smem)) return -2;
+    std::memset(g_smem, 0xFF, sizeof(g_smem));
+    const dim3 grid(n_chunks * stems * p.segs), block(warps * 32);
+    if (warps == 8) {
+        if (mask) emul_launch(grid, block, [&] { istft_pk2_kernel<true, 8>(p); });
+        else emul_launch(grid, block, [&] { istft_pk2_kernel<false, 8>(p); });
+    } else {
+        if (mask) emul_launch(grid, block, [&] { istft_pk2_kernel<true, 4>(p); });
+        else emul_launch(grid, block, [&] { istft_pk2_kernel<false, 4>(p); });
+    }
+    return p.segs;
+}
+
 extern "C" void emul_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                                 const long long* offsets, const int* mult, const float* wtab, const int* tab_id,
                                 long long n_total, long long p0, long long p1, const float* halo_in, int raw_out,
@@ -107,8 +133,9 @@ def region(path):
 
 
 def build(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu")]
-    whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh")]       # no launch syntax: taken whole
+    srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu",
+                                            "al_istft_pk.cu")]
+    whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh", "fft32p_gen.cuh", "al_fftp.cuh")]   # taken whole
     deps = srcs + whole + [os.path.join(HERE, "cuda_emul.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):
         return SO
@@ -123,7 +150,7 @@ def build(force=False):
             f.write(f"// ---- from {os.path.basename(s)}\n" + region(s) + "\n")
         f.write("}  // namespace al\n")
         f.write(GLUE)
-    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread",
+    subprocess.run(["g++", "-std=c++20", "-O1", "-DAL_CPU_EMUL", "-g", "-mfma", "-ffp-contract=fast", "-shared", "-fPIC", "-pthread",
                     "-I", HERE, "-o", SO, gen], check=True)
     return SO
 
