@@ -117,6 +117,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+#else   // host emulation (tools/cpu_emul): the same protocol on std::atomic_ref, bulk copies done at issue time
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) { std::memcpy(gdst, ssrc, bytes); }
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read_all() {}
+__device__ __forceinline__ void bulk_wait_all() {}
+__device__ __forceinline__ void fence_async_smem() {}
+// word = expected arrivals << 32 | pending arrivals << 1 | phase parity
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    std::atomic_ref<uint64_t>(*bar).store(((uint64_t)count << 32) | ((uint64_t)count << 1));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    std::atomic_ref<uint64_t> a(*bar);
+    uint64_t v = a.load();
+    for (;;) {
+        const uint64_t count = v >> 32, pending = (v & 0xFFFFFFFFull) >> 1, phase = v & 1;
+        const uint64_t nv = pending > 1 ? ((count << 32) | ((pending - 1) << 1) | phase)
+                                        : ((count << 32) | (count << 1) | (phase ^ 1));
+        if (a.compare_exchange_weak(v, nv)) return;
+    }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    std::atomic_ref<uint64_t> a(*bar);
+    while ((a.load() & 1) == parity) std::this_thread::yield();
+}
 #endif  // AL_CPU_EMUL
 
 }  // namespace al

@@ -22,6 +22,7 @@
 
 namespace al {
 
+// [emul-begin]
 constexpr int kPkWarps = 8;          // compute warps = frames per tile (2 per SM sub-partition) + 1 producer
 constexpr int kPkProd = 4;           // producer warps (memory-level parallelism of the stage fill)
 constexpr int kPkThreads = (kPkWarps + kPkProd) * 32;
@@ -35,7 +36,7 @@ __device__ __forceinline__ float2 shfl2(float2 v, int src) {
 template <int LAYOUT, bool FULL>
 __global__ void __launch_bounds__(kPkThreads, 1)
 stft_pk2_kernel(const StftPkParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);          // [1024]
     float2* s_win = s_tw + 1024;                                  // [1024] window pairs (w[2m], w[2m+1])
     float2* s_ctw = s_win + 1024;                                 // [kPkCtw] 0.5 * exp(-2 pi i k / 2048)
@@ -254,8 +255,8 @@ static int pk_sp(int hop) {
     return (((span + 1) / 2 + 2) + 1) & ~1;
 }
 
-cudaError_t launch_stft_pk(const StftPkParams& p0, cudaStream_t stream) {
-    StftPkParams p = p0;
+// launch shape of stft_pk2_kernel: fills sp / tiles / n_stages, returns the dynamic shared memory size (0 = does not fit)
+static size_t pk_launch_shape(StftPkParams& p) {
     p.sp = pk_sp(p.hop);
     p.tiles_per_chunk = (p.n_frames + kPkWarps - 1) / kPkWarps;
     p.total_tiles = p.tiles_per_chunk * p.n_chunks;
@@ -264,10 +265,18 @@ cudaError_t launch_stft_pk(const StftPkParams& p0, cudaStream_t stream) {
     const size_t per_stage = (size_t)2 * p.sp * sizeof(float2);
     const size_t cap = 227 * 1024;
     int ns = (int)((cap - fixed) / per_stage);
-    if (ns < 1) return cudaErrorInvalidValue;
+    if (ns < 1) return 0;
     if (ns > 3) ns = 3;
     p.n_stages = ns;
-    const size_t smem = fixed + ns * per_stage;
+    return fixed + ns * per_stage;
+}
+// [emul-end]
+
+cudaError_t launch_stft_pk(const StftPkParams& p0, cudaStream_t stream) {
+    StftPkParams p = p0;
+    const size_t cap = 227 * 1024;
+    const size_t smem = pk_launch_shape(p);
+    if (smem == 0) return cudaErrorInvalidValue;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;

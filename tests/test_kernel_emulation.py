@@ -222,3 +222,42 @@ def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warp
             ref = torch.istft(torch.tensor(np.ascontiguousarray(y.transpose(2, 1, 0))), n_fft, hop, window=win, center=True)
             ref = ref.numpy() * weight
             assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("hop,T,layout,crop,low,n_chunks", [(441, 21, 3, 1025, 0, 2), (441, 9, 0, 1025, 0, 1), (512, 12, 3, 1000, 3, 2),
+                                                           (441, 26, 3, 1025, 0, 3)])
+def test_packed_stft_emulated_matches_torch(emul, hop, T, layout, crop, low, n_chunks):
+    """stft_pk2_kernel (stereo, n_fft 2048): producer / consumer stage ring on mbarriers, packed f32x2 FFT, lane-mirror
+    separation, bulk row stores; chunks cut out of one track (reflect padding at chunk ends, zero beyond the track),
+    a persistent grid smaller than the number of tiles, cropped / zeroed bins."""
+    import torch
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emul.emul_stft_pk.argtypes = [P, LL, LL, LL, LL, I, I, I, I, I, P, P, P, P, I, I, I, I, I]
+    emul.emul_stft_pk.restype = I
+    n_fft, F = 2048, 1025
+    L = (T - 1) * hop
+    n = n_chunks * L - 100                                              # the last chunk runs 100 samples past the track
+    rs = np.random.RandomState(T)
+    x = np.zeros((2, n_chunks * L + 8), np.float32)
+    x[:, :n] = rs.uniform(-1, 1, size=(2, n))
+    x[:, n:] = np.nan                                                   # beyond n_valid: must never be read as data
+    wa, _, tw, _, _ = _plan_tables(n_fft, hop)
+    half = np.zeros((544, 2), np.float32)
+    k = np.arange(513)
+    half[:513, 0], half[:513, 1] = 0.5 * np.cos(-2 * np.pi * k / n_fft), 0.5 * np.sin(-2 * np.pi * k / n_fft)
+    spec = np.full(n_chunks * 2 * T * crop * 2, np.nan, np.float32)
+    ns = emul.emul_stft_pk(_p(x), n, x.shape[1], 0, L, n_chunks, L, n_fft // 2, hop, T, _p(wa), _p(tw), _p(half), _p(spec),
+                           layout, crop, low, 1, 2)
+    assert ns >= 1
+    assert np.isfinite(spec).all()
+    xz = np.nan_to_num(x[:, :n_chunks * L], nan=0.0)
+    for c in range(n_chunks):
+        ref = torch.stft(torch.tensor(xz[:, c * L:(c + 1) * L]), n_fft, hop, window=torch.hann_window(n_fft), center=True,
+                         return_complex=True)
+        ref = torch.view_as_real(ref).numpy()[:, :crop].copy()          # [2, crop, T, 2]
+        ref[:, :low] = 0
+        if layout == 3:
+            got = spec.reshape(n_chunks, T, crop, 2, 2)[c].transpose(2, 1, 0, 3)        # [t, f, ch, ri] -> [ch, f, t, ri]
+        else:
+            got = spec.reshape(n_chunks, 2, T, crop, 2)[c].transpose(0, 2, 1, 3)        # [ch, t, f, ri] -> [ch, f, t, ri]
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()

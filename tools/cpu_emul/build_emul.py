@@ -72,6 +72,31 @@ extern "C" int emul_istft(int n_fft, int hop, const float* spec, const float* ma
     return -1;
 }
 
+extern "C" int emul_stft_pk(const float* track, long long n_valid, long long ch_stride, long long off0, long long off_step,
+                            int n_chunks, int chunk_len, int center, int hop, int n_frames, const float* window,
+                            const float* tw, const float* ctw_half, float* spec, int layout, int n_bins_out,
+                            int zero_low_bins, int aligned, int grid_x) {
+    StftPkParams p{};
+    p.track = track; p.n_valid = n_valid; p.ch_stride = ch_stride; p.chunk_offsets = nullptr; p.off0 = off0;
+    p.off_step = off_step; p.n_chunks = n_chunks; p.chunk_len = chunk_len; p.center = center; p.hop = hop;
+    p.n_frames = n_frames; p.window = window; p.tw = reinterpret_cast<const float2*>(tw);
+    p.ctw_half = reinterpret_cast<const float2*>(ctw_half); p.spec = spec; p.layout = layout; p.n_bins_out = n_bins_out;
+    p.zero_low_bins = zero_low_bins; p.aligned = aligned;
+    const size_t smem = pk_launch_shape(p);
+    if (smem == 0 || smem > sizeof(g_smem)) return -2;
+    std::memset(g_smem, 0xFF, sizeof(g_smem));
+    const bool full = n_bins_out == 1025 && zero_low_bins == 0;
+    const dim3 grid(std::min(p.total_tiles, grid_x)), block(kPkThreads);
+    if (layout == 3) {
+        if (full) emul_launch(grid, block, [&] { stft_pk2_kernel<3, true>(p); });
+        else emul_launch(grid, block, [&] { stft_pk2_kernel<3, false>(p); });
+    } else {
+        if (full) emul_launch(grid, block, [&] { stft_pk2_kernel<0, true>(p); });
+        else emul_launch(grid, block, [&] { stft_pk2_kernel<0, false>(p); });
+    }
+    return p.n_stages;
+}
+
 extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames, int stems, int spec_has_stems, int hop,
                              const float* window, const float* tw, const float* ctw_full, const float* inv_env,
                              int out_start, int out_len, const float* weight, float* dst, long long dst_ch_stride,
@@ -134,7 +159,7 @@ def region(path):
 
 def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu",
-                                            "al_istft_pk.cu")]
+                                            "al_istft_pk.cu", "al_stft_pk.cu")]
     whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh", "fft32p_gen.cuh", "al_fftp.cuh")]   # taken whole
     deps = srcs + whole + [os.path.join(HERE, "cuda_emul.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):

@@ -3,6 +3,7 @@
 // Test infrastructure only (tests/test_kernel_emulation.py); never part of the product.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <climits>
 #include <cmath>
