@@ -13,8 +13,8 @@
 //    loads of a register pair (r, 31-r) fall on the same 128-byte lines and are issued back to
 //    back), so there is no shuffle, no lane-0 special case and no spectrum staging in shared memory;
 //  * HBM latency is covered by bulk L2 prefetches (cp.async.bulk.prefetch.L2) of the rows of the next
-//    round, issued before the current round's loads, and by a four-deep register pipeline of loads
-//    (the FFT registers are still empty while the first stages are in flight);
+//    two rounds ahead, by a four-deep register pipeline of loads, and by issuing the first three stages
+//    of the NEXT round's frame before this round's overlap-add (the FFT registers are free by then);
 //  * the windowed frame is parked in the warp's own transposition scratch; after one CTA barrier all
 //    threads gather-sum the round's frames (+ the carry of earlier rounds) in ascending frame
 //    order -- the deterministic order of istft_kernel -- and emit both channels.
@@ -37,6 +37,7 @@ constexpr int kIpBins = 1025;
 #ifndef AL_IP_DEPTH
 #define AL_IP_DEPTH 4
 #endif
+// PRE (template) = stages of the NEXT round's frame loaded before this round's overlap-add (0: none; AL_IP_PRE selects)
 constexpr int kIpDepth = AL_IP_DEPTH;    // register pipeline depth of the row loads (stages of 4 + 4 x 16 B per lane)
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
@@ -68,10 +69,11 @@ __device__ __forceinline__ void ip_combine(float2 pr, float2 pi, float2 qr, floa
     zi = pfma(di, w.y, pfma(dr, w.x, ai));                  // A.im + Re(D conj(w))
 }
 
-template <bool MASK, int W>
+template <bool MASK, int W, int PRE>
 __global__ void __launch_bounds__(W * 32, kIpSmWarps / W)
 istft_pk2_kernel(const IstftPkParams p) {
-    constexpr int kIpWarps = W, kIpThreads = W * 32;
+    constexpr int kIpWarps = W, kIpThreads = W * 32, kIpPre = PRE;
+    static_assert(PRE <= kIpDepth - 1, "preloaded stages must fit the register ring");
     AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);           // [1024]
     float2* s_win = s_tw + 1024;                                   // [1024] (w[2k], w[2k+1])
@@ -104,9 +106,36 @@ istft_pk2_kernel(const IstftPkParams p) {
     const float4* __restrict__ X = p.spec + (long long)(p.spec_has_stems ? g : chunk) * T * kIpBins;
     const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
 
-    if (lane == 0 && ta + warp <= tb) {   // the first round's rows: start them towards L2 right away
-        prefetch_l2_bulk(X + (long long)(ta + warp) * kIpBins, kIpBins * 16);
-        if (MASK) prefetch_l2_bulk(M + (long long)(ta + warp) * kIpBins, kIpBins * 16);
+    // pair r: k1 = 32 r + lane (reg r), k2 = 32 (31 - r) + lane (reg 31 - r); mirrors q = 1024 - k
+    float4 bx[kIpDepth][4], bm[kIpDepth][4];
+#define IP_ISSUE(xrow_, mrow_, r_, b_)                                            \
+    do {                                                                          \
+        const int k1_ = 32 * (r_) + lane, k2_ = 32 * (31 - (r_)) + lane;          \
+        bx[b_][0] = __ldg((xrow_) + k1_);                                         \
+        bx[b_][1] = __ldg((xrow_) + (1024 - k2_));                                \
+        bx[b_][2] = __ldg((xrow_) + k2_);                                         \
+        bx[b_][3] = __ldg((xrow_) + (1024 - k1_));                                \
+        if (MASK) {                                                               \
+            bm[b_][0] = __ldg((mrow_) + k1_);                                     \
+            bm[b_][1] = __ldg((mrow_) + (1024 - k2_));                            \
+            bm[b_][2] = __ldg((mrow_) + k2_);                                     \
+            bm[b_][3] = __ldg((mrow_) + (1024 - k1_));                            \
+        }                                                                         \
+    } while (0)
+    if (ta + warp <= tb) {   // the first round's frame: its first stages leave now, the second round's rows go to L2
+        const float4* __restrict__ xr = X + (long long)(ta + warp) * kIpBins;
+        const float4* __restrict__ mr = MASK ? M + (long long)(ta + warp) * kIpBins : nullptr;
+#pragma unroll
+        for (int r = 0; r < kIpPre; ++r) IP_ISSUE(xr, mr, r, r);
+        if (lane == 0) {
+            if (kIpPre == 0) {
+                prefetch_l2_bulk(xr, kIpBins * 16);
+                if (MASK) prefetch_l2_bulk(mr, kIpBins * 16);
+            } else if (ta + warp + kIpWarps <= tb) {
+                prefetch_l2_bulk(xr + (long long)kIpWarps * kIpBins, kIpBins * 16);
+                if (MASK) prefetch_l2_bulk(mr + (long long)kIpWarps * kIpBins, kIpBins * 16);
+            }
+        }
     }
     for (int i = tid; i < 1024; i += kIpThreads) {
         s_tw[i] = p.tw[i];
@@ -123,35 +152,21 @@ istft_pk2_kernel(const IstftPkParams p) {
         const bool live = warp < nf;                          // warp-uniform
         float2 re[32], im[32];
         if (live) {
-            if (lane == 0 && t + kIpWarps <= tb) {
-                prefetch_l2_bulk(X + (long long)(t + kIpWarps) * kIpBins, kIpBins * 16);
-                if (MASK) prefetch_l2_bulk(M + (long long)(t + kIpWarps) * kIpBins, kIpBins * 16);
+            constexpr int kAhead = kIpPre ? 2 : 1;   // rounds ahead of the L2 prefetch
+            if (lane == 0 && t + kAhead * kIpWarps <= tb) {
+                prefetch_l2_bulk(X + (long long)(t + kAhead * kIpWarps) * kIpBins, kIpBins * 16);
+                if (MASK) prefetch_l2_bulk(M + (long long)(t + kAhead * kIpWarps) * kIpBins, kIpBins * 16);
             }
             // ---- build Z from the spectrum (and mask) rows: register pairs (r, 31 - r) --------------
+            // stages 0 .. kIpPre - 1 were issued before the previous round's overlap-add
             const float4* __restrict__ xrow = X + (long long)t * kIpBins;
             const float4* __restrict__ mrow = MASK ? M + (long long)t * kIpBins : nullptr;
-            // pair r: k1 = 32 r + lane (reg r), k2 = 32 (31 - r) + lane (reg 31 - r); mirrors q = 1024 - k
-            float4 bx[kIpDepth][4], bm[kIpDepth][4];
-#define IP_ISSUE(r_, b_)                                                         \
-    do {                                                                          \
-        const int k1_ = 32 * (r_) + lane, k2_ = 32 * (31 - (r_)) + lane;          \
-        bx[b_][0] = __ldg(xrow + k1_);                                            \
-        bx[b_][1] = __ldg(xrow + (1024 - k2_));                                   \
-        bx[b_][2] = __ldg(xrow + k2_);                                            \
-        bx[b_][3] = __ldg(xrow + (1024 - k1_));                                   \
-        if (MASK) {                                                               \
-            bm[b_][0] = __ldg(mrow + k1_);                                        \
-            bm[b_][1] = __ldg(mrow + (1024 - k2_));                               \
-            bm[b_][2] = __ldg(mrow + k2_);                                        \
-            bm[b_][3] = __ldg(mrow + (1024 - k1_));                               \
-        }                                                                         \
-    } while (0)
 #pragma unroll
-            for (int r = 0; r < kIpDepth - 1; ++r) IP_ISSUE(r, r);
+            for (int r = kIpPre; r < kIpDepth - 1; ++r) IP_ISSUE(xrow, mrow, r, r);
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int b = r % kIpDepth;
-                if (r + kIpDepth - 1 < 16) IP_ISSUE(r + kIpDepth - 1, (r + kIpDepth - 1) % kIpDepth);
+                if (r + kIpDepth - 1 < 16) IP_ISSUE(xrow, mrow, r + kIpDepth - 1, (r + kIpDepth - 1) % kIpDepth);
                 float2 p1r, p1i, q2r, q2i, p2r, p2i, q1r, q1i;
                 ip_product<MASK>(bx[b][0], bm[b][0], p1r, p1i);
                 ip_product<MASK>(bx[b][1], bm[b][1], q2r, q2i);
@@ -165,7 +180,6 @@ istft_pk2_kernel(const IstftPkParams p) {
                 ip_combine(p1r, p1i, q1r, q1i, w1, re[r], im[r]);
                 ip_combine(p2r, p2i, q2r, q2i, w2, re[31 - r], im[31 - r]);
             }
-#undef IP_ISSUE
         }
         __syncthreads();   // the previous round's overlap-add has finished reading the scratches
         if (live) {
@@ -177,6 +191,12 @@ istft_pk2_kernel(const IstftPkParams p) {
                 const float2 ev = pscale(re[r], w.x), od = pscale(im[r], w.y);
                 scr[32 * r + lane] = make_float4(ev.x, ev.y, od.x, od.y);
             }
+        }
+        if (kIpPre > 0 && t + kIpWarps <= tb) {   // next round's frame: first stages fly during the overlap-add
+            const float4* __restrict__ xr = X + (long long)(t + kIpWarps) * kIpBins;
+            const float4* __restrict__ mr = MASK ? M + (long long)(t + kIpWarps) * kIpBins : nullptr;
+#pragma unroll
+            for (int r = 0; r < kIpPre; ++r) IP_ISSUE(xr, mr, r, r);
         }
         __syncthreads();   // all frames of the round are parked
 
@@ -299,6 +319,8 @@ istft_pk2_kernel(const IstftPkParams p) {
     }
 }
 
+#undef IP_ISSUE
+
 // segments per row: minimise waves * rounds per segment (a round = kIpWarps frames; each segment re-computes the
 // ceil((2048 - hop) / hop) frames that precede its first owned sample)
 static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int kIpWarps, int* hpc_out, int* segs_out) {
@@ -345,22 +367,28 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     const size_t smem = ip_launch_shape(p, n_chunks, n_sm, W);
     const size_t cap = 227 * 1024;
     if (smem > cap) return cudaErrorInvalidValue;
-#define AL_IP_LAUNCH(MSK, WW)                                                                                    \
+#define AL_IP_LAUNCH(MSK, WW, PP)                                                                                    \
     do {                                                                                                      \
         static bool attr = false;                                                                             \
         if (!attr) {                                                                                          \
-            cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)cap);                                                   \
             if (e != cudaSuccess) return e;                                                                   \
-            e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+            e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW, PP>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
                                      cudaSharedmemCarveoutMaxShared);                                         \
             if (e != cudaSuccess) return e;                                                                   \
             attr = true;                                                                                      \
         }                                                                                                     \
-        istft_pk2_kernel<MSK, WW><<<(unsigned)(rows * p.segs), WW * 32, smem, stream>>>(p);                 \
+        istft_pk2_kernel<MSK, WW, PP><<<(unsigned)(rows * p.segs), WW * 32, smem, stream>>>(p);                 \
     } while (0)
-    if (W == 8) { if (p.mask) AL_IP_LAUNCH(true, 8); else AL_IP_LAUNCH(false, 8); }
-    else { if (p.mask) AL_IP_LAUNCH(true, 4); else AL_IP_LAUNCH(false, 4); }
+    static const int PRE = getenv("AL_IP_PRE") ? atoi(getenv("AL_IP_PRE")) : 2;
+#define AL_IP_PICK(WW, PP) do { if (p.mask) AL_IP_LAUNCH(true, WW, PP); else AL_IP_LAUNCH(false, WW, PP); } while (0)
+    if (W == 8) {
+        if (PRE == 0) AL_IP_PICK(8, 0); else AL_IP_PICK(8, 2);
+    } else {
+        if (PRE == 0) AL_IP_PICK(4, 0); else if (PRE == 3) AL_IP_PICK(4, 3); else AL_IP_PICK(4, 2);
+    }
+#undef AL_IP_PICK
 #undef AL_IP_LAUNCH
     count_launch();
     return cudaGetLastError();

@@ -8,6 +8,8 @@
 // bit-identical however the chunks were batched or sharded.  The covering chunks are walked in groups of
 // four whose 128-bit loads (chunk + weight table) are all issued before the first dependent add.  The weight sum ("counter") is
 // recomputed from the same tables instead of being stored.
+#include <stdlib.h>
+
 #include "al_kernels.h"
 
 namespace al {
@@ -30,7 +32,10 @@ __device__ __forceinline__ void ola_load4(const float* __restrict__ src, unsigne
     }
 }
 
-__global__ void __launch_bounds__(256, 3)
+// RB = rows handled by one thread: the offsets, masks, weights and the weight sum of a position are the same
+// for every row (channel / stem), so they are computed once and only the chunk samples are loaded per row.
+template <int RB>
+__global__ void __launch_bounds__(256, RB == 1 ? 3 : 2)
 ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                   const long long* __restrict__ offsets, const int* __restrict__ mult,
                   const float* __restrict__ wtab, const int* __restrict__ tab_id, long long n_total,
@@ -48,12 +53,15 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk
     }
     const int c_first = lo;
     const unsigned own = p + kOlaVec <= p1 ? 0xFu : ((1u << (int)(p1 - p)) - 1u);   // positions inside [p0, p1)
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-        float acc[kOlaVec], wsum[kOlaVec];
-        if (halo_in) ola_load4(halo_in + (long long)r * (p1 - p0) + (p - p0), own, acc);
-        else {
+    for (int r0 = blockIdx.y * RB; r0 < rows; r0 += gridDim.y * RB) {               // rows is a multiple of RB
+        float acc[RB][kOlaVec], wsum[kOlaVec];
 #pragma unroll
-            for (int e = 0; e < kOlaVec; ++e) acc[e] = 0.f;
+        for (int b = 0; b < RB; ++b) {
+            if (halo_in) ola_load4(halo_in + (long long)(r0 + b) * (p1 - p0) + (p - p0), own, acc[b]);
+            else {
+#pragma unroll
+                for (int e = 0; e < kOlaVec; ++e) acc[b][e] = 0.f;
+            }
         }
 #pragma unroll
         for (int e = 0; e < kOlaVec; ++e) wsum[e] = 0.f;
@@ -61,7 +69,7 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk
         // load of a group before its first dependent add
         for (int c0 = c_first; c0 < n_chunks; c0 += kOlaGroup) {
             if (__ldg(offsets + c0) > p + (kOlaVec - 1)) break;      // ascending: nothing further covers us
-            float x[kOlaGroup][kOlaVec], w[kOlaGroup][kOlaVec];
+            float x[kOlaGroup][RB][kOlaVec], w[kOlaGroup][kOlaVec];
             unsigned msk[kOlaGroup];
             int mm[kOlaGroup];
 #pragma unroll
@@ -89,44 +97,43 @@ ola_gather_kernel(const float* __restrict__ chunks, int n_chunks, int data_chunk
                 }
                 // chunks before data_chunk0 belong to the left neighbour: their partial sums arrive through
                 // halo_in, only their weights are counted here
-                if (c >= data_chunk0) ola_load4(chunks + ((long long)(c - data_chunk0) * rows + r) * chunk_len + j, m4, x[g]);
-                else {
 #pragma unroll
-                    for (int e = 0; e < kOlaVec; ++e) x[g][e] = 0.f;
+                for (int b = 0; b < RB; ++b) {
+                    if (c >= data_chunk0)
+                        ola_load4(chunks + ((long long)(c - data_chunk0) * rows + r0 + b) * chunk_len + j, m4, x[g][b]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < kOlaVec; ++e) x[g][b][e] = 0.f;
+                    }
                 }
             }
 #pragma unroll
             for (int g = 0; g < kOlaGroup; ++g) {
-                if (msk[g] == 0xFu) {
-                    for (int k = 0; k < mm[g]; ++k) {                // keep the reference's rounding: m separate adds
+                if (!msk[g]) continue;
+                for (int k = 0; k < mm[g]; ++k) {                    // keep the reference's rounding: m separate adds
 #pragma unroll
-                        for (int e = 0; e < kOlaVec; ++e) {
-                            acc[e] += x[g][e] * w[g][e];
+                    for (int e = 0; e < kOlaVec; ++e) {
+                        if (msk[g] == 0xFu || ((msk[g] >> e) & 1u)) {
+#pragma unroll
+                            for (int b = 0; b < RB; ++b) acc[b][e] += x[g][b][e] * w[g][e];
                             wsum[e] += w[g][e];
-                        }
-                    }
-                } else if (msk[g]) {
-                    for (int k = 0; k < mm[g]; ++k) {
-#pragma unroll
-                        for (int e = 0; e < kOlaVec; ++e) {
-                            if ((msk[g] >> e) & 1u) {
-                                acc[e] += x[g][e] * w[g][e];
-                                wsum[e] += w[g][e];
-                            }
                         }
                     }
                 }
             }
         }
-        float v[kOlaVec];
 #pragma unroll
-        for (int e = 0; e < kOlaVec; ++e) v[e] = raw_out ? acc[e] : scale * acc[e] / fmaxf(wsum[e], eps);
-        float* dst = track + (long long)r * track_stride + p;
-        if (own == 0xFu && al_aligned16(dst)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-        else {
+        for (int b = 0; b < RB; ++b) {
+            float v[kOlaVec];
 #pragma unroll
-            for (int e = 0; e < kOlaVec; ++e)
-                if ((own >> e) & 1u) dst[e] = v[e];
+            for (int e = 0; e < kOlaVec; ++e) v[e] = raw_out ? acc[b][e] : scale * acc[b][e] / fmaxf(wsum[e], eps);
+            float* dst = track + (long long)(r0 + b) * track_stride + p;
+            if (own == 0xFu && al_aligned16(dst)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+                for (int e = 0; e < kOlaVec; ++e)
+                    if ((own >> e) & 1u) dst[e] = v[e];
+            }
         }
     }
 }
@@ -140,10 +147,16 @@ cudaError_t launch_ola_gather(const float* chunks, int n_chunks, int data_chunk0
     if (p1 <= p0) return cudaSuccess;
     const long long n = p1 - p0;
     const long long per_cta = 256LL * kOlaVec;
-    dim3 grid((unsigned)((n + per_cta - 1) / per_cta), (unsigned)min(rows, 8));
-    ola_gather_kernel<<<grid, 256, 0, stream>>>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id,
-                                                n_total, p0, p1, halo_in, raw_out, eps, scale, track,
-                                                track_stride);
+    static const bool one_row = getenv("AL_OLA_RB1") != nullptr;
+#define AL_OLA_LAUNCH(RB_)                                                                                         \
+    do {                                                                                                           \
+        dim3 grid((unsigned)((n + per_cta - 1) / per_cta), (unsigned)min(rows / RB_, 8));                          \
+        ola_gather_kernel<RB_><<<grid, 256, 0, stream>>>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, \
+                                                         tab_id, n_total, p0, p1, halo_in, raw_out, eps, scale, track,       \
+                                                         track_stride);                                            \
+    } while (0)
+    if (rows % 2 == 0 && !one_row) AL_OLA_LAUNCH(2); else AL_OLA_LAUNCH(1);
+#undef AL_OLA_LAUNCH
     count_launch();
     return cudaGetLastError();
 }

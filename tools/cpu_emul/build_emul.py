@@ -101,7 +101,7 @@ extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames,
                              const float* window, const float* tw, const float* ctw_full, const float* inv_env,
                              int out_start, int out_len, const float* weight, float* dst, long long dst_ch_stride,
                              long long dst_chunk_stride, long long dst_off0, long long dst_off_step, long long dst_limit,
-                             int n_chunks, int warps, int n_sm) {
+                             int n_chunks, int warps, int n_sm, int pre) {
     IstftPkParams p{};
     p.spec = reinterpret_cast<const float4*>(spec); p.mask = reinterpret_cast<const float4*>(mask); p.n_frames = n_frames;
     p.stems = stems; p.spec_has_stems = spec_has_stems; p.hop = hop; p.window = window;
@@ -113,13 +113,14 @@ extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames,
     if (smem > sizeof(g_smem)) return -2;
     std::memset(g_smem, 0xFF, sizeof(g_smem));
     const dim3 grid(n_chunks * stems * p.segs), block(warps * 32);
-    if (warps == 8) {
-        if (mask) emul_launch(grid, block, [&] { istft_pk2_kernel<true, 8>(p); });
-        else emul_launch(grid, block, [&] { istft_pk2_kernel<false, 8>(p); });
-    } else {
-        if (mask) emul_launch(grid, block, [&] { istft_pk2_kernel<true, 4>(p); });
-        else emul_launch(grid, block, [&] { istft_pk2_kernel<false, 4>(p); });
-    }
+#define EMUL_IP(WW, PP)                                                                          \
+    do {                                                                                         \
+        if (mask) emul_launch(grid, block, [&] { istft_pk2_kernel<true, WW, PP>(p); });         \
+        else emul_launch(grid, block, [&] { istft_pk2_kernel<false, WW, PP>(p); });             \
+    } while (0)
+    if (warps == 8) { if (pre == 0) EMUL_IP(8, 0); else EMUL_IP(8, 2); }
+    else { if (pre == 0) EMUL_IP(4, 0); else if (pre == 3) EMUL_IP(4, 3); else EMUL_IP(4, 2); }
+#undef EMUL_IP
     return p.segs;
 }
 
@@ -128,11 +129,19 @@ extern "C" void emul_ola_gather(const float* chunks, int n_chunks, int data_chun
                                 long long n_total, long long p0, long long p1, const float* halo_in, int raw_out,
                                 float eps, float scale, float* track, long long track_stride, int block) {
     const long long per_cta = (long long)block * kOlaVec;
-    dim3 grid((unsigned)((p1 - p0 + per_cta - 1) / per_cta), (unsigned)std::min(rows, 2));
-    emul_launch(grid, dim3(block), [&] {
-        ola_gather_kernel(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id, n_total, p0, p1,
-                          halo_in, raw_out, eps, scale, track, track_stride);
-    });
+    if (rows % 2 == 0) {
+        dim3 grid((unsigned)((p1 - p0 + per_cta - 1) / per_cta), (unsigned)std::min(rows / 2, 2));
+        emul_launch(grid, dim3(block), [&] {
+            ola_gather_kernel<2>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id, n_total, p0, p1,
+                                 halo_in, raw_out, eps, scale, track, track_stride);
+        });
+    } else {
+        dim3 grid((unsigned)((p1 - p0 + per_cta - 1) / per_cta), (unsigned)std::min(rows, 2));
+        emul_launch(grid, dim3(block), [&] {
+            ola_gather_kernel<1>(chunks, n_chunks, data_chunk0, rows, chunk_len, offsets, mult, wtab, tab_id, n_total, p0, p1,
+                                 halo_in, raw_out, eps, scale, track, track_stride);
+        });
+    }
 }
 
 extern "C" int emul_resample(const float* in, long long in_stride, float* out, long long out_stride, int rows,
