@@ -13,8 +13,8 @@
 //    loads of a register pair (r, 31-r) fall on the same 128-byte lines and are issued back to
 //    back), so there is no shuffle, no lane-0 special case and no spectrum staging in shared memory;
 //  * HBM latency is covered by bulk L2 prefetches (cp.async.bulk.prefetch.L2) of the rows of the next
-//    two rounds ahead, by a four-deep register pipeline of loads, and by issuing the first three stages
-//    of the NEXT round's frame before this round's overlap-add (the FFT registers are free by then);
+//    a round ahead and by a four-deep register pipeline of loads (optionally, AL_IP_PRE, also by issuing the
+//    first stages of the NEXT round's frame before this round's overlap-add -- measured slower, off by default);
 //  * the windowed frame is parked in the warp's own transposition scratch; after one CTA barrier all
 //    threads gather-sum the round's frames (+ the carry of earlier rounds) in ascending frame
 //    order -- the deterministic order of istft_kernel -- and emit both channels.
@@ -37,7 +37,9 @@ constexpr int kIpBins = 1025;
 #ifndef AL_IP_DEPTH
 #define AL_IP_DEPTH 4
 #endif
-// PRE (template) = stages of the NEXT round's frame loaded before this round's overlap-add (0: none; AL_IP_PRE selects)
+// PRE (template) = stages of the NEXT round's frame loaded before this round's overlap-add (AL_IP_PRE selects; default 0:
+// holding 64-96 load registers across the overlap-add costs more -- ptxas can no longer hoist the round's own loads --
+// than the hidden latency gains, profiles/r01l_kernel_bench_pre*.jsonl)
 constexpr int kIpDepth = AL_IP_DEPTH;    // register pipeline depth of the row loads (stages of 4 + 4 x 16 B per lane)
 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) {
@@ -381,7 +383,7 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
         }                                                                                                     \
         istft_pk2_kernel<MSK, WW, PP><<<(unsigned)(rows * p.segs), WW * 32, smem, stream>>>(p);                 \
     } while (0)
-    static const int PRE = getenv("AL_IP_PRE") ? atoi(getenv("AL_IP_PRE")) : 2;
+    static const int PRE = getenv("AL_IP_PRE") ? atoi(getenv("AL_IP_PRE")) : 0;   // measured (profiles/r01l): 0 -> 37.1 %, 2 -> 28.6 %, 3 -> 26.4 % of HBM
 #define AL_IP_PICK(WW, PP) do { if (p.mask) AL_IP_LAUNCH(true, WW, PP); else AL_IP_LAUNCH(false, WW, PP); } while (0)
     if (W == 8) {
         if (PRE == 0) AL_IP_PICK(8, 0); else AL_IP_PICK(8, 2);
