@@ -214,6 +214,61 @@ istft_pk2_kernel(const IstftPkParams p) {
         const int emit = kIpWarps * hop;
         const int span = emit + carry_len;
         const int fstride = 2 * kScrF4 - hop;                       // float2 step from (f, h) to (f + 1, h)
+        // Interior round (CTA-uniform): every frame is live, every emitted position is owned and lands inside the
+        // destination -- the register form without per-position predicates and with 32-bit indexing from four bases.
+        const long long rel = S - p.out_start;
+        if (p.ola_fast && kOla_K <= kIpKMax && nf == kIpWarps && S >= Pa && S + emit <= Pb && place + rel >= 0 &&
+            place + rel + emit <= p.dst_limit) {
+            constexpr int NH = kIpWarps + kIpKMax - 1;
+            const float* __restrict__ envp = p.inv_env + S;
+            const float* __restrict__ wgp = p.weight ? p.weight + rel : nullptr;
+            float* __restrict__ d0 = dst0 + rel;
+            float* __restrict__ d1 = dst1 + rel;
+            for (int j = tid; j < hop; j += kIpThreads) {
+                const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
+                const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
+                float ev[kIpWarps], wg[kIpWarps];
+#pragma unroll
+                for (int h = 0; h < kIpWarps; ++h) {
+                    ev[h] = __ldg(envp + h * hop + j);
+                    wg[h] = wgp ? __ldg(wgp + h * hop + j) : 1.f;
+                }
+                float2 out[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    out[h] = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int f = 0; f < kIpWarps; ++f) {
+                    const float2* __restrict__ sf = sj + f * (2 * kScrF4);
+#pragma unroll
+                    for (int k = 0; k < kIpKMax; ++k) {
+                        if (k <= kj) {
+                            const float2 v = sf[k * hop];
+                            out[f + k].x += v.x;
+                            out[f + k].y += v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < kIpWarps; ++h) {
+                    float v0 = out[h].x * ev[h], v1 = out[h].y * ev[h];
+                    if (wgp) {
+                        v0 *= wg[h];
+                        v1 *= wg[h];
+                    }
+                    d0[h * hop + j] = v0;
+                    d1[h * hop + j] = v1;
+                }
+#pragma unroll
+                for (int h = kIpWarps; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    if (i < span) cout[i - emit] = out[h];
+                }
+            }
+            continue;
+        }
         for (int j = tid; j < hop; j += kIpThreads) {
             const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
             const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
@@ -366,6 +421,8 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     }
     const int rows = n_chunks * p.stems;
     static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
+    static const int ola_fast = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
+    p.ola_fast = ola_fast;
     const size_t smem = ip_launch_shape(p, n_chunks, n_sm, W);
     const size_t cap = 227 * 1024;
     if (smem > cap) return cudaErrorInvalidValue;

@@ -114,6 +114,7 @@ struct IstftPkParams {
     const long long* dst_offsets;
     long long dst_off0, dst_off_step;
     long long dst_limit;
+    int ola_fast;             // interior rounds take the predicate-free overlap-add (AL_IP_OLAFAST=0 disables)
     // filled by the launcher
     int hops_per_cta;
     int segs;

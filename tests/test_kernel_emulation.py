@@ -190,15 +190,17 @@ def test_generic_istft_emulated_matches_torch(emul, n_fft, hop, T, frame_pad, la
     assert np.abs(dst - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("hop,T,stems,use_mask,warps,pre", [(441, 21, 1, True, 4, 2), (441, 13, 2, True, 8, 2), (512, 17, 1, False, 4, 3),
-                                                           (1024, 9, 1, True, 4, 0), (441, 30, 1, True, 4, 3)])
-def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warps, pre):
+@pytest.mark.parametrize("hop,T,stems,use_mask,warps,pre,fast", [(441, 21, 1, True, 4, 2, 1), (441, 13, 2, True, 8, 2, 1),
+                                                                (512, 17, 1, False, 4, 3, 0), (1024, 9, 1, True, 4, 0, 1),
+                                                                (441, 30, 1, True, 4, 0, 1), (441, 30, 1, True, 4, 0, 0),
+                                                                (441, 61, 1, False, 4, 0, 1)])
+def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warps, pre, fast):
     """istft_pk2_kernel (stereo, n_fft 2048, frame-interleaved spectrum and mask): fused complex mask, packed f32x2
     inverse FFT, register-form overlap-add with the in-place carry, several segments per chunk (n_sm = 3 forces
     ip_tiling to split), both warps-per-CTA variants, and the cross-round load pipelining depths (pre)."""
     import torch
     P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
-    emul.emul_istft_pk.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I, I]
+    emul.emul_istft_pk.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I, I, I]
     emul.emul_istft_pk.restype = I
     n_fft, F, n_chunks = 2048, 1025, 2
     rs = np.random.RandomState(hop + T)
@@ -212,7 +214,7 @@ def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warp
     weight = rs.uniform(0.5, 1.5, out_len).astype(np.float32)
     dst = np.full((n_chunks, stems, 2, out_len), np.nan, np.float32)
     segs = emul.emul_istft_pk(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), n_fft // 2, out_len,
-                              _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, n_chunks, warps, 3, pre)
+                              _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, n_chunks, warps, 3 if T < 40 else 1, pre, fast)
     assert segs >= 1
     assert np.isfinite(dst).all()
     win = torch.hann_window(n_fft)

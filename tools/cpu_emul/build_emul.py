@@ -101,7 +101,7 @@ extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames,
                              const float* window, const float* tw, const float* ctw_full, const float* inv_env,
                              int out_start, int out_len, const float* weight, float* dst, long long dst_ch_stride,
                              long long dst_chunk_stride, long long dst_off0, long long dst_off_step, long long dst_limit,
-                             int n_chunks, int warps, int n_sm, int pre) {
+                             int n_chunks, int warps, int n_sm, int pre, int ola_fast) {
     IstftPkParams p{};
     p.spec = reinterpret_cast<const float4*>(spec); p.mask = reinterpret_cast<const float4*>(mask); p.n_frames = n_frames;
     p.stems = stems; p.spec_has_stems = spec_has_stems; p.hop = hop; p.window = window;
@@ -109,6 +109,7 @@ extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames,
     p.out_start = out_start; p.out_len = out_len; p.weight = weight; p.dst = dst; p.dst_ch_stride = dst_ch_stride;
     p.dst_chunk_stride = dst_chunk_stride; p.dst_offsets = nullptr; p.dst_off0 = dst_off0; p.dst_off_step = dst_off_step;
     p.dst_limit = dst_limit;
+    p.ola_fast = ola_fast;
     const size_t smem = ip_launch_shape(p, n_chunks, n_sm, warps);
     if (smem > sizeof(g_smem)) return -2;
     std::memset(g_smem, 0xFF, sizeof(g_smem));
