@@ -191,6 +191,9 @@ def ola_gather(chunks: torch.Tensor, offsets: torch.Tensor, n_total: int, *,
     return out
 
 
+_TAPS_CACHE = {}
+
+
 def resample_taps(up: int, down: int) -> np.ndarray:
     """Kaiser(5.0)-windowed sinc of scipy.signal.resample_poly, in float32 like scipy uses it.
 
@@ -216,7 +219,10 @@ def resample_poly(x: torch.Tensor, up: int = 147, down: int = 160,
     g = int(np.gcd(up, down))
     up, down = up // g, down // g
     if taps is None:
-        taps = torch.from_numpy(resample_taps(up, down)).to(x.device)
+        key = (up, down, str(x.device))
+        taps = _TAPS_CACHE.get(key)
+        if taps is None:                                   # one firwin design + upload per ratio and device
+            taps = _TAPS_CACHE[key] = torch.from_numpy(resample_taps(up, down)).to(x.device)
     rows, n_in = x.shape
     n_out = (n_in * up + down - 1) // down
     out = torch.empty((rows, n_out), dtype=torch.float32, device=x.device)
