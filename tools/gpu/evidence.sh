@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence call (1 GPU): GPU tests, kernel roofline, default bench line, smoke, ncu --set full of al_istft inside
 # a timed bench step (traffic), ncu launch list of one timed bench step of the default configuration.
-# Usage: gpurun --timeout 600 -- 'bash tools/gpu_final.sh [tag]'
+# Usage: gpurun --timeout 600 -- 'bash tools/gpu/evidence.sh [tag]'
 TAG=${1:-fin}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

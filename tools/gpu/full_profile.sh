@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU tests, kernel roofline (+ K2 A/B of warps per CTA), bench line, smoke, ncu launch list of one
 # timed bench step, ncu --set full of the spectral kernels (one launch each) and of al_istft inside the bench step.
-# Usage: gpurun --timeout 900 -- 'bash tools/gpu_round3.sh [tag]'
+# Usage: gpurun --timeout 900 -- 'bash tools/gpu/full_profile.sh [tag]'
 TAG=${1:-r01d}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

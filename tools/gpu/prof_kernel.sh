@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu --set full capture of one kernel from tools/kernel_bench.py; exports small CSV/txt pages.
-# usage: bash tools/gpu_prof.sh TAG KERNEL_REGEX CASE ONLY
+# usage: bash tools/gpu/prof_kernel.sh TAG KERNEL_REGEX CASE ONLY
 TAG=$1; KRE=$2; CASE=${3:-roformer_2048_441}; ONLY=${4:-stft}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU gpurun call: NCCL halo-exchange parity check and the two multi-GPU bench modes.
-# Usage: gpurun --gpus 2 --timeout 420 -- 'bash tools/gpu_n2.sh [tag]'
+# Usage: gpurun --gpus 2 --timeout 420 -- 'bash tools/gpu/two_gpus.sh [tag]'
 TAG=${1:-n2}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
