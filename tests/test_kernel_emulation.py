@@ -263,3 +263,66 @@ def test_packed_stft_emulated_matches_torch(emul, hop, T, layout, crop, low, n_c
         else:
             got = spec.reshape(n_chunks, 2, T, crop, 2)[c].transpose(0, 2, 1, 3)        # [ch, t, f, ri] -> [ch, f, t, ri]
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_generic_istft_emulated_mask_stems_weight_and_clipped_placement(emul):
+    """Generic al_istft, c64 [rows, T, F] layout: fused complex mask over two stems of one shared spectrum, zeroed low
+    bins, chunk weight, out_start past the centre trim, chunks placed every `gen` samples into one track and clipped at
+    dst_limit (the MDX trim-and-concat form, mdxnet.py:178-183)."""
+    import torch
+    _bind_fft(emul)
+    n_fft, hop, T, stems, n_chunks, low = 4096, 1024, 24, 2, 2, 3
+    F = n_fft // 2 + 1
+    rs = np.random.RandomState(11)
+    cplx = lambda *shape: (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+    spec = cplx(n_chunks, 2, T, F)                                        # [chunk, ch, t, f]   (layout 0)
+    mask = cplx(n_chunks, stems, 2, T, F)                                 # [chunk, stem, ch, t, f]
+    trim = 700
+    gen = (T - 1) * hop - 2 * trim
+    n_total = 2 * gen - 333                                               # the second chunk is clipped by dst_limit
+    weight = rs.uniform(0.5, 1.5, gen).astype(np.float32)
+    _, ws, tw, ctw, env = _plan_tables(n_fft, hop, T)
+    dst = np.full((stems * 2, n_total), np.nan, np.float32)
+    segs = emul.emul_istft(n_fft, hop, _p(spec), _p(mask), 0, F, T, 0, n_chunks, stems, 2, 0, low, _p(ws), _p(tw), _p(ctw), _p(env),
+                           n_fft // 2 + trim, gen, _p(weight), _p(dst), n_total, 0, 0, gen, n_total)
+    assert segs >= 1
+    assert np.isfinite(dst).all()
+    win = torch.hann_window(n_fft)
+    for c in range(n_chunks):
+        for s_ in range(stems):
+            y = spec[c] * mask[c, s_]                                     # [ch, t, f]
+            y[:, :, :low] = 0
+            ref = torch.istft(torch.tensor(np.ascontiguousarray(y.transpose(0, 2, 1))), n_fft, hop, window=win, center=True).numpy()
+            ref = ref[:, trim:trim + gen] * weight
+            lo, hi = c * gen, min((c + 1) * gen, n_total)
+            got = dst[s_ * 2:s_ * 2 + 2, lo:hi]
+            assert np.abs(got - ref[:, :hi - lo]).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_generic_stft_emulated_virtual_padding_and_crop(emul):
+    """Generic al_stft on chunks cut out of one track with a negative first offset and a tail past the track (zeros
+    outside [0, n_valid), reflect padding about the CHUNK ends like torch.stft on the materialised chunk), cropped
+    frequency rows and zeroed low bins, CaC output (mdxnet.py:41-56, :152-164)."""
+    import torch
+    _bind_fft(emul)
+    n_fft, hop, T, n_chunks, crop, low = 6144, 1024, 8, 3, 3072, 2
+    L = (T - 1) * hop
+    n = 2 * L + 500
+    rs = np.random.RandomState(5)
+    x = rs.uniform(-1, 1, size=(2, n)).astype(np.float32)
+    off0, step = -3072, L - 1024
+    wa, _, tw, ctw, _ = _plan_tables(n_fft, hop)
+    spec = np.full((n_chunks, 4, crop, T), np.nan, np.float32)
+    rc = emul.emul_stft(n_fft, hop, _p(x), n, n, 2, off0, step, n_chunks, L, n_fft // 2, T, _p(wa), _p(tw), _p(ctw), _p(spec), 2,
+                        crop, low)
+    assert rc == 0 and np.isfinite(spec).all()
+    padded = np.zeros((2, n + 2 * L + 4096), np.float32)
+    padded[:, 3072:3072 + n] = x                                          # track position p lives at padded[p + 3072]
+    for c in range(n_chunks):
+        a = off0 + c * step + 3072
+        chunk = padded[:, a:a + L]
+        ref = torch.stft(torch.tensor(chunk), n_fft, hop, window=torch.hann_window(n_fft), center=True, return_complex=True)
+        ref = torch.view_as_real(ref).numpy()[:, :crop].copy()           # [2, crop, T, 2]
+        ref[:, :low] = 0
+        got = spec[c].reshape(2, 2, crop, T).transpose(0, 2, 3, 1)
+        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
