@@ -326,3 +326,33 @@ def test_generic_stft_emulated_virtual_padding_and_crop(emul):
         ref[:, :low] = 0
         got = spec[c].reshape(2, 2, crop, T).transpose(0, 2, 3, 1)
         assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_emulated_kernels_match_reference_golden_stft_istft(emul, tag):
+    """The kernels' source (host-emulated) against outputs of the REFERENCE's own ConvTDFNetTrim.stft / .istft
+    (/root/reference/modules/rvc/infer/modules/uvr5/mdxnet.py:41-75, vectors from tests/golden/make_mdx_golden.py):
+    pins al_stft / al_istft to the reference on a box without a GPU (the GPU twin is
+    tests/test_demix_gpu.py::test_mdx_demix_matches_reference_golden)."""
+    from oracle.synth import synth_mix
+    _bind_fft(emul)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mdx_stft.npz"))
+    n_fft, dim_f, dim_t_log2, seed = (int(v) for v in g[f"{tag}_cfg"])
+    hop, T = 1024, 2 ** dim_t_log2
+    chunk = hop * (T - 1)
+    track = np.ascontiguousarray(synth_mix(2 * chunk, seed=seed))          # [2 ch, 2 chunks back to back]
+    wa, ws, tw, ctw, env = _plan_tables(n_fft, hop, T)
+    spec = np.full((2, 4, dim_f, T), np.nan, np.float32)
+    rc = emul.emul_stft(n_fft, hop, _p(track), 2 * chunk, 2 * chunk, 2, 0, chunk, 2, chunk, n_fft // 2, T, _p(wa), _p(tw), _p(ctw),
+                        _p(spec), 2, dim_f, 0)
+    assert rc == 0 and np.isfinite(spec).all()
+    ref_sub = g[f"{tag}_spek_sub"]
+    assert np.abs(spec[:, :, ::7, :] - ref_sub).max() <= 2e-6 * np.abs(ref_sub).max()
+    ref_sum = g[f"{tag}_spek_sum"]
+    assert abs(float(spec.astype(np.float64).sum()) - ref_sum[0]) <= 1e-5 * ref_sum[1]
+    back = np.full((2, 2, chunk), np.nan, np.float32)
+    segs = emul.emul_istft(n_fft, hop, _p(spec), None, 2, dim_f, T, 0, 2, 1, 2, 0, 0, _p(ws), _p(tw), _p(ctw), _p(env), n_fft // 2,
+                           chunk, None, _p(back), chunk, 2 * chunk, 0, 0, chunk)
+    assert segs >= 1 and np.isfinite(back).all()
+    ref_back = g[f"{tag}_istft"]
+    assert np.abs(back - ref_back).max() <= 1e-4 * max(1.0, np.abs(ref_back).max())
