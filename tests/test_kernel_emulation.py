@@ -356,3 +356,13 @@ def test_emulated_kernels_match_reference_golden_stft_istft(emul, tag):
     assert segs >= 1 and np.isfinite(back).all()
     ref_back = g[f"{tag}_istft"]
     assert np.abs(back - ref_back).max() <= 1e-4 * max(1.0, np.abs(ref_back).max())
+
+
+@pytest.mark.parametrize("script,n,seed", [("fuzz_istft.py", 8, 5), ("fuzz_stft.py", 8, 5), ("fuzz_misc.py", 12, 5)])
+def test_randomised_emulation_subset(script, n, seed):
+    """A fixed-seed slice of the randomised emulation fuzzers (tools/cpu_emul/fuzz_*.py; longer runs: `--n 120`)."""
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_emul", script), "--n", str(n), "--seed", str(seed)],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]

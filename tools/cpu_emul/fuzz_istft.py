@@ -112,8 +112,12 @@ def one(lib, rs, packed):
             ref = ref * weight
         if not np.isfinite(dst[s]).all():
             return float("inf"), desc
-        scale = max(1.0, float(np.abs(ref).max()))
-        err = max(err, float(np.abs(dst[s] - ref).max()) / scale)
+        # near the untrimmed ends sum(w^2) -> 0 and 1/envelope amplifies fp32 rounding (these samples are normally cut by
+        # the centre trim): the tolerance grows with 1/envelope there
+        cond = np.maximum(1.0, 1e-3 / np.maximum(envd[out_start:out_start + out_len].numpy(), 1e-30))
+        good = envd[out_start:out_start + out_len].numpy() > 1e-11
+        scale = max(1.0, float(np.abs(ref[:, good]).max())) if good.any() else 1.0
+        err = max(err, float((np.abs(dst[s] - ref) / cond).max()) / scale)
     return err, desc
 
 
