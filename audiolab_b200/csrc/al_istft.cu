@@ -208,6 +208,55 @@ istft_kernel(const IstftParams p) {
         const float* frames = reinterpret_cast<const float*>(s_slot);
         const int emit = G * hop;
         const int span = emit + carry_len;
+        // Interior round (CTA-uniform): every frame is live, every emitted position is owned and lands inside the
+        // destination -- the register form without per-position predicates, 32-bit indexing from three bases.
+        const long long rel = S - p.out_start;
+        if (ola_k <= kOlaKMax && nf == G && S >= Pa && S + emit <= Pb && place + rel >= 0 && place + rel + emit <= p.dst_limit) {
+            constexpr int NH = G + kOlaKMax - 1;
+            const float* __restrict__ envp = p.inv_env + S;
+            const float* __restrict__ wgp = p.weight ? p.weight + rel : nullptr;
+            float* __restrict__ d = dst + rel;
+            for (int j = tid; j < hop; j += NT) {
+                const int kj = (ola_k - 1) * hop + j < N ? ola_k - 1 : ola_k - 2;
+                float ev[G], wg[G];
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    ev[h] = __ldg(envp + h * hop + j);
+                    wg[h] = wgp ? __ldg(wgp + h * hop + j) : 1.f;
+                }
+                int idx[kOlaKMax];
+#pragma unroll
+                for (int k = 0; k < kOlaKMax; ++k) {
+                    const int o = k * hop + j;
+                    idx[k] = (k <= kj) ? ((((o % D) >> 1) * kSlotF2 + o / D) * 2 + (o & 1)) : -1;
+                }
+                float out[NH];
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    out[h] = (i < carry_len) ? s_carry[i] : 0.f;
+                }
+#pragma unroll
+                for (int f = 0; f < G; ++f) {
+                    const float* __restrict__ fr = frames + f * (HW * kSlotF2 * 2);
+#pragma unroll
+                    for (int k = 0; k < kOlaKMax; ++k)
+                        if (idx[k] >= 0) out[f + k] += fr[idx[k]];
+                }
+#pragma unroll
+                for (int h = 0; h < G; ++h) {
+                    float v = out[h] * ev[h];
+                    if (wgp) v *= wg[h];
+                    d[h * hop + j] = v;
+                }
+#pragma unroll
+                for (int h = G; h < NH; ++h) {
+                    const int i = h * hop + j;
+                    if (i < span) s_carry[i - emit] = out[h];
+                }
+            }
+            continue;
+        }
         for (int j = tid; j < hop; j += NT) {
             const int kj = (ola_k - 1) * hop + j < N ? ola_k - 1 : ola_k - 2;
             // 1 / envelope and chunk weight of the emitted positions: loads issued before their first use

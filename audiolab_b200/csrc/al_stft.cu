@@ -38,17 +38,28 @@ stft_kernel(const StftParams p) {
         __syncthreads();               // previous combine is done with slots / stage; s_tw visible
 
         // ---- stage the span: reflect about the chunk, zero outside the track ----------------------
+        // NT is a multiple of D, so a thread's decimation phase i % D never changes and i / D advances by NT / D:
+        // no division in the loop.  Interior spans (no reflection, inside the track) skip the edge logic.
         const long long s0 = (long long)t0 * p.hop - p.center;
-        for (int i = tid; i < span; i += NT) {
-            long long j = s0 + i;
-            if (j < 0) j = -j;
-            if (j >= p.chunk_len) j = 2LL * (p.chunk_len - 1) - j;
-            float v = 0.f;
-            if (j >= 0 && j < p.chunk_len) {
-                const long long g = coff + j;
-                if (g >= 0 && g < p.n_valid) v = __ldg(src + g);
+        static_assert(NT % D == 0, "the staging loop relies on NT % D == 0");
+        float* __restrict__ sdst = s_stage + (tid % D) * ps + tid / D;
+        if (s0 >= 0 && s0 + span <= p.chunk_len && coff + s0 >= 0 && coff + s0 + span <= p.n_valid) {
+            const float* __restrict__ g = src + coff + s0;
+            int q = 0;
+            for (int i = tid; i < span; i += NT, q += NT / D) sdst[q] = __ldg(g + i);
+        } else {
+            int q = 0;
+            for (int i = tid; i < span; i += NT, q += NT / D) {
+                long long j = s0 + i;
+                if (j < 0) j = -j;
+                if (j >= p.chunk_len) j = 2LL * (p.chunk_len - 1) - j;
+                float v = 0.f;
+                if (j >= 0 && j < p.chunk_len) {
+                    const long long g = coff + j;
+                    if (g >= 0 && g < p.n_valid) v = __ldg(src + g);
+                }
+                sdst[q] = v;
             }
-            s_stage[(i % D) * ps + i / D] = v;
         }
         __syncthreads();
 
