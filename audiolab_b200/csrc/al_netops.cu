@@ -17,6 +17,7 @@
 
 namespace al {
 
+// [emul-begin]
 __device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -82,6 +83,8 @@ rmsnorm_bf16_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     }
 }
 
+// [emul-end]
+
 cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, long long n_rows, int dim,
                                 float scale, float eps, cudaStream_t stream) {
     const int wpb = 8;
@@ -95,6 +98,7 @@ cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, 
     return cudaGetLastError();
 }
 
+// [emul-begin]
 // q, k: [n_rows, heads * dim_head] bf16, rotated in place.  Element pair (2i, 2i+1) of every head turns by
 // the angle pos * freq_i, pos = (row / pos_div) % pos_mod;  cs[pos][i] = (cos, sin).
 __global__ void __launch_bounds__(256)
@@ -123,6 +127,8 @@ rotary_bf16_kernel(uint4* __restrict__ q, uint4* __restrict__ k, const float2* _
     k[i] = f32_to_bf16x8(rb);
 }
 
+// [emul-end]
+
 cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head,
                                long long pos_div, int pos_mod, cudaStream_t stream) {
     const int vec_per_row = heads * dim_head / 8;
@@ -134,6 +140,7 @@ cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_ro
     return cudaGetLastError();
 }
 
+// [emul-begin]
 // o: [n_rows, heads * dim_head] bf16, gates: [n_rows, heads] bf16;  o[row, h, :] *= sigmoid(gates[row, h])
 __global__ void __launch_bounds__(256)
 gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates, long long n_vec, int vec_per_row,
@@ -151,6 +158,8 @@ gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates,
     o[i] = f32_to_bf16x8(a);
 }
 
+// [emul-end]
+
 cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
                              cudaStream_t stream) {
     const int vec_per_row = heads * dim_head / 8;
@@ -167,6 +176,7 @@ cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int h
 // kernel keeps the whole function as a 128 KB table in shared memory (built once per process with the
 // fp32 formula torch uses, x * 0.5 * (1 + erff(x / sqrt 2)), rounded to bf16), so one element costs one
 // LDS.U16 and the result is the exact formula's for every bit pattern.
+// [emul-begin]
 constexpr int kGeluThreads = 1024;
 constexpr int kGeluLutBytes = 65536 * 2;
 
@@ -184,7 +194,7 @@ __device__ __forceinline__ unsigned gelu_lut2(const unsigned short* __restrict__
 
 __global__ void __launch_bounds__(kGeluThreads, 1)
 gelu_bf16_kernel(uint4* __restrict__ x, long long n_vec, const uint4* __restrict__ lut_g) {
-    extern __shared__ __align__(16) unsigned char gelu_smem[];
+    AL_DYN_SMEM(unsigned char, gelu_smem);
     uint4* lut4 = reinterpret_cast<uint4*>(gelu_smem);
     for (int i = threadIdx.x; i < kGeluLutBytes / 16; i += kGeluThreads) lut4[i] = __ldg(lut_g + i);
     __syncthreads();
@@ -205,6 +215,8 @@ gelu_bf16_kernel(uint4* __restrict__ x, long long n_vec, const uint4* __restrict
         x[i] = a;
     }
 }
+
+// [emul-end]
 
 cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream) {
     const long long n_vec = n / 8;

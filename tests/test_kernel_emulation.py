@@ -366,3 +366,81 @@ def test_randomised_emulation_subset(script, n, seed):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_emul", script), "--n", str(n), "--seed", str(seed)],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+# ---- row-wise bf16 operators of the RoFormer inference path (al_netops.cu), emulated ------------------------------------
+def _bf16(t):
+    """torch bf16 tensor -> numpy uint16 view (and back with _from_bf16)."""
+    import torch
+    return t.contiguous().view(torch.int16).numpy().view(np.uint16).copy()
+
+
+def _from_bf16(a, shape):
+    import torch
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16).reshape(shape)
+
+
+def test_netops_emulated_match_their_torch_definitions(emul):
+    """rmsnorm (+ deferred bias), rotary, sigmoid gate and the table-driven GELU against the PyTorch definitions used by
+    tests/test_netops.py (upstream RMSNorm / rotary_embed / gated attention / nn.GELU)."""
+    import torch
+    import torch.nn.functional as F
+    spec_ = importlib.util.spec_from_file_location("tnet", os.path.join(ROOT, "tests", "test_netops.py"))
+    tnet = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(tnet)
+    ref_gate_, ref_rmsnorm, ref_rotary_ = tnet.ref_gate_, tnet.ref_rmsnorm, tnet.ref_rotary_
+    P, LL, I, FL = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+    emul.emul_rmsnorm.argtypes = [P, P, P, P, LL, I, FL, FL]
+    emul.emul_rotary.argtypes = [P, P, P, LL, I, I, LL, I]
+    emul.emul_gate.argtypes = [P, P, LL, I, I]
+    emul.emul_gelu.argtypes = [P, LL, I]
+    for f in (emul.emul_rmsnorm, emul.emul_rotary, emul.emul_gate, emul.emul_gelu):
+        f.restype = None
+    g = torch.Generator().manual_seed(3)
+    # rmsnorm, with and without the deferred bias, dims of the three register tilings
+    for n, d, with_bias in [(37, 512, True), (19, 136, False), (9, 1024, True), (5, 2048, False)]:
+        x = torch.randn(n, d, generator=g).to(torch.bfloat16)
+        gamma = (1 + 0.1 * torch.randn(d, generator=g)).float()
+        bias = (0.1 * torch.randn(d, generator=g)).float() if with_bias else None
+        xr = x.clone()
+        ref = ref_rmsnorm(xr, gamma, bias)
+        xa, out = _bf16(x), np.zeros(n * d, np.uint16)
+        ga, ba = gamma.numpy().copy(), (None if bias is None else bias.numpy().copy())
+        emul.emul_rmsnorm(_p(xa), _p(ga), _p(ba), _p(out), n, d, float(d) ** 0.5, 1e-12)
+        got = _from_bf16(out, (n, d)).float()
+        assert float((got - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())
+        if with_bias:                                         # x += bias is stored back (the residual stream)
+            assert torch.equal(_from_bf16(xa, (n, d)), xr)
+    # rotary over a [batch, time, band] token grid
+    heads, dh, pos_div, pos_mod, n = 4, 32, 3, 7, 3 * 7 * 2
+    q = torch.randn(n, heads * dh, generator=g).to(torch.bfloat16)
+    k = torch.randn(n, heads * dh, generator=g).to(torch.bfloat16)
+    ang = torch.arange(pos_mod)[:, None].float() * (1.0 / (10000 ** (torch.arange(0, dh, 2).float() / dh)))[None]
+    cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()
+    qr, kr = q.clone(), k.clone()
+    ref_rotary_(qr, kr, cs, heads, dh, pos_div, pos_mod)
+    qa, ka, csa = _bf16(q), _bf16(k), cs.numpy().copy()
+    emul.emul_rotary(_p(qa), _p(ka), _p(csa), n, heads, dh, pos_div, pos_mod)
+    for got, ref in ((_from_bf16(qa, q.shape), qr), (_from_bf16(ka, k.shape), kr)):
+        assert float((got.float() - ref.float()).abs().max()) <= 2 ** -7 * float(ref.float().abs().max())
+    # gate
+    o = torch.randn(33, heads * dh, generator=g).to(torch.bfloat16)
+    gates = (2 * torch.randn(33, heads, generator=g)).to(torch.bfloat16)
+    orf = o.clone()
+    ref_gate_(orf, gates, heads, dh)
+    oa, gta = _bf16(o), _bf16(gates)
+    emul.emul_gate(_p(oa), _p(gta), 33, heads, dh)
+    assert float((_from_bf16(oa, o.shape).float() - orf.float()).abs().max()) <= 2 ** -7 * float(orf.float().abs().max())
+    # GELU: the table must reproduce torch's bf16 gelu for every bf16 bit pattern
+    bits = np.arange(65536, dtype=np.uint16)
+    xall = _from_bf16(bits, (65536,))
+    ref = F.gelu(xall.float()).to(torch.bfloat16)
+    xa = bits.copy()
+    emul.emul_gelu(_p(xa), 65536, 3)
+    got = _from_bf16(xa, (65536,))
+    # torch's CPU kernel evaluates x * (1 + erf) before the 0.5 and overflows above 1.7e38; below that the table is
+    # identical to torch's bf16 gelu for all but a few dozen inputs
+    ok = torch.isfinite(xall.float()) & (xall.float().abs() < 1e38)
+    gi, ri = got.view(torch.int16)[ok].int(), ref.view(torch.int16)[ok].int()
+    assert int((gi - ri).abs().max()) <= 1                    # one bf16 ulp where 1 + erf cancels (x in [-5, -3]): libm's erff
+    assert int((gi != ri).sum()) <= 64                        # (host emulation) and torch's differ in the last bits there

@@ -72,6 +72,43 @@ extern "C" int emul_istft(int n_fft, int hop, const float* spec, const float* ma
     return -1;
 }
 
+extern "C" void emul_rmsnorm(void* x, const float* gamma, const float* bias, void* out, long long n_rows, int dim, float scale,
+                             float eps) {
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    auto* xb = reinterpret_cast<__nv_bfloat16*>(x);
+    auto* ob = reinterpret_cast<__nv_bfloat16*>(out);
+    if (dim <= 512) emul_launch(dim3(grid), dim3(256), [&] { rmsnorm_bf16_kernel<2>(xb, gamma, bias, ob, n_rows, dim, scale, eps); });
+    else if (dim <= 1024) emul_launch(dim3(grid), dim3(256), [&] { rmsnorm_bf16_kernel<4>(xb, gamma, bias, ob, n_rows, dim, scale, eps); });
+    else emul_launch(dim3(grid), dim3(256), [&] { rmsnorm_bf16_kernel<8>(xb, gamma, bias, ob, n_rows, dim, scale, eps); });
+}
+
+extern "C" void emul_rotary(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head, long long pos_div,
+                            int pos_mod) {
+    const int vec_per_row = heads * dim_head / 8;
+    const long long n_vec = n_rows * vec_per_row;
+    emul_launch(dim3((unsigned)((n_vec + 255) / 256)), dim3(256), [&] {
+        rotary_bf16_kernel(reinterpret_cast<uint4*>(q), reinterpret_cast<uint4*>(k), reinterpret_cast<const float2*>(cs), n_vec,
+                           vec_per_row, dim_head, pos_div, pos_mod);
+    });
+}
+
+extern "C" void emul_gate(void* o, const void* gates, long long n_rows, int heads, int dim_head) {
+    const int vec_per_row = heads * dim_head / 8;
+    const long long n_vec = n_rows * vec_per_row;
+    emul_launch(dim3((unsigned)((n_vec + 255) / 256)), dim3(256), [&] {
+        gate_bf16_kernel(reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
+    });
+}
+
+extern "C" void emul_gelu(void* x, long long n, int grid_x) {
+    static std::vector<unsigned short> lut(65536);
+    emul_launch(dim3(256), dim3(256), [&] { gelu_lut_init_kernel(lut.data()); });
+    const long long n_vec = n / 8;
+    emul_launch(dim3(grid_x), dim3(kGeluThreads), [&] {
+        gelu_bf16_kernel(reinterpret_cast<uint4*>(x), n_vec, reinterpret_cast<const uint4*>(lut.data()));
+    });
+}
+
 extern "C" int emul_stft_pk(const float* track, long long n_valid, long long ch_stride, long long off0, long long off_step,
                             int n_chunks, int chunk_len, int center, int hop, int n_frames, const float* window,
                             const float* tw, const float* ctw_half, float* spec, int layout, int n_bins_out,
@@ -169,7 +206,7 @@ def region(path):
 
 def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu",
-                                            "al_istft_pk.cu", "al_stft_pk.cu")]
+                                            "al_istft_pk.cu", "al_stft_pk.cu", "al_netops.cu")]
     whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh", "fft32p_gen.cuh", "al_fftp.cuh")]   # taken whole
     deps = srcs + whole + [os.path.join(HERE, "cuda_emul.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):

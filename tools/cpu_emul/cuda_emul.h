@@ -22,6 +22,24 @@ static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)}; }
+// bfloat16 (round-to-nearest-even conversions, like cuda_bf16.h)
+struct __nv_bfloat16 { unsigned short v; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __bfloat162float(__nv_bfloat16 h) { return __uint_as_float((unsigned)h.v << 16); }
+static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+    unsigned u = __float_as_uint(f);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return __nv_bfloat16{(unsigned short)0x7FFF};   // NaN
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return __nv_bfloat16{(unsigned short)(u >> 16)};
+}
+static inline unsigned short __bfloat16_as_ushort(__nv_bfloat16 h) { return h.v; }
+static inline float2 __bfloat1622float2(__nv_bfloat162 h) { return float2{__bfloat162float(h.x), __bfloat162float(h.y)}; }
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)}; }
+#define __expf(x) std::exp((float)(x))      // glibc declares __expf itself
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 static thread_local dim3 threadIdx, blockIdx;
@@ -41,6 +59,8 @@ static std::vector<std::barrier<>*> g_warp_bar;
 static unsigned g_shfl[64][32];
 static inline void __syncwarp(unsigned = 0xffffffffu) { g_warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
 template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask);
+template <class T>
 static inline T __shfl_sync(unsigned, T v, int src) {
     static_assert(sizeof(T) == 4, "4-byte shuffles only");
     const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -56,6 +76,9 @@ alignas(16) static unsigned char g_smem[228 * 1024];
 static inline void al_cp_async16(void* d, const void* s) { std::memcpy(d, s, 16); }
 static inline void al_cp_async_commit() {}
 template <int N> static inline void al_cp_async_wait() {}
+
+template <class T>
+static inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)((threadIdx.x & 31) ^ lane_mask)); }
 
 template <class F>
 static void emul_launch(dim3 grid, dim3 block, F f) {
