@@ -19,10 +19,15 @@ timeout 200 ncu --set full --clock-control none --profile-from-start off -k rege
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-mode --track-seconds 60 > $OUT/prof_bench_istft.log 2>&1 ; echo "rc=$?"
 ncu -i $OUT/prof_bench_istft.ncu-rep --page raw --csv > $OUT/prof_bench_istft_raw.csv 2>/dev/null
 echo "== ncu full: spectral kernels, kernel_bench --once"
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:"stft_pk2_kernel|istft_pk2_kernel|ola_gather_kernel|resample_rb_kernel|istft_kernel|gelu_bf16" \
-    -o $OUT/prof_k -f python tools/kernel_bench.py --once --cases roformer_2048_441,htdemucs_4096_1024 --gelu > $OUT/prof_k.log 2>&1 ; echo "rc=$?"
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:"stft_pk2_kernel|istft_pk2_kernel|ola_gather_kernel|resample_rb_kernel|istft_kernel|stft_kernel|gelu_bf16" \
+    -o $OUT/prof_k -f python tools/kernel_bench.py --once --cases roformer_2048_441,htdemucs_4096_1024,mdx_6144_1024 --gelu > $OUT/prof_k.log 2>&1 ; echo "rc=$?"
 ncu -i $OUT/prof_k.ncu-rep --page raw --csv > $OUT/prof_k_raw.csv 2>/dev/null
 ncu -i $OUT/prof_k.ncu-rep --page source --csv -k regex:istft_pk2 > $OUT/prof_k_istft_source.csv 2>/dev/null
 ncu -i $OUT/prof_k.ncu-rep --page source --csv -k regex:resample_rb > $OUT/prof_k_resample_source.csv 2>/dev/null
+ncu -i $OUT/prof_k.ncu-rep --page source --csv -k regex:'^(void )?(al::)?istft_kernel' > $OUT/prof_k_istft_generic_source.csv 2>/dev/null
+ncu -i $OUT/prof_k.ncu-rep --page source --csv -k regex:'^(void )?(al::)?stft_kernel' > $OUT/prof_k_stft_generic_source.csv 2>/dev/null
+ncu -i $OUT/prof_k.ncu-rep --page source --csv -k regex:stft_pk2 > $OUT/prof_k_stft_pk_source.csv 2>/dev/null
+# phase split of every captured kernel (SASS view cut at the CTA barriers)
+for f in $OUT/prof_k_*_source.csv; do for i in 0 1 2 3 4 5; do python tools/ncu_phase_split.py $f $i 2>/dev/null; done > ${f%_source.csv}_phases.txt; done
 rm -f $OUT/prof_k.ncu-rep
 ls -la $OUT
