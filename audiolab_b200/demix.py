@@ -179,6 +179,44 @@ class MdxDemixer:
         return track[:, trim: trim + n]
 
 
+    # ---- secondary stem by spectral inversion (invert_using_spec, stem_separator.py:105) -------------------
+    _inv_plan = None
+
+    @torch.no_grad()
+    def invert_stem(self, raw_mix: torch.Tensor, stem: torch.Tensor) -> torch.Tensor:
+        """Upstream ``spec_utils.invert_stem``: STFT (n_fft 2048, hop 1024, zero centre padding -- librosa >= 0.10) of the
+        match-mix pass and of the primary stem, the in-tree "invert_p" arithmetic
+        (/root/reference/modules/rvc/infer/lib/uvr5_pack/lib_v5/spec_utils.py:614-623)
+        ``v = y - max(|X|, |y|) * exp(1j * angle(X))``, iSTFT, sign flipped.  [2, n] x 2 -> [2, n] (the tail past
+        hop * (n // hop), which librosa's istft does not produce, is zero)."""
+        n_fft, hop = 2048, 1024
+        if MdxDemixer._inv_plan is None:
+            MdxDemixer._inv_plan = sp.StftPlan(n_fft, hop)
+        plan = MdxDemixer._inv_plan
+        raw_mix, stem = _check_mix(raw_mix), _check_mix(stem)
+        n = raw_mix.shape[1]
+        T = 1 + n // hop
+        # zero centre padding = a chunk that starts n_fft/2 before the track: K1 reads zeros outside [0, n)
+        kw = dict(chunk_len=n + n_fft, n_chunks=1, off0=-(n_fft // 2), off_step=0, n_valid=n, center_pad=0, n_frames=T,
+                  layout=sp.FRAME_MAJOR)
+        X = plan.stft(raw_mix, **kw)                                   # c64 [2, T, F]
+        y = plan.stft(stem, **kw)
+        x_mag, y_mag = X.abs(), y.abs()
+        max_mag = torch.where(x_mag >= y_mag, x_mag, y_mag)
+        unit = torch.where(x_mag > 0, X / x_mag.clamp(min=1e-30), torch.ones_like(X))   # exp(1j * angle(X)); angle(0) = 0
+        v = (y - max_mag * unit).contiguous()
+        wave = plan.istft(v, n_chunks=1, channels=2, layout=sp.FRAME_MAJOR)              # [1, 1, 2, hop * (T - 1)]
+        out = torch.zeros_like(raw_mix)
+        m = min(n, wave.shape[-1])
+        out[:, :m] = -wave[0, 0, :, :m]
+        return out
+
+    @torch.no_grad()
+    def secondary_by_inversion(self, mix: torch.Tensor, primary: torch.Tensor) -> torch.Tensor:
+        """``invert_stem(demix(mix, is_match_mix=True), primary)`` -- upstream MDXSeparator.separate with invert_using_spec."""
+        return self.invert_stem(self.demix_windowed(mix, is_match_mix=True), primary)
+
+
 # ======================================================================================
 # BS-RoFormer / Mel-Band RoFormer
 # ======================================================================================

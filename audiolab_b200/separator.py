@@ -219,7 +219,11 @@ class Separator:
         stems = inst.run(mix)                                  # [S, 2, n]
         out = {name: stems[i] for i, name in enumerate(inst.stem_names)}
         if len(inst.stem_names) == 1:
-            out[inst.secondary_stem] = sp.sub(mix, stems[0])   # `mix - primary`
+            if self.invert_using_spec and inst.arch == "mdx":
+                # upstream MDXSeparator.separate: match-mix pass + spec_utils.invert_stem
+                out[inst.secondary_stem] = inst.demixer.secondary_by_inversion(mix, stems[0])
+            else:
+                out[inst.secondary_stem] = sp.sub(mix, stems[0])   # `mix - primary`
         return out
 
     def separate(self, audio_file_path: str) -> List[str]:

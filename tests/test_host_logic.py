@@ -194,3 +194,60 @@ def test_separator_arch_resolution():
     assert _arch_of("UVR-MDX-NET-Voc_FT.onnx") == "mdx"
     assert _arch_of("htdemucs_6s.yaml") == "htdemucs"
     assert _arch_of("17_HP-Wind_Inst-UVR.pth") == "vr"
+
+
+class _TorchPlan:
+    """CPU stand-in for spectral.StftPlan with al_stft / al_istft semantics (chunk gather with zeros outside the track,
+    reflection about the chunk ends by `center_pad`, FRAME_MAJOR layout) on torch.fft -- host-logic tests only."""
+
+    def __init__(self, n_fft, hop):
+        self.n_fft, self.hop, self.win = n_fft, hop, torch.hann_window(n_fft)
+
+    def stft(self, track, *, chunk_len, n_chunks=1, off0=0, off_step=0, n_valid=None, center_pad=None, n_frames=None,
+             layout=0, **_):
+        assert layout == 0
+        ch, n = track.shape
+        n_valid = n if n_valid is None else n_valid
+        center_pad = self.n_fft // 2 if center_pad is None else center_pad
+        out = []
+        for c in range(n_chunks):
+            idx = torch.arange(off0 + c * off_step, off0 + c * off_step + chunk_len)
+            ok = (idx >= 0) & (idx < n_valid)
+            chunk = torch.zeros(ch, chunk_len)
+            chunk[:, ok] = track[:, idx[ok]]
+            j = torch.arange(-center_pad, (n_frames - 1) * self.hop - center_pad + self.n_fft)
+            j = torch.where(j < 0, -j, j)
+            j = torch.where(j >= chunk_len, 2 * (chunk_len - 1) - j, j)
+            S = torch.stft(chunk[:, j], self.n_fft, self.hop, window=self.win, center=False, return_complex=True)
+            out.append(S.transpose(1, 2))                                   # [ch, T, F]
+        return torch.cat(out, 0).contiguous()
+
+    def istft(self, spec, *, n_chunks, channels, layout=0, **_):
+        assert layout == 0 and n_chunks == 1
+        w = torch.istft(spec.transpose(1, 2), self.n_fft, self.hop, window=self.win, center=True)
+        return w[None, None]                                                # [1, 1, ch, hop * (T - 1)]
+
+
+def test_mdx_secondary_stem_by_spectral_inversion_host_logic(monkeypatch):
+    """MdxDemixer.invert_stem (device path: two al_stft with zero centre padding, the in-tree
+    "invert_p" arithmetic, al_istft) against the oracle's torch / librosa-convention restatement -- the kernels are
+    replaced by their torch definitions, so this pins the host logic (padding convention, layout, length, sign)."""
+    import audiolab_b200.demix as demix
+    from oracle import mdx as omdx
+    monkeypatch.setattr(demix, "_check_mix", lambda m, channels=2: m.contiguous().float())
+    monkeypatch.setattr(demix.MdxDemixer, "_inv_plan", _TorchPlan(2048, 1024))
+    d = object.__new__(demix.MdxDemixer)
+    for n in (44100, 1024 * 7, 5000):
+        mix = torch.tensor(synth_mix(n, seed=n))
+        stem = 0.6 * mix.flip(0) + 0.1 * torch.tensor(synth_mix(n, seed=n + 1))
+        got = d.invert_stem(mix, stem)
+        ref = omdx.invert_stem(mix.numpy(), stem.numpy())
+        m = ref.shape[1]
+        assert got.shape == (2, n) and m == 1024 * (n // 1024)
+        assert float((got[:, :m] - torch.tensor(ref)).abs().max()) <= 2e-5
+        assert not got[:, m:].any()
+    # a stem equal to the mix inverts to (almost) silence; a silent stem inverts to minus-minus the mix = the mix's STFT round trip
+    mix = torch.tensor(synth_mix(20480, seed=3))
+    assert float(d.invert_stem(mix, mix).abs().max()) <= 1e-5
+    back = d.invert_stem(mix, torch.zeros_like(mix))
+    assert float((back[:, 1024:-1024] - mix[:, 1024:-1024]).abs().max()) <= 1e-4
