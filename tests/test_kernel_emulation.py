@@ -446,3 +446,49 @@ def test_netops_emulated_match_their_torch_definitions(emul):
     ne = got.view(torch.int16)[ok] != ref.view(torch.int16)[ok]
     assert int(ne.sum()) <= 64
     assert float((got.float()[ok] - ref.float()[ok]).abs().max()) <= 2e-5
+
+
+def test_invert_stem_composition_on_emulated_kernels(emul):
+    """Row a14 end to end on the host: the exact kernel calls MdxDemixer.invert_stem makes (packed al_stft with a chunk that
+    starts n_fft/2 before the track and no reflection = librosa's zero centre padding; generic al_istft, frame-major)
+    around the in-tree "invert_p" arithmetic, against the oracle's librosa-convention restatement."""
+    import torch
+    from oracle import mdx as omdx
+    from oracle.synth import synth_mix
+    _bind_fft(emul)
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emul.emul_stft_pk.argtypes = [P, LL, LL, LL, LL, I, I, I, I, I, P, P, P, P, I, I, I, I, I]
+    emul.emul_stft_pk.restype = I
+    n_fft, hop = 2048, 1024
+    wa, _, tw, _, _ = _plan_tables(n_fft, hop)
+    half = np.zeros((544, 2), np.float32)
+    k = np.arange(513)
+    half[:513, 0], half[:513, 1] = 0.5 * np.cos(-2 * np.pi * k / n_fft), 0.5 * np.sin(-2 * np.pi * k / n_fft)
+
+    def stft_dev(x):
+        n = x.shape[1]
+        T = 1 + n // hop
+        x = np.ascontiguousarray(x)
+        out = np.full(2 * T * 1025 * 2, np.nan, np.float32)
+        rc = emul.emul_stft_pk(_p(x), n, n, -(n_fft // 2), 0, 1, n + n_fft, 0, hop, T, _p(wa), _p(tw), _p(half), _p(out), 0, 1025, 0,
+                               0, 3)
+        assert rc >= 1 and np.isfinite(out).all()
+        return torch.view_as_complex(torch.tensor(out.reshape(2, T, 1025, 2)))
+
+    for n in (5000, 1024 * 9):
+        mix = synth_mix(n, seed=n)
+        stem = (0.6 * mix[::-1] + 0.1 * synth_mix(n, seed=n + 1)).astype(np.float32)
+        X, y = stft_dev(mix), stft_dev(stem)
+        xm, ym = X.abs(), y.abs()
+        unit = torch.where(xm > 0, X / xm.clamp(min=1e-30), torch.ones_like(X))
+        v = torch.view_as_real((y - torch.where(xm >= ym, xm, ym) * unit).contiguous()).numpy()
+        T = v.shape[1]
+        out_len = (T - 1) * hop
+        _, ws, tw2, ctw2, env = _plan_tables(n_fft, hop, T)
+        wave = np.full((2, out_len), np.nan, np.float32)
+        segs = emul.emul_istft(n_fft, hop, _p(np.ascontiguousarray(v)), None, 0, 1025, T, 0, 1, 1, 2, 0, 0, _p(ws), _p(tw2), _p(ctw2),
+                               _p(env), n_fft // 2, out_len, None, _p(wave), out_len, 2 * out_len, 0, 0, out_len)
+        assert segs >= 1 and np.isfinite(wave).all()
+        ref = omdx.invert_stem(mix, stem)
+        assert ref.shape[1] == out_len
+        assert np.abs(-wave - ref).max() <= 2e-5
