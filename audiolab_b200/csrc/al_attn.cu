@@ -1,0 +1,173 @@
+// Band-axis attention of the RoFormer mask network (opt-in, AUDIOLAB_B200_BAND_ATTN=1): softmax(Q K^T / sqrt(d)) V over the
+// <= 64 frequency bands of one (batch, frame), head by head -- upstream Attention.forward inside the frequency
+// transformer (driven by MDXCSeparator.demix behind stem_separator.py:281).
+//
+// Why a kernel of our own: for 62-token sequences cuDNN picks an sm_80 `wmma` flash kernel that moves q, k, v, o at
+// ~2.4 TB/s (profiles/r01j_launches_bench_step.txt, 7 % of the step).  The problem is HBM-bound (0.03 flop/B short of
+// nothing: 1 MFLOP per 32 KB), so warp-level mma.sync (m16n8k16, bf16 -> fp32) is enough to follow the memory system;
+// tcgen05 tiles of 128 rows would be 52 % padding here.
+//
+// q, k, v, o: [n_seq * F, H * 64] bf16, token (s, f) in row s * F + f (the token-major layout of the residual stream,
+// read and written in place -- no transposition copies).  One CTA = 4 warps = one (s, h); warp w owns query rows
+// 16 w .. 16 w + 15.  Q, K, V tiles (64 x 64, rows >= F zero) sit in shared memory with a 72-element row stride
+// (conflict-free 32-bit fragment loads); S = Q K^T and O = P V stay in mma accumulator registers, the softmax runs on
+// the accumulator fragments (row max / sum over the 4 lanes that share a row), P is re-used as the A operand of the second
+// product without leaving registers.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "al_kernels.h"
+
+namespace al {
+
+// [emul-begin]
+constexpr int kBaD = 64;          // head dimension
+constexpr int kBaF = 64;          // padded sequence length (bands)
+constexpr int kBaLd = 72;         // shared-memory row stride in bf16 elements (144 B: rows shift by 4 banks)
+
+#ifndef AL_CPU_EMUL
+// D (16x8, fp32) += A (16x16, bf16, row) * B (16x8, bf16, col); fragment layouts: PTX ISA "mma.m16n8k16"
+//   a0..a3: (row lane/4 [+8 for a1, a3], cols 2 (lane%4) + {0,1} [+8 for a2, a3])
+//   b0, b1: (k = 2 (lane%4) + {0,1} [+8 for b1], n = lane/4)
+//   d0..d3: (row lane/4 [+8 for d2, d3], cols 2 (lane%4) + {0,1})
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128)
+band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                      const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, int F, int H, float scale) {
+    __shared__ __align__(16) __nv_bfloat16 Qs[kBaF * kBaLd];
+    __shared__ __align__(16) __nv_bfloat16 Ks[kBaF * kBaLd];
+    __shared__ __align__(16) __nv_bfloat16 Vs[kBaF * kBaLd];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x / H, h = blockIdx.x - s * H;
+    const long long ld = (long long)H * kBaD;                       // elements per token row
+    const long long base = (long long)s * F * ld + (long long)h * kBaD;
+
+    // ---- stage Q, K, V: 64 rows x 8 vectors of 16 B each; rows >= F are zero ----------------------------------
+    for (int i = tid; i < kBaF * 8; i += 128) {
+        const int row = i >> 3, c8 = (i & 7) * 8;
+        uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq;
+        if (row < F) {
+            const long long g = base + (long long)row * ld + c8;
+            vq = __ldg(reinterpret_cast<const uint4*>(q + g));
+            vk = __ldg(reinterpret_cast<const uint4*>(k + g));
+            vv = __ldg(reinterpret_cast<const uint4*>(v + g));
+        }
+        *reinterpret_cast<uint4*>(Qs + row * kBaLd + c8) = vq;
+        *reinterpret_cast<uint4*>(Ks + row * kBaLd + c8) = vk;
+        *reinterpret_cast<uint4*>(Vs + row * kBaLd + c8) = vv;
+    }
+    __syncthreads();
+
+    const int r0 = 16 * warp + (lane >> 2);                          // this lane's rows: r0 and r0 + 8
+    const int c2 = 2 * (lane & 3);
+    // ---- S = Q K^T ---------------------------------------------------------------------------------------------
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const __nv_bfloat16* p0 = Qs + r0 * kBaLd + ks * 16 + c2;
+        qa[ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+        qa[ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kBaLd);
+        qa[ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        qa[ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * kBaLd + 8);
+    }
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+        const __nv_bfloat16* kp = Ks + (nt * 8 + (lane >> 2)) * kBaLd + c2;   // B[k][n] = K[n][k]
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t b[2];
+            b[0] = *reinterpret_cast<const uint32_t*>(kp + ks * 16);
+            b[1] = *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8);
+            mma_bf16_16816(sc[nt], qa[ks], b);
+        }
+    }
+    // ---- softmax over the keys (columns); keys >= F are masked out ------------------------------------------------
+    float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int key = nt * 8 + c2 + (i & 1);
+            sc[nt][i] = key < F ? sc[nt][i] * scale : -3.0e38f;
+        }
+        mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t pa[4][4];                                               // P as the A operand of P V: k-step = 16 keys = 2 n-tiles
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const float e0 = __expf(sc[nt][0] - mx0), e1 = __expf(sc[nt][1] - mx0);
+        const float e2 = __expf(sc[nt][2] - mx1), e3 = __expf(sc[nt][3] - mx1);
+        sum0 += e0 + e1;
+        sum1 += e2 + e3;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(e0, e1);         // a0 / a2: row r0,     cols (+8 for the odd tile)
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(e2, e3);         // a1 / a3: row r0 + 8
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    // ---- O = P V -------------------------------------------------------------------------------------------------
+    const unsigned short* vs16 = reinterpret_cast<const unsigned short*>(Vs);
+    __nv_bfloat16* orow = Qs;                                        // the warp's own 16 Q rows become its output rows
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {                                 // nt = tile of 8 head-dimension columns
+        float oc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n = nt * 8 + (lane >> 2);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {                             // B[k][n] = V[key k][n]: two keys per register
+            const int k0 = ks * 16 + c2;
+            uint32_t b[2];
+            b[0] = (uint32_t)vs16[k0 * kBaLd + n] | ((uint32_t)vs16[(k0 + 1) * kBaLd + n] << 16);
+            b[1] = (uint32_t)vs16[(k0 + 8) * kBaLd + n] | ((uint32_t)vs16[(k0 + 9) * kBaLd + n] << 16);
+            mma_bf16_16816(oc, pa[ks], b);
+        }
+        *reinterpret_cast<uint32_t*>(orow + r0 * kBaLd + nt * 8 + c2) = pack_bf16x2(oc[0] * inv0, oc[1] * inv0);
+        *reinterpret_cast<uint32_t*>(orow + (r0 + 8) * kBaLd + nt * 8 + c2) = pack_bf16x2(oc[2] * inv1, oc[3] * inv1);
+    }
+    __syncwarp();
+    // ---- the warp's 16 rows leave as 16-byte vectors ---------------------------------------------------------------
+#pragma unroll
+    for (int i = lane; i < 16 * 8; i += 32) {
+        const int row = 16 * warp + (i >> 3), c8 = (i & 7) * 8;
+        if (row < F)
+            *reinterpret_cast<uint4*>(o + base + (long long)row * ld + c8) = *reinterpret_cast<const uint4*>(orow + row * kBaLd + c8);
+    }
+}
+// [emul-end]
+
+cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, long long n_seq, int F, int heads,
+                                  float scale, cudaStream_t stream) {
+    if (n_seq <= 0) return cudaSuccess;
+    const long long ctas = n_seq * heads;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    band_attn_bf16_kernel<<<(unsigned)ctas, 128, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+        reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o), F, heads, scale);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace al

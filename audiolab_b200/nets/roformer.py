@@ -21,7 +21,11 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+import os
+
 from ..configs import RoformerConfig
+
+_BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
 
 
 class RMSNorm(nn.Module):
@@ -252,13 +256,17 @@ class RoformerMaskNet(nn.Module):
                     netops.rotary_(q, k, self._cos_sin(attn.rotary_embed, f, x2.device), h, dh, 1, f)
             # attention over time: batch b, "heads" (band, head); over bands: batch (b, t).  Strided views of the
             # token-major buffers -- no transposition copies around the attention.
-            shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
-            o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
-                                               v.view(shape).transpose(1, 2))
-            o = o.transpose(1, 2)
-            if not o.is_contiguous():
-                o = o.contiguous()
-            o2 = o.view(-1, inner)
+            if not time_axis and _BAND_ATTN and dh == 64 and f <= 64:
+                # opt-in (AUDIOLAB_B200_BAND_ATTN=1): our mma.sync kernel for the short band axis (csrc/al_attn.cu)
+                o2 = netops.band_attention(q, k, v, b * t, f, h, dh)
+            else:
+                shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
+                o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
+                                                   v.view(shape).transpose(1, 2))
+                o = o.transpose(1, 2)
+                if not o.is_contiguous():
+                    o = o.contiguous()
+                o2 = o.view(-1, inner)
             gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
             netops.gate_sigmoid_(o2, gates, h, dh)
             x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())

@@ -76,6 +76,47 @@ def test_fused_axial_host_logic_matches_module_path(kind, monkeypatch):
     assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
 
 
+def ref_band_attention(q, k, v, n_seq, seq_len, heads, dh):
+    shp = (n_seq, seq_len, heads, dh)
+    o = F.scaled_dot_product_attention(q.view(shp).transpose(1, 2).float(), k.view(shp).transpose(1, 2).float(),
+                                       v.view(shp).transpose(1, 2).float())
+    return o.transpose(1, 2).reshape(q.shape).to(q.dtype)
+
+
+def test_fused_axial_host_logic_with_band_attention_kernel(monkeypatch):
+    """The opt-in band-axis attention (AUDIOLAB_B200_BAND_ATTN=1, csrc/al_attn.cu): token-major q / k / v of the frequency
+    transformer go to the kernel as [b*t sequences x f bands]; with the kernel replaced by its torch definition the fused
+    path must still equal the module path."""
+    import audiolab_b200.netops as netops
+    import audiolab_b200.nets.roformer as rof
+    torch.manual_seed(0)
+    cfg = RoformerConfig(dim=32, depth=1, heads=2, dim_head=64, chunk_size=441 * 12)
+    net = RoformerMaskNet(cfg).eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    calls = []
+
+    def spy(q, k, v, n_seq, seq_len, heads, dh):
+        calls.append((tuple(q.shape), n_seq, seq_len, heads, dh))
+        return ref_band_attention(q, k, v, n_seq, seq_len, heads, dh)
+
+    monkeypatch.setattr(netops, "rmsnorm", ref_rmsnorm)
+    monkeypatch.setattr(netops, "rotary_", ref_rotary_)
+    monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    monkeypatch.setattr(netops, "gelu_", ref_gelu_)
+    monkeypatch.setattr(netops, "band_attention", spy)
+    monkeypatch.setattr(rof, "_BAND_ATTN", True)
+    net._fused_dtype = torch.float32
+    b, t, f = 2, 13, len(net.band_split.dim_inputs)
+    x = torch.randn(b, t, f, cfg.dim)
+    with torch.no_grad():
+        ref = net.final_norm(net._axial(x.clone()))
+        got = net._axial_fused(x.clone())
+    assert calls and all(c == ((b * t * f, 128), b * t, f, 2, 64) for c in calls)
+    assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_netops_refuse_cpu_tensors():
     import audiolab_b200.netops as netops
     x = torch.zeros(4, 64, dtype=torch.bfloat16)
@@ -187,3 +228,16 @@ def test_fused_bf16_mask_matches_autocast_module_path(cuda, kind):
     assert fused.shape == m32.shape and torch.isfinite(torch.view_as_real(fused)).all()
     rel = float((torch.view_as_real(fused) - torch.view_as_real(m32)).norm() / torch.view_as_real(m32).norm())
     assert rel <= 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("AUDIOLAB_B200_BAND_ATTN") != "1",
+                    reason="opt-in kernel (csrc/al_attn.cu): emulation-tested, not yet run on a GPU -- set AUDIOLAB_B200_BAND_ATTN=1")
+@pytest.mark.parametrize("F_,H,n_seq", [(62, 8, 700), (64, 8, 33), (17, 4, 5)])
+def test_band_attention_kernel(cuda, F_, H, n_seq):
+    import audiolab_b200.netops as netops
+    g = torch.Generator().manual_seed(F_ + H)
+    q, k, v = (torch.randn(n_seq * F_, H * 64, generator=g).to(torch.bfloat16).to(cuda) for _ in range(3))
+    got = netops.band_attention(q, k, v, n_seq, F_, H, 64).float()
+    ref = ref_band_attention(q, k, v, n_seq, F_, H, 64).float()
+    assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())

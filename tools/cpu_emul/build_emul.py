@@ -100,6 +100,13 @@ extern "C" void emul_gate(void* o, const void* gates, long long n_rows, int head
     });
 }
 
+extern "C" void emul_band_attn(const void* q, const void* k, const void* v, void* o, int n_seq, int F, int H, float scale) {
+    emul_launch(dim3(n_seq * H), dim3(128), [&] {
+        band_attn_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                              reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o), F, H, scale);
+    });
+}
+
 extern "C" void emul_gelu(void* x, long long n, int grid_x) {
     static std::vector<unsigned short> lut(65536);
     emul_launch(dim3(256), dim3(256), [&] { gelu_lut_init_kernel(lut.data()); });
@@ -206,7 +213,7 @@ def region(path):
 
 def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in ("al_kernels.h", "al_ola.cu", "al_resample.cu", "al_stft.cu", "al_istft.cu",
-                                            "al_istft_pk.cu", "al_stft_pk.cu", "al_netops.cu")]
+                                            "al_istft_pk.cu", "al_stft_pk.cu", "al_netops.cu", "al_attn.cu")]
     whole = [os.path.join(CSRC, f) for f in ("fft32_gen.cuh", "al_fft.cuh", "fft32p_gen.cuh", "al_fftp.cuh")]   # taken whole
     deps = srcs + whole + [os.path.join(HERE, "cuda_emul.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) > os.path.getmtime(d) for d in deps):

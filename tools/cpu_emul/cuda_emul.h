@@ -45,6 +45,8 @@ typedef void* cudaStream_t;
 static thread_local dim3 threadIdx, blockIdx;
 static dim3 blockDim, gridDim;
 #define __global__
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
@@ -79,6 +81,30 @@ template <int N> static inline void al_cp_async_wait() {}
 
 template <class T>
 static inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, (int)((threadIdx.x & 31) ^ lane_mask)); }
+
+// mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 as a warp collective: every lane publishes its fragments, then
+// computes its four outputs from the assembled 16x16 A and 16x8 B (fragment layouts of the PTX ISA; CuTe states the same
+// in cute/atom/mma_traits_sm80.hpp: A (m = lane/4 + 8 v1, k = 2 (lane%4) + v0 + 8 v2), B (n = lane/4, k = 2 (lane%4) + v0 + 8 v1),
+// C (m = lane/4 + 8 v1, n = 2 (lane%4) + v0)).
+static unsigned g_mma_a[64][32][4], g_mma_b[64][32][2];
+static inline void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int i = 0; i < 4; ++i) g_mma_a[w][l][i] = a[i];
+    for (int i = 0; i < 2; ++i) g_mma_b[w][l][i] = b[i];
+    g_warp_bar[w]->arrive_and_wait();
+    auto bf = [](unsigned u, int half) { return __uint_as_float(((u >> (16 * half)) & 0xFFFFu) << 16); };
+    for (int i = 0; i < 4; ++i) {
+        const int row = (int)(l >> 2) + 8 * (i >> 1), col = 2 * (int)(l & 3) + (i & 1);
+        float acc = d[i];
+        for (int k = 0; k < 16; ++k) {
+            const int la = (row & 7) * 4 + (k & 7) / 2, ra = (row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0);
+            const int lb = col * 4 + (k & 7) / 2, rb = k >= 8 ? 1 : 0;
+            acc += bf(g_mma_a[w][la][ra], k & 1) * bf(g_mma_b[w][lb][rb], k & 1);
+        }
+        d[i] = acc;
+    }
+    g_warp_bar[w]->arrive_and_wait();
+}
 
 template <class F>
 static void emul_launch(dim3 grid, dim3 block, F f) {
