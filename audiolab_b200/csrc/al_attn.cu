@@ -12,7 +12,8 @@
 // 16 w .. 16 w + 15.  Q, K, V tiles (64 x 64, rows >= F zero) sit in shared memory with a 72-element row stride
 // (conflict-free 32-bit fragment loads); S = Q K^T and O = P V stay in mma accumulator registers, the softmax runs on
 // the accumulator fragments (row max / sum over the 4 lanes that share a row), P is re-used as the A operand of the second
-// product without leaving registers.
+// product without leaving registers.  With `gates` the sigmoid gate of upstream's Attention (out * to_gates(x).sigmoid())
+// is folded into the final normalisation, which removes the separate gate pass for this axis.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,7 +46,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __global__ void __launch_bounds__(128)
 band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                      const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, int F, int H, float scale) {
+                      const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o,
+                      const __nv_bfloat16* __restrict__ gates, int F, int H, float scale) {
     __shared__ __align__(16) __nv_bfloat16 Qs[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Ks[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Vs[kBaF * kBaLd];
@@ -127,7 +129,12 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
     sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    if (gates) {   // upstream Attention: out * to_gates(x).sigmoid(), gates [n_seq * F, H]; folded into the normalisation
+        const long long t0 = (long long)s * F + r0;
+        if (r0 < F) inv0 *= 1.f / (1.f + __expf(-__bfloat162float(gates[t0 * H + h])));
+        if (r0 + 8 < F) inv1 *= 1.f / (1.f + __expf(-__bfloat162float(gates[(t0 + 8) * H + h])));
+    }
     // ---- O = P V -------------------------------------------------------------------------------------------------
     const unsigned short* vs16 = reinterpret_cast<const unsigned short*>(Vs);
     __nv_bfloat16* orow = Qs;                                        // the warp's own 16 Q rows become its output rows
@@ -158,14 +165,15 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 }
 // [emul-end]
 
-cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, long long n_seq, int F, int heads,
-                                  float scale, cudaStream_t stream) {
+cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, long long n_seq,
+                                  int F, int heads, float scale, cudaStream_t stream) {
     if (n_seq <= 0) return cudaSuccess;
     const long long ctas = n_seq * heads;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     band_attn_bf16_kernel<<<(unsigned)ctas, 128, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-        reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o), F, heads, scale);
+        reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
+        reinterpret_cast<const __nv_bfloat16*>(gates), F, heads, scale);
     count_launch();
     return cudaGetLastError();
 }

@@ -71,15 +71,21 @@ def gelu_(x: torch.Tensor) -> torch.Tensor:
 
 
 def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, seq_len: int, heads: int,
-                   dim_head: int) -> torch.Tensor:
+                   dim_head: int, gates: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T / sqrt(dim_head)) v per (sequence, head) on token-major [n_seq * seq_len, heads * dim_head] buffers
-    (al_attn.cu; seq_len <= 64, dim_head == 64).  Returns a new [n_seq * seq_len, heads * dim_head] tensor."""
+    (al_attn.cu; seq_len <= 64, dim_head == 64).  With `gates` [n_seq * seq_len, heads] the output is also multiplied by
+    sigmoid(gates) per (token, head).  Returns a new [n_seq * seq_len, heads * dim_head] tensor."""
     for t, name in ((q, "q"), (k, "k"), (v, "v")):
         _check_bf16_rows(t, name)
     if q.shape != k.shape or q.shape != v.shape or tuple(q.shape) != (n_seq * seq_len, heads * dim_head):
         raise ValueError("q, k, v must be [n_seq * seq_len, heads * dim_head]")
+    if gates is not None:
+        _check_bf16_rows(gates, "gates")
+        if tuple(gates.shape) != (q.shape[0], heads):
+            raise ValueError("gates must be [n_seq * seq_len, heads]")
     o = torch.empty_like(q)
-    _lib.check(_lib.lib().al_band_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), int(n_seq), int(seq_len),
+    _lib.check(_lib.lib().al_band_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                                 None if gates is None else gates.data_ptr(), int(n_seq), int(seq_len),
                                                  int(heads), int(dim_head), float(dim_head) ** -0.5, _stream()),
                "al_band_attention_bf16")
     return o

@@ -257,8 +257,11 @@ class RoformerMaskNet(nn.Module):
             # attention over time: batch b, "heads" (band, head); over bands: batch (b, t).  Strided views of the
             # token-major buffers -- no transposition copies around the attention.
             if not time_axis and _BAND_ATTN and dh == 64 and f <= 64:
-                # opt-in (AUDIOLAB_B200_BAND_ATTN=1): our mma.sync kernel for the short band axis (csrc/al_attn.cu)
-                o2 = netops.band_attention(q, k, v, b * t, f, h, dh)
+                # opt-in (AUDIOLAB_B200_BAND_ATTN=1): our mma.sync kernel for the short band axis (csrc/al_attn.cu),
+                # with the sigmoid gate folded into its epilogue
+                gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
+                o2 = netops.band_attention(q, k, v, b * t, f, h, dh, gates=gates)
+                x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
             else:
                 shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
                 o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
@@ -267,9 +270,9 @@ class RoformerMaskNet(nn.Module):
                 if not o.is_contiguous():
                     o = o.contiguous()
                 o2 = o.view(-1, inner)
-            gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
-            netops.gate_sigmoid_(o2, gates, h, dh)
-            x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
+                gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
+                netops.gate_sigmoid_(o2, gates, h, dh)
+                x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
             lin1, lin2 = ff.net[1], ff.net[4]
             xn = netops.rmsnorm(x2, ff.net[0].gamma.detach())
             hid = netops.gelu_(F.linear(xn, self._bf16(lin1.weight), self._bf16(lin1.bias)))

@@ -494,24 +494,28 @@ def test_invert_stem_composition_on_emulated_kernels(emul):
         assert np.abs(-wave - ref).max() <= 2e-5
 
 
-@pytest.mark.parametrize("F,H,n_seq", [(62, 8, 3), (64, 2, 2), (17, 4, 2)])
-def test_band_attention_emulated_matches_torch_sdpa(emul, F, H, n_seq):
+@pytest.mark.parametrize("F,H,n_seq,gated", [(62, 8, 3, True), (64, 2, 2, False), (17, 4, 2, True)])
+def test_band_attention_emulated_matches_torch_sdpa(emul, F, H, n_seq, gated):
     """Opt-in band-axis attention kernel (al_attn.cu, mma.sync m16n8k16 emulated as a warp collective from the PTX fragment
     layouts): softmax(Q K^T / 8) V per (sequence, head) on token-major [n_seq * F, H * 64] bf16 buffers, against
     torch's scaled_dot_product_attention on the same bf16 inputs."""
     import torch
     import torch.nn.functional as Fn
-    emul.emul_band_attn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_float]
+    emul.emul_band_attn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_float]
     emul.emul_band_attn.restype = None
     g = torch.Generator().manual_seed(F + H)
     q, k, v = (torch.randn(n_seq * F, H * 64, generator=g).to(torch.bfloat16) for _ in range(3))
     qa, ka, va = _bf16(q), _bf16(k), _bf16(v)
     oa = np.full(q.numel(), 0x7FC0, np.uint16)                        # NaN: every output element must be written
-    emul.emul_band_attn(_p(qa), _p(ka), _p(va), _p(oa), n_seq, F, H, 0.125)
+    gates = (2 * torch.randn(n_seq * F, H, generator=g)).to(torch.bfloat16) if gated else None
+    ga = None if gates is None else _bf16(gates)
+    emul.emul_band_attn(_p(qa), _p(ka), _p(va), _p(oa), _p(ga), n_seq, F, H, 0.125)
     got = _from_bf16(oa, q.shape).float()
     shp = (n_seq, F, H, 64)
     ref = Fn.scaled_dot_product_attention(q.float().view(shp).transpose(1, 2), k.float().view(shp).transpose(1, 2),
                                           v.float().view(shp).transpose(1, 2)).transpose(1, 2).reshape(q.shape)
+    if gated:
+        ref = (ref.view(n_seq * F, H, 64) * torch.sigmoid(gates.float())[:, :, None]).reshape(q.shape)
     assert torch.isfinite(got).all()
     assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())      # bf16 probabilities and bf16 output
     assert float((got - ref).abs().mean()) <= 2e-3 * float(ref.abs().mean() + 1e-6) + 2e-3

@@ -76,11 +76,14 @@ def test_fused_axial_host_logic_matches_module_path(kind, monkeypatch):
     assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
 
 
-def ref_band_attention(q, k, v, n_seq, seq_len, heads, dh):
+def ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates=None):
     shp = (n_seq, seq_len, heads, dh)
     o = F.scaled_dot_product_attention(q.view(shp).transpose(1, 2).float(), k.view(shp).transpose(1, 2).float(),
                                        v.view(shp).transpose(1, 2).float())
-    return o.transpose(1, 2).reshape(q.shape).to(q.dtype)
+    o = o.transpose(1, 2).reshape(q.shape)
+    if gates is not None:
+        o = (o.view(-1, heads, dh) * torch.sigmoid(gates.float())[:, :, None]).reshape(q.shape)
+    return o.to(q.dtype)
 
 
 def test_fused_axial_host_logic_with_band_attention_kernel(monkeypatch):
@@ -97,9 +100,10 @@ def test_fused_axial_host_logic_with_band_attention_kernel(monkeypatch):
             p.add_(0.05 * torch.randn_like(p))
     calls = []
 
-    def spy(q, k, v, n_seq, seq_len, heads, dh):
+    def spy(q, k, v, n_seq, seq_len, heads, dh, gates=None):
+        assert gates is not None and tuple(gates.shape) == (q.shape[0], heads)
         calls.append((tuple(q.shape), n_seq, seq_len, heads, dh))
-        return ref_band_attention(q, k, v, n_seq, seq_len, heads, dh)
+        return ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates)
 
     monkeypatch.setattr(netops, "rmsnorm", ref_rmsnorm)
     monkeypatch.setattr(netops, "rotary_", ref_rotary_)
@@ -238,6 +242,7 @@ def test_band_attention_kernel(cuda, F_, H, n_seq):
     import audiolab_b200.netops as netops
     g = torch.Generator().manual_seed(F_ + H)
     q, k, v = (torch.randn(n_seq * F_, H * 64, generator=g).to(torch.bfloat16).to(cuda) for _ in range(3))
-    got = netops.band_attention(q, k, v, n_seq, F_, H, 64).float()
-    ref = ref_band_attention(q, k, v, n_seq, F_, H, 64).float()
+    gates = (2 * torch.randn(n_seq * F_, H, generator=g)).to(torch.bfloat16).to(cuda)
+    got = netops.band_attention(q, k, v, n_seq, F_, H, 64, gates=gates).float()
+    ref = ref_band_attention(q, k, v, n_seq, F_, H, 64, gates).float()
     assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())
