@@ -13,7 +13,9 @@
 // (conflict-free 32-bit fragment loads); S = Q K^T and O = P V stay in mma accumulator registers, the softmax runs on
 // the accumulator fragments (row max / sum over the 4 lanes that share a row), P is re-used as the A operand of the second
 // product without leaving registers.  With `gates` the sigmoid gate of upstream's Attention (out * to_gates(x).sigmoid())
-// is folded into the final normalisation, which removes the separate gate pass for this axis.
+// is folded into the final normalisation, and with `cos_sin` the rotary embedding of q and k (position = band index) is
+// applied while the tiles are staged -- both remove a separate HBM pass for this axis, with the same roundings as the
+// stand-alone rotary / gate kernels (bf16 after the rotation; the gate multiplies before the single output rounding).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,10 +46,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// 8 bf16 = 4 (even, odd) pairs, each turned by its (cos, sin): fp32 inside, rounded back to bf16 like rotary_bf16_kernel
+__device__ __forceinline__ uint4 rotate_bf16x8(uint4 u, const float2* __restrict__ cs) {
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = __uint_as_float(w[j] << 16), b = __uint_as_float(w[j] & 0xFFFF0000u);
+        const float2 t = __ldg(cs + j);
+        w[j] = pack_bf16x2(a * t.x - b * t.y, b * t.x + a * t.y);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(128)
 band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o,
-                      const __nv_bfloat16* __restrict__ gates, int F, int H, float scale) {
+                      const __nv_bfloat16* __restrict__ gates, const float2* __restrict__ cos_sin, int F, int H,
+                      float scale) {
     __shared__ __align__(16) __nv_bfloat16 Qs[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Ks[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Vs[kBaF * kBaLd];
@@ -65,6 +80,11 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
             vq = __ldg(reinterpret_cast<const uint4*>(q + g));
             vk = __ldg(reinterpret_cast<const uint4*>(k + g));
             vv = __ldg(reinterpret_cast<const uint4*>(v + g));
+            if (cos_sin) {   // upstream rotary_embed.rotate_queries_or_keys on q and k, position = band index (= row)
+                const float2* cs = cos_sin + row * (kBaD / 2) + (c8 >> 1);
+                vq = rotate_bf16x8(vq, cs);
+                vk = rotate_bf16x8(vk, cs);
+            }
         }
         *reinterpret_cast<uint4*>(Qs + row * kBaLd + c8) = vq;
         *reinterpret_cast<uint4*>(Ks + row * kBaLd + c8) = vk;
@@ -165,15 +185,15 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 }
 // [emul-end]
 
-cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, long long n_seq,
-                                  int F, int heads, float scale, cudaStream_t stream) {
+cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
+                                  long long n_seq, int F, int heads, float scale, cudaStream_t stream) {
     if (n_seq <= 0) return cudaSuccess;
     const long long ctas = n_seq * heads;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     band_attn_bf16_kernel<<<(unsigned)ctas, 128, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
         reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
-        reinterpret_cast<const __nv_bfloat16*>(gates), F, heads, scale);
+        reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, heads, scale);
     count_launch();
     return cudaGetLastError();
 }

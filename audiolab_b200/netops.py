@@ -71,10 +71,12 @@ def gelu_(x: torch.Tensor) -> torch.Tensor:
 
 
 def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, seq_len: int, heads: int,
-                   dim_head: int, gates: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   dim_head: int, gates: Optional[torch.Tensor] = None,
+                   cos_sin: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T / sqrt(dim_head)) v per (sequence, head) on token-major [n_seq * seq_len, heads * dim_head] buffers
     (al_attn.cu; seq_len <= 64, dim_head == 64).  With `gates` [n_seq * seq_len, heads] the output is also multiplied by
-    sigmoid(gates) per (token, head).  Returns a new [n_seq * seq_len, heads * dim_head] tensor."""
+    sigmoid(gates) per (token, head); with `cos_sin` [seq_len, dim_head/2, 2] fp32, q and k are rotated by their position in
+    the sequence first (rotary_ semantics, without modifying q / k).  Returns a new [n_seq * seq_len, heads * dim_head] tensor."""
     for t, name in ((q, "q"), (k, "k"), (v, "v")):
         _check_bf16_rows(t, name)
     if q.shape != k.shape or q.shape != v.shape or tuple(q.shape) != (n_seq * seq_len, heads * dim_head):
@@ -83,9 +85,13 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
         _check_bf16_rows(gates, "gates")
         if tuple(gates.shape) != (q.shape[0], heads):
             raise ValueError("gates must be [n_seq * seq_len, heads]")
+    if cos_sin is not None and (cos_sin.dtype != torch.float32 or tuple(cos_sin.shape) != (seq_len, dim_head // 2, 2)
+                                or not cos_sin.is_contiguous() or not cos_sin.is_cuda):
+        raise ValueError("cos_sin must be a contiguous CUDA fp32 [seq_len, dim_head/2, 2] tensor")
     o = torch.empty_like(q)
     _lib.check(_lib.lib().al_band_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
-                                                 None if gates is None else gates.data_ptr(), int(n_seq), int(seq_len),
+                                                 None if gates is None else gates.data_ptr(),
+                                                 None if cos_sin is None else cos_sin.data_ptr(), int(n_seq), int(seq_len),
                                                  int(heads), int(dim_head), float(dim_head) ** -0.5, _stream()),
                "al_band_attention_bf16")
     return o

@@ -249,18 +249,20 @@ class RoformerMaskNet(nn.Module):
             pending = None
             w = self._bf16(attn.to_qkv.weight)
             q, k, v = F.linear(xn, w[:inner]), F.linear(xn, w[inner:2 * inner]), F.linear(xn, w[2 * inner:])
-            if attn.rotary_embed is not None:
+            band_kernel = not time_axis and _BAND_ATTN and dh == 64 and f <= 64
+            if attn.rotary_embed is not None and not band_kernel:
                 if time_axis:
                     netops.rotary_(q, k, self._cos_sin(attn.rotary_embed, t, x2.device), h, dh, f, t)
                 else:
                     netops.rotary_(q, k, self._cos_sin(attn.rotary_embed, f, x2.device), h, dh, 1, f)
             # attention over time: batch b, "heads" (band, head); over bands: batch (b, t).  Strided views of the
             # token-major buffers -- no transposition copies around the attention.
-            if not time_axis and _BAND_ATTN and dh == 64 and f <= 64:
+            if band_kernel:
                 # opt-in (AUDIOLAB_B200_BAND_ATTN=1): our mma.sync kernel for the short band axis (csrc/al_attn.cu),
-                # with the sigmoid gate folded into its epilogue
+                # with the rotary embedding folded into its tile staging and the sigmoid gate into its epilogue
                 gates = F.linear(xn, self._bf16(attn.to_gates.weight), self._bf16(attn.to_gates.bias))
-                o2 = netops.band_attention(q, k, v, b * t, f, h, dh, gates=gates)
+                cs = None if attn.rotary_embed is None else self._cos_sin(attn.rotary_embed, f, x2.device)
+                o2 = netops.band_attention(q, k, v, b * t, f, h, dh, gates=gates, cos_sin=cs)
                 x2.addmm_(o2, self._bf16(attn.to_out[0].weight).t())
             else:
                 shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)

@@ -182,7 +182,8 @@ int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream);
  *   x [n] bf16, n a multiple of 8.
  * al_band_attention_bf16 -- upstream Attention.forward of the frequency (band-axis) transformer:
  *   softmax(q k^T * scale) v per (sequence, head); q, k, v, o [n_seq * seq_len, heads * 64] bf16, token (s, f) in row
- *   s * seq_len + f; seq_len <= 64, dim_head = 64.  gates (nullable) [n_seq * seq_len, heads] bf16: o *= sigmoid(gate).  Opt-in on the host side (AUDIOLAB_B200_BAND_ATTN=1); the default
+ *   s * seq_len + f; seq_len <= 64, dim_head = 64.  gates (nullable) [n_seq * seq_len, heads] bf16: o *= sigmoid(gate);
+ *   cos_sin (nullable) [seq_len, 32, 2] fp32: q and k are rotated by their band position first (al_rotary_bf16 semantics).  Opt-in on the host side (AUDIOLAB_B200_BAND_ATTN=1); the default
  *   calls the library attention (cuDNN through PyTorch).
  */
 int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, int64_t n_rows, int dim, float scale,
@@ -191,8 +192,8 @@ int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int h
                    int pos_mod, void* stream);
 int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream);
 int al_gelu_bf16(void* x, int64_t n, void* stream);
-int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t n_seq,
-                           int seq_len, int heads, int dim_head, float scale, void* stream);
+int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
+                           int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -501,7 +501,7 @@ def test_band_attention_emulated_matches_torch_sdpa(emul, F, H, n_seq, gated):
     torch's scaled_dot_product_attention on the same bf16 inputs."""
     import torch
     import torch.nn.functional as Fn
-    emul.emul_band_attn.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_float]
+    emul.emul_band_attn.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 3 + [ctypes.c_float]
     emul.emul_band_attn.restype = None
     g = torch.Generator().manual_seed(F + H)
     q, k, v = (torch.randn(n_seq * F, H * 64, generator=g).to(torch.bfloat16) for _ in range(3))
@@ -509,7 +509,15 @@ def test_band_attention_emulated_matches_torch_sdpa(emul, F, H, n_seq, gated):
     oa = np.full(q.numel(), 0x7FC0, np.uint16)                        # NaN: every output element must be written
     gates = (2 * torch.randn(n_seq * F, H, generator=g)).to(torch.bfloat16) if gated else None
     ga = None if gates is None else _bf16(gates)
-    emul.emul_band_attn(_p(qa), _p(ka), _p(va), _p(oa), _p(ga), n_seq, F, H, 0.125)
+    cs = None
+    if gated:                                                         # the gated cases also fold the rotary embedding in
+        ang = torch.arange(F)[:, None].float() * (1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64)))[None]
+        cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous()
+        spec_ = importlib.util.spec_from_file_location("tnet", os.path.join(ROOT, "tests", "test_netops.py"))
+        tnet = importlib.util.module_from_spec(spec_)
+        spec_.loader.exec_module(tnet)
+        tnet.ref_rotary_(q, k, cs, H, 64, 1, F)                       # reference: rotate (and round to bf16) first
+    emul.emul_band_attn(_p(qa), _p(ka), _p(va), _p(oa), _p(ga), _p(None if cs is None else cs.numpy().copy()), n_seq, F, H, 0.125)
     got = _from_bf16(oa, q.shape).float()
     shp = (n_seq, F, H, 64)
     ref = Fn.scaled_dot_product_attention(q.float().view(shp).transpose(1, 2), k.float().view(shp).transpose(1, 2),

@@ -100,9 +100,12 @@ def test_fused_axial_host_logic_with_band_attention_kernel(monkeypatch):
             p.add_(0.05 * torch.randn_like(p))
     calls = []
 
-    def spy(q, k, v, n_seq, seq_len, heads, dh, gates=None):
+    def spy(q, k, v, n_seq, seq_len, heads, dh, gates=None, cos_sin=None):
         assert gates is not None and tuple(gates.shape) == (q.shape[0], heads)
+        assert cos_sin is not None and tuple(cos_sin.shape) == (seq_len, dh // 2, 2)
         calls.append((tuple(q.shape), n_seq, seq_len, heads, dh))
+        q, k = q.clone(), k.clone()
+        ref_rotary_(q, k, cos_sin, heads, dh, 1, seq_len)
         return ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates)
 
     monkeypatch.setattr(netops, "rmsnorm", ref_rmsnorm)
@@ -243,6 +246,10 @@ def test_band_attention_kernel(cuda, F_, H, n_seq):
     g = torch.Generator().manual_seed(F_ + H)
     q, k, v = (torch.randn(n_seq * F_, H * 64, generator=g).to(torch.bfloat16).to(cuda) for _ in range(3))
     gates = (2 * torch.randn(n_seq * F_, H, generator=g)).to(torch.bfloat16).to(cuda)
-    got = netops.band_attention(q, k, v, n_seq, F_, H, 64, gates=gates).float()
-    ref = ref_band_attention(q, k, v, n_seq, F_, H, 64, gates).float()
+    ang = torch.arange(F_)[:, None].float() * (1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64)))[None]
+    cs = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().to(cuda)
+    got = netops.band_attention(q, k, v, n_seq, F_, H, 64, gates=gates, cos_sin=cs).float()
+    qr, kr = q.clone(), k.clone()
+    ref_rotary_(qr, kr, cs, H, 64, 1, F_)
+    ref = ref_band_attention(qr, kr, v, n_seq, F_, H, 64, gates).float()
     assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())

@@ -100,12 +100,12 @@ extern "C" void emul_gate(void* o, const void* gates, long long n_rows, int head
     });
 }
 
-extern "C" void emul_band_attn(const void* q, const void* k, const void* v, void* o, const void* gates, int n_seq, int F, int H,
-                               float scale) {
+extern "C" void emul_band_attn(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
+                               int n_seq, int F, int H, float scale) {
     emul_launch(dim3(n_seq * H), dim3(128), [&] {
         band_attn_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                               reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
-                              reinterpret_cast<const __nv_bfloat16*>(gates), F, H, scale);
+                              reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, H, scale);
     });
 }
 
