@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/audiolab_b200.h"
+#include "al_gemm.h"
 #include "al_kernels.h"
 
 namespace al {
@@ -402,6 +403,31 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
         return fail(AL_E_ARG, "al_band_attention_bf16: pointers must be 16-byte aligned");
     cudaError_t e = al::launch_band_attn_bf16(q, k, v, o, gates, cos_sin, n_seq, seq_len, heads, scale, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_band_attention_bf16");
+    return AL_OK;
+}
+
+int al_gemm_bf16(const al_gemm_args* a, void* stream) {
+    if (!a || !a->A || !a->W) return fail(AL_E_ARG, "al_gemm_bf16: NULL argument");
+    if (a->M == 0) return AL_OK;
+    if (a->epi != AL_GEMM_EPI_BF16 && a->epi != AL_GEMM_EPI_RESIDUAL) return fail(AL_E_ARG, "al_gemm_bf16: bad epi %d", a->epi);
+    cudaError_t ce = cudaSuccess;
+    const char* msg = al::launch_gemm_bf16(*a, (cudaStream_t)stream, &ce);
+    if (!msg) return AL_OK;
+    if (ce != cudaSuccess) return cuda_fail(ce, "al_gemm_bf16");
+    return fail(AL_E_ARG, "al_gemm_bf16: %s", msg);
+}
+
+int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
+                     int64_t n_rows, int dim, int ss_parts, float eps, void* stream) {
+    if (!x_in || !x32 || !xb || !ss) return fail(AL_E_ARG, "al_resid_prepare: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || dim <= 0 || dim > 2048 || ss_parts <= 0 || ss_parts > 8 || dim % (8 * ss_parts) != 0)
+        return fail(AL_E_ARG, "al_resid_prepare: dim %d must be a multiple of 8 * ss_parts (%d), <= 2048", dim, ss_parts);
+    if (((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x32) | reinterpret_cast<uintptr_t>(xb) |
+          reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(gamma)) & 15) != 0)
+        return fail(AL_E_ARG, "al_resid_prepare: pointers must be 16-byte aligned");
+    cudaError_t e = al::launch_resid_prepare(x_in, bias, gamma, x32, xb, ss, n_rows, dim, ss_parts, eps, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_resid_prepare");
     return AL_OK;
 }
 

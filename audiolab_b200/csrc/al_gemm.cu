@@ -1,0 +1,520 @@
+// K4: the dense contractions of the RoFormer mask network on the 5th-generation tensor cores (sm_100a).
+//
+//   out[g][m, n] = epilogue( sum_k A[g][m, k] * W[g][n, k] )        A, W bf16 K-major (nn.Linear layout), fp32 accumulate
+//
+// One persistent CTA per SM, warp-specialised (the roles never meet on a CTA-wide barrier after start-up):
+//   warp 0     producer : TMA (cp.async.bulk.tensor) loads of 128 x 64 A tiles and BN x 64 W tiles, 128-byte swizzle,
+//                         into a STAGES-deep shared-memory ring (mbarrier full / empty)
+//   warp 1     MMA      : one thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) from shared-memory descriptors
+//                         into one of TWO accumulators in tensor memory; tcgen05.commit releases ring slots and
+//                         publishes the finished accumulator
+//   warps 2..5 epilogue : tcgen05.ld of their 32-lane quadrant, the fused epilogue in registers, swizzled staging in
+//                         shared memory and TMA stores; accumulator t+1 is being computed while t is drained
+//
+// Fused epilogues (what the reference runs as separate PyTorch kernels between two GEMMs):
+//   EPI_BF16 : v = acc * rowscale[m] + bias[n]  -> optional rotary embedding on column pairs -> optional GELU / tanh
+//              -> bf16.  rowscale = sqrt(d) / max(||x_m||, eps) from the partial sums of squares the residual epilogue
+//              left behind: RMSNorm(x) W^T = diag(rowscale) x (gamma (.) W)^T, so the normalisation pass disappears
+//              (gamma is folded into W once on the host).  The output columns may be routed to up to 4 tensors
+//              (q / k / v / gates).
+//   EPI_RES  : x32 += acc + bias (fp32 residual stream, read and written in place through TMA), xb = bf16(x32) (the
+//              next GEMM's A operand), ss[m][n_tile] = partial sum of squares of the new row (the next rowscale).
+//
+// Reference call site accelerated: modules/separator/stem_separator.py:281 (separator.separate -> model forward under
+// autocast, :106); upstream module tree restated in nets/roformer.py.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+
+#include "al_gemm.h"
+#include "al_kernels.h"
+#include "al_tc.cuh"
+
+namespace al {
+namespace tc {
+
+constexpr int BM = 128;          // rows of A per tile = tensor memory lanes
+constexpr int BK = 64;           // bf16 elements per 128-byte swizzled row
+constexpr int UK = 16;           // K of one tcgen05.mma kind::f16
+constexpr int kThreads = 192;    // 6 warps
+constexpr int kEpiWarps = 4;
+constexpr int kResSlots = 4;     // EPI_RES: ring of 32-column fp32 chunks in flight per epilogue warp
+
+struct Tmaps {
+    CUtensorMap a, b;
+    CUtensorMap o[4];   // EPI_BF16: outputs (bf16, box 64 x 32, 128-byte swizzle)
+                        // EPI_RES : o[0] = x32 (fp32, box 32 x 32, 128-byte swizzle), o[1] = xb (bf16, box 32 x 32, 64-byte swizzle)
+};
+
+template <int BN, int STAGES, int EPI>
+struct SmemLayout {
+    static constexpr int kA = BM * BK * 2;                    // 16 KB
+    static constexpr int kB = BN * BK * 2;
+    static constexpr int kStage = kA + kB;
+    static constexpr int kEpiPerWarp = EPI == EPI_RES ? (kResSlots * 4096 + 2 * 2048) : (2 * 4096);
+    static constexpr int kEpiOff = STAGES * kStage;
+    static constexpr int kBarOff = kEpiOff + kEpiWarps * kEpiPerWarp;
+    static constexpr int kNumBars = 2 * STAGES + 4 + kEpiWarps * kResSlots;
+    static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+    static constexpr int kDynamic = kTotal + 1024;            // slack for the manual 1024-byte alignment
+};
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
+    using L = SmemLayout<BN, STAGES, EPI>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = smem_addr(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;            // 128-byte swizzle atoms are 1024-byte aligned
+    unsigned char* base_ptr = smem_dyn + (base - raw);
+    const uint32_t bars = base + L::kBarOff;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    auto res_bar = [&](int w, int s) { return bars + 8u * (2 * STAGES + 4 + w * kResSlots + s); };
+    const uint32_t tmem_slot = bars + 8u * L::kNumBars;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::kBarOff + 8 * L::kNumBars);
+
+    const int warp = (int)(threadIdx.x >> 5);
+    const int lane = lane_id();
+    constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; BN is a power of two >= 16
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.a);
+            tma_prefetch_desc(&tm.b);
+            tma_prefetch_desc(&tm.o[0]);
+            if (EPI == EPI_RES) tma_prefetch_desc(&tm.o[1]);
+        }
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    } else if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), kEpiWarps);
+        }
+        for (int w = 0; w < kEpiWarps; ++w)
+            for (int s = 0; s < kResSlots; ++s) mbar_init(res_bar(w, s), 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int tiles_per_group = g.m_tiles * g.n_tiles;
+    const int total_tiles = tiles_per_group * g.groups;
+    const int k_blocks = (g.K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ================================= TMA producer =================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x) {
+                const int grp = tile / tiles_per_group;
+                const int rem = tile - grp * tiles_per_group;
+                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)L::kStage);
+                    const uint32_t sa = base + (uint32_t)stage * L::kStage;
+                    tma_load_3d(sa, &tm.a, full_bar(stage), kb * BK, m_blk * BM, grp);
+                    tma_load_3d(sa + L::kA, &tm.b, full_bar(stage), kb * BK, n_blk * BN, grp);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================= MMA issuer =================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
+                const int rem = tile % tiles_per_group;
+                const int n_blk = rem % g.n_tiles;
+                int n_cur = g.N - n_blk * BN;
+                n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
+                const uint32_t idesc = umma_idesc_bf16(BM, n_cur);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = base + (uint32_t)stage * L::kStage;
+                    const uint64_t a_desc = umma_desc_sw128(sa);
+                    const uint64_t b_desc = umma_desc_sw128(sa + L::kA);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) {
+                        // advancing K inside the 128-byte swizzle atom = advancing the start address by 32 bytes
+                        umma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * ((UK * 2) >> 4)), b_desc + (uint64_t)(k * ((UK * 2) >> 4)),
+                                     idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));               // ring slot free once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));                     // accumulator complete
+            }
+        }
+    } else {
+        // ================================= epilogue warps =================================
+        const int ew = warp - 2;                 // 0..3: private staging buffers / barriers
+        const int q = warp & 3;                  // tensor memory lane quadrant this warp may access
+        const uint32_t ebuf = base + L::kEpiOff + (uint32_t)ew * L::kEpiPerWarp;
+        unsigned char* ebuf_ptr = base_ptr + L::kEpiOff + ew * L::kEpiPerWarp;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+        if constexpr (EPI == EPI_BF16) {
+            int it = 0;
+            int buf = 0;
+            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
+                const int grp = tile / tiles_per_group;
+                const int rem = tile - grp * tiles_per_group;
+                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                const int row0 = m_blk * BM + q * 32;
+                const long long row = (long long)row0 + lane;
+                const long long grow = (long long)grp * g.M + row;      // row of the per-row side inputs
+                float rs = 1.f;
+                if (g.row_ss != nullptr && row < g.M) {
+                    float ss = 0.f;
+                    for (int p = 0; p < g.ss_parts; ++p) ss += __ldg(g.row_ss + grow * g.ss_parts + p);
+                    rs = g.ss_scale / fmaxf(sqrtf(ss), g.ss_eps);
+                }
+                int pos = 0;
+                if (g.cos_sin != nullptr) pos = (int)((row / g.pos_div) % g.pos_mod);
+                const int n0 = n_blk * BN;
+                const int n_cols = min(BN, g.N - n0);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const int steps = (n_cols + 63) >> 6;
+                for (int st = 0; st < steps; ++st) {
+                    uint32_t r[2][32];
+                    const uint32_t ta = lane_taddr + (uint32_t)(acc * BN + st * 64);
+                    tmem_ld_32x32(ta, r[0]);
+                    if (BN >= 64) tmem_ld_32x32(ta + 32, r[1]);
+                    tmem_wait_ld();
+                    if (st == steps - 1) {                      // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    const int col0 = n0 + st * 64;
+                    const bool rot = g.cos_sin != nullptr && col0 < g.rot_cols;
+                    // the staging buffer about to be written was handed to a TMA store two steps ago
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+                    unsigned char* sb = ebuf_ptr + buf * 4096 + lane * 128;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (BN < 64 && h == 1) break;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[h][j]) * rs;
+                        if (g.bias != nullptr) {
+                            const float4* bp = reinterpret_cast<const float4*>(g.bias + (long long)grp * g.N + col0 + h * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (col0 + h * 32 + j * 4 < g.N) {
+                                    const float4 b = __ldg(bp + j);
+                                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                                }
+                            }
+                        }
+                        if (rot) {
+                            // pair (2i, 2i+1) of a 64-wide head turns by pos * freq_i; a 64-column step is one head
+                            const float4* cp = reinterpret_cast<const float4*>(g.cos_sin) + ((long long)pos * 32 + h * 16) / 2;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 c = __ldg(cp + j);          // (cos, sin) of pairs 2j, 2j+1 of this half
+                                const float a0 = v[4 * j], a1 = v[4 * j + 1], b0 = v[4 * j + 2], b1 = v[4 * j + 3];
+                                v[4 * j] = a0 * c.x - a1 * c.y;
+                                v[4 * j + 1] = a1 * c.x + a0 * c.y;
+                                v[4 * j + 2] = b0 * c.z - b1 * c.w;
+                                v[4 * j + 3] = b1 * c.z + b0 * c.w;
+                            }
+                        }
+                        if (g.act == ACT_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        } else if (g.act == ACT_TANH) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+                            u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                            u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            const int chunk = h * 4 + j;                 // 16-byte chunk of the 128-byte row
+                            *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int oi = col0 / g.out_split;
+                        tma_store_3d(&tm.o[oi], ebuf + (uint32_t)buf * 4096, col0 - oi * g.out_split, row0, grp);
+                        bulk_commit();
+                    }
+                    buf ^= 1;
+                }
+            }
+            if (lane == 0) bulk_wait<0>();
+        } else {
+            // ---------------- EPI_RES: x32 += acc + bias ; xb = bf16(x32) ; ss partials ----------------
+            constexpr int CH = BN / 32;
+            const int n_my = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const long long n_chunks = (long long)n_my * CH;
+            auto coords = [&](long long gc, int& grp, int& row0, int& col0) {
+                const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                grp = tile / tiles_per_group;
+                const int rem = tile - grp * tiles_per_group;
+                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+                row0 = m_blk * BM + q * 32;
+                col0 = n_blk * BN + c * 32;
+            };
+            auto issue_load = [&](long long gc) {
+                int grp, row0, col0;
+                coords(gc, grp, row0, col0);
+                const int slot = (int)(gc & (kResSlots - 1));
+                mbar_arrive_expect_tx(res_bar(ew, slot), 4096u);
+                tma_load_3d(ebuf + (uint32_t)slot * 4096, &tm.o[0], res_bar(ew, slot), col0, row0, grp);
+            };
+            if (lane == 0)
+                for (long long gc = 0; gc < kResSlots - 1 && gc < n_chunks; ++gc) issue_load(gc);
+            float ss = 0.f;
+            for (long long gc = 0; gc < n_chunks; ++gc) {
+                const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                int grp, row0, col0;
+                coords(gc, grp, row0, col0);
+                if (c == 0) {
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    ss = 0.f;
+                }
+                uint32_t r[32];
+                tmem_ld_32x32(lane_taddr + (uint32_t)(acc * BN + c * 32), r);
+                const int slot = (int)(gc & (kResSlots - 1));
+                mbar_wait(res_bar(ew, slot), (uint32_t)(gc / kResSlots) & 1u);
+                tmem_wait_ld();
+                if (c == CH - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                unsigned char* rb = ebuf_ptr + slot * 4096 + lane * 128;
+                unsigned char* xb = ebuf_ptr + kResSlots * 4096 + (int)(gc & 1) * 2048 + lane * 64;
+                const float* bias = g.bias != nullptr ? g.bias + (long long)grp * g.N + col0 : nullptr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4* p = reinterpret_cast<float4*>(rb + ((j ^ (lane & 7)) << 4));
+                    float4 x = *p;
+                    x.x += __uint_as_float(r[4 * j]);
+                    x.y += __uint_as_float(r[4 * j + 1]);
+                    x.z += __uint_as_float(r[4 * j + 2]);
+                    x.w += __uint_as_float(r[4 * j + 3]);
+                    if (bias != nullptr) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + j);
+                        x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                    }
+                    ss = fmaf(x.x, x.x, ss);
+                    ss = fmaf(x.y, x.y, ss);
+                    ss = fmaf(x.z, x.z, ss);
+                    ss = fmaf(x.w, x.w, ss);
+                    *p = x;
+                    r[4 * j] = __float_as_uint(x.x);
+                    r[4 * j + 1] = __float_as_uint(x.y);
+                    r[4 * j + 2] = __float_as_uint(x.z);
+                    r[4 * j + 3] = __float_as_uint(x.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    u.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+                    u.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                    u.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                    u.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                    *reinterpret_cast<uint4*>(xb + ((j ^ ((lane >> 1) & 3)) << 4)) = u;   // 64-byte swizzle
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tm.o[0], ebuf + (uint32_t)slot * 4096, col0, row0, grp);
+                    tma_store_3d(&tm.o[1], ebuf + (uint32_t)(kResSlots * 4096 + (int)(gc & 1) * 2048), col0, row0, grp);
+                    bulk_commit();
+                    bulk_wait_read<1>();                      // chunk gc-1's stores have read their buffers
+                    if (gc + kResSlots - 1 < n_chunks) issue_load(gc + kResSlots - 1);
+                }
+                __syncwarp();
+                if (c == CH - 1 && g.ss_out != nullptr) {
+                    const long long row = (long long)row0 + lane;
+                    if (row < g.M) g.ss_out[((long long)grp * g.M + row) * g.n_tiles + (col0 / BN)] = ss;
+                }
+            }
+            if (lane == 0) bulk_wait<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// rank-3 map of a [groups][rows][cols] tensor (cols innermost), box = box_cols x box_rows x 1
+static bool make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem, long long cols, long long rows,
+                     long long groups, long long ld, long long group_stride, int box_cols, int box_rows,
+                     CUtensorMapSwizzle sw) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)groups};
+    cuuint64_t strides[2] = {(cuuint64_t)(ld * elem), (cuuint64_t)((groups > 1 ? group_stride : ld * rows) * elem)};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    return fn(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct DevInfo {
+    int n_sm = 0;
+    bool attr[8] = {};
+};
+static DevInfo& dev_info(int dev) {
+    static DevInfo info[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    DevInfo& d = info[dev & 63];
+    if (d.n_sm == 0) {
+        cudaDeviceGetAttribute(&d.n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (d.n_sm <= 0) d.n_sm = 148;
+    }
+    return d;
+}
+
+template <int BN, int STAGES, int EPI>
+static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
+    using L = SmemLayout<BN, STAGES, EPI>;
+    static_assert(L::kDynamic <= 232448, "shared memory budget");
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    DevInfo& d = dev_info(dev);
+    if (!d.attr[slot]) {
+        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        if (e != cudaSuccess) return e;
+        d.attr[slot] = true;
+    }
+    const int total = g.m_tiles * g.n_tiles * g.groups;
+    int grid = total < d.n_sm ? total : d.n_sm;
+    if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
+    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kThreads, L::kDynamic, stream>>>(tm, g);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace tc
+
+const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t* cuda_err) {
+    using namespace tc;
+    *cuda_err = cudaSuccess;
+    if (c.M <= 0 || c.N <= 0 || c.K <= 0 || c.groups <= 0) return "bad sizes";
+    if ((c.K & 7) != 0 || (c.lda & 7) != 0 || (c.ldw & 7) != 0) return "K, lda, ldw must be multiples of 8 (16-byte rows)";
+    if ((reinterpret_cast<uintptr_t>(c.A) | reinterpret_cast<uintptr_t>(c.W)) & 15) return "A, W must be 16-byte aligned";
+    const int BN = c.epi == EPI_RES ? 256 : (c.N > 128 ? 256 : (c.N > 64 ? 128 : 64));
+    GemmArgs g{};
+    g.M = (int)c.M; g.N = c.N; g.K = c.K; g.groups = c.groups;
+    g.m_tiles = (int)((c.M + BM - 1) / BM);
+    g.n_tiles = (c.N + BN - 1) / BN;
+    g.bias = c.bias;
+    g.row_ss = c.row_ss; g.ss_parts = c.ss_parts; g.ss_scale = c.ss_scale; g.ss_eps = c.ss_eps;
+    g.cos_sin = c.cos_sin; g.pos_div = c.pos_div > 0 ? c.pos_div : 1; g.pos_mod = c.pos_mod > 0 ? c.pos_mod : 1;
+    g.rot_cols = c.rot_cols; g.act = c.act;
+    g.ss_out = c.ss_out;
+    g.max_ctas = c.max_ctas;
+    if ((long long)g.m_tiles * g.n_tiles * g.groups > 0x7fffffffll) return "too many tiles";
+    Tmaps tm;
+    if (!make_map(&tm.a, c.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
+                  CU_TENSOR_MAP_SWIZZLE_128B))
+        return "cuTensorMapEncodeTiled(A) failed";
+    if (!make_map(&tm.b, c.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, BN,
+                  CU_TENSOR_MAP_SWIZZLE_128B))
+        return "cuTensorMapEncodeTiled(W) failed";
+    if (c.epi == EPI_RES) {
+        if (c.N % 256 != 0) return "residual epilogue needs N to be a multiple of 256";
+        if (!c.x32 || !c.xb) return "residual epilogue needs x32 and xb";
+        if ((c.ldx & 3) != 0 || (c.ldxb & 7) != 0) return "ldx / ldxb must give 16-byte rows";
+        if (!make_map(&tm.o[0], c.x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.N, c.M, c.groups, c.ldx, c.x_group_stride, 32, 32,
+                      CU_TENSOR_MAP_SWIZZLE_128B))
+            return "cuTensorMapEncodeTiled(x32) failed";
+        if (!make_map(&tm.o[1], c.xb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.N, c.M, c.groups, c.ldxb, c.xb_group_stride, 32, 32,
+                      CU_TENSOR_MAP_SWIZZLE_64B))
+            return "cuTensorMapEncodeTiled(xb) failed";
+        tm.o[2] = tm.o[1];
+        tm.o[3] = tm.o[1];
+        g.out_split = c.N;
+        *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
+        return *cuda_err == cudaSuccess ? nullptr : "launch failed";
+    }
+    // EPI_BF16
+    const int split = c.out_split > 0 ? c.out_split : c.N;
+    if (split % 64 != 0 && split != c.N) return "out_split must be a multiple of 64";
+    if (split != c.N && split % BN != 0) return "out_split must be a multiple of the N tile";
+    const int n_out = (c.N + split - 1) / split;
+    if (n_out > 4) return "at most 4 output tensors";
+    if ((c.N & 7) != 0) return "N must be a multiple of 8";
+    if (c.cos_sin != nullptr && (c.rot_cols % 64 != 0)) return "rot_cols must be a multiple of 64";
+    g.out_split = split;
+    for (int i = 0; i < 4; ++i) {
+        const void* o = c.out[i < n_out ? i : 0];
+        const int src = i < n_out ? i : 0;
+        if (!o) return "missing output tensor";
+        if ((reinterpret_cast<uintptr_t>(o) & 15) != 0 || (c.ldo[src] & 7) != 0) return "outputs need 16-byte aligned rows";
+        const int cols = (src == n_out - 1) ? c.N - split * (n_out - 1) : split;
+        if (!make_map(&tm.o[i], o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cols, c.M, c.groups, c.ldo[src],
+                      c.o_group_stride[src], 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+            return "cuTensorMapEncodeTiled(out) failed";
+    }
+    if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_BF16>(tm, g, 1, stream);
+    else if (BN == 128) *cuda_err = launch_cfg<128, 6, EPI_BF16>(tm, g, 2, stream);
+    else *cuda_err = launch_cfg<64, 8, EPI_BF16>(tm, g, 3, stream);
+    return *cuda_err == cudaSuccess ? nullptr : "launch failed";
+}
+
+}  // namespace al

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "al_gemm.h"
 #include "al_kernels.h"
 
 namespace al {
@@ -166,6 +167,97 @@ cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int h
     const long long n_vec = n_rows * vec_per_row;
     gate_bf16_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// [emul-begin]
+// Start / re-normalise the fp32 residual stream of the tcgen05 path (al_gemm.cu EPI_RES keeps it afterwards):
+// y = x_in (+ bias) (then RMSNorm if gamma);  x32 = y, xb = bf16(y), ss[row][p] = partial sums of y^2.
+// One warp per row; lane l owns elements [c * 256 + 8 l, + 8) of chunk c.
+template <int MAXC>
+__global__ void __launch_bounds__(256)
+resid_prepare_kernel(const float* __restrict__ x_in, const float* __restrict__ bias, const float* __restrict__ gamma,
+                     float* __restrict__ x32, __nv_bfloat16* __restrict__ xb, float* __restrict__ ss_out,
+                     long long n_rows, int dim, int ss_parts, float scale, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x_in + row * dim);
+    float v[MAXC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int e = c * 256 + lane * 8;
+        if (e < dim) {
+            const float4 a = xr[e >> 2], b = xr[(e >> 2) + 1];
+            v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+            v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+            if (bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + e));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + e) + 1);
+                v[c][0] += b0.x; v[c][1] += b0.y; v[c][2] += b0.z; v[c][3] += b0.w;
+                v[c][4] += b1.x; v[c][5] += b1.y; v[c][6] += b1.z; v[c][7] += b1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(v[c][i], v[c][i], ss);
+        }
+    }
+    if (gamma) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float inv = scale / fmaxf(sqrtf(ss), eps);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int e = c * 256 + lane * 8;
+            if (e < dim) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e) + 1);
+                v[c][0] *= inv * g0.x; v[c][1] *= inv * g0.y; v[c][2] *= inv * g0.z; v[c][3] *= inv * g0.w;
+                v[c][4] *= inv * g1.x; v[c][5] *= inv * g1.y; v[c][6] *= inv * g1.z; v[c][7] *= inv * g1.w;
+            }
+        }
+    }
+    // partial sums of squares of the stored row: part p covers elements [p * dim / ss_parts, (p + 1) * dim / ss_parts)
+    const int part_len = dim / ss_parts;
+    float4* o32 = reinterpret_cast<float4*>(x32 + row * dim);
+    uint4* ob = reinterpret_cast<uint4*>(xb + row * dim);
+    for (int p = 0; p < ss_parts; ++p) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int e = c * 256 + lane * 8;
+            if (e < dim && e / part_len == p) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s = fmaf(v[c][i], v[c][i], s);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) ss_out[row * ss_parts + p] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int e = c * 256 + lane * 8;
+        if (e < dim) {
+            o32[e >> 2] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+            o32[(e >> 2) + 1] = make_float4(v[c][4], v[c][5], v[c][6], v[c][7]);
+            ob[e >> 3] = f32_to_bf16x8(v[c]);
+        }
+    }
+}
+
+// [emul-end]
+
+cudaError_t launch_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
+                                 long long n_rows, int dim, int ss_parts, float eps, cudaStream_t stream) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
+    auto* ob = reinterpret_cast<__nv_bfloat16*>(xb);
+    const float scale = sqrtf((float)dim);
+    if (dim <= 512) resid_prepare_kernel<2><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
+    else if (dim <= 1024) resid_prepare_kernel<4><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
+    else resid_prepare_kernel<8><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
     count_launch();
     return cudaGetLastError();
 }

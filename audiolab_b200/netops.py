@@ -95,3 +95,138 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
                                                  int(heads), int(dim_head), float(dim_head) ** -0.5, _stream()),
                "al_band_attention_bf16")
     return o
+
+
+# ---- K4: tcgen05 GEMM with fused epilogues (csrc/al_gemm.cu) ---------------------------------------------------
+import ctypes as _C
+
+
+class GemmArgs(_C.Structure):
+    """ctypes mirror of `al_gemm_args` (include/audiolab_b200.h)."""
+    _fields_ = [
+        ("A", _C.c_void_p), ("W", _C.c_void_p), ("M", _C.c_int64),
+        ("N", _C.c_int32), ("K", _C.c_int32), ("groups", _C.c_int32),
+        ("lda", _C.c_int64), ("a_group_stride", _C.c_int64), ("ldw", _C.c_int64), ("w_group_stride", _C.c_int64),
+        ("epi", _C.c_int32), ("act", _C.c_int32),
+        ("bias", _C.c_void_p), ("row_ss", _C.c_void_p), ("ss_parts", _C.c_int32),
+        ("ss_scale", _C.c_float), ("ss_eps", _C.c_float),
+        ("cos_sin", _C.c_void_p), ("pos_div", _C.c_int64), ("pos_mod", _C.c_int32), ("rot_cols", _C.c_int32),
+        ("out", _C.c_void_p * 4), ("ldo", _C.c_int64 * 4), ("o_group_stride", _C.c_int64 * 4),
+        ("out_split", _C.c_int32),
+        ("x32", _C.c_void_p), ("xb", _C.c_void_p),
+        ("ldx", _C.c_int64), ("x_group_stride", _C.c_int64), ("ldxb", _C.c_int64), ("xb_group_stride", _C.c_int64),
+        ("ss_out", _C.c_void_p), ("max_ctas", _C.c_int32),
+    ]
+
+
+ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
+
+
+def _rows2d(t: torch.Tensor, name: str, dtype) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype or t.dim() not in (2, 3) or t.stride(-1) != 1:
+        raise ValueError(f"{name} must be a {dtype} [rows, cols] or [groups, rows, cols] tensor with unit column stride")
+
+
+def _geom(t: torch.Tensor):
+    """(groups, rows, cols, row stride, group stride) of a 2-D / 3-D operand."""
+    if t.dim() == 2:
+        return 1, t.shape[0], t.shape[1], t.stride(0), t.stride(0) * t.shape[0]
+    return t.shape[0], t.shape[1], t.shape[2], t.stride(1), t.stride(0)
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Tensor] = None,
+              row_ss: Optional[torch.Tensor] = None, ss_scale: float = 1.0, ss_eps: float = 1e-12,
+              cos_sin: Optional[torch.Tensor] = None, pos_div: int = 1, pos_mod: int = 1, rot_cols: int = 0,
+              act: Optional[str] = None, out_split: int = 0, max_ctas: int = 0) -> None:
+    """outs[i][..., m, :] = epilogue(a @ w^T) columns [i * out_split, (i+1) * out_split)  (al_gemm_bf16, EPI_BF16).
+
+    a [M, K] / [G, M, K] bf16, w [N, K] / [G, N, K] bf16 (nn.Linear layout), outs: one bf16 tensor or a list of up to 4.
+    row_ss [M(, G), parts] fp32 turns on the folded RMSNorm row scale ss_scale / max(sqrt(sum row_ss), ss_eps)."""
+    if isinstance(outs, torch.Tensor):
+        outs = [outs]
+    _rows2d(a, "a", torch.bfloat16)
+    _rows2d(w, "w", torch.bfloat16)
+    g, m, k, lda, ags = _geom(a)
+    gw, n, kw, ldw, wgs = _geom(w)
+    if gw != g or kw != k:
+        raise ValueError("a and w disagree on groups / K")
+    args = GemmArgs()
+    args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
+    args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
+    args.epi, args.act = 0, ACT[act]
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != g * n or not bias.is_contiguous():
+            raise ValueError("bias must be contiguous fp32 [groups, N]")
+        args.bias = bias.data_ptr()
+    if row_ss is not None:
+        if row_ss.dtype != torch.float32 or not row_ss.is_contiguous() or row_ss.numel() % (g * m) != 0:
+            raise ValueError("row_ss must be contiguous fp32 [groups * M, parts]")
+        args.row_ss, args.ss_parts = row_ss.data_ptr(), row_ss.numel() // (g * m)
+        args.ss_scale, args.ss_eps = float(ss_scale), float(ss_eps)
+    if cos_sin is not None:
+        if cos_sin.dtype != torch.float32 or tuple(cos_sin.shape) != (pos_mod, 32, 2) or not cos_sin.is_contiguous():
+            raise ValueError("cos_sin must be contiguous fp32 [pos_mod, 32, 2] (dim_head 64)")
+        args.cos_sin, args.pos_div, args.pos_mod, args.rot_cols = cos_sin.data_ptr(), int(pos_div), int(pos_mod), int(rot_cols)
+    if len(outs) > 4:
+        raise ValueError("at most 4 outputs")
+    for i, o in enumerate(outs):
+        _rows2d(o, f"outs[{i}]", torch.bfloat16)
+        go, mo, _, ldo, ogs = _geom(o)
+        if go != g or mo != m:
+            raise ValueError("outputs disagree with a on groups / M")
+        args.out[i], args.ldo[i], args.o_group_stride[i] = o.data_ptr(), ldo, ogs
+    args.out_split = int(out_split)
+    args.max_ctas = int(max_ctas)
+    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16")
+
+
+def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss_out: torch.Tensor, *,
+                       bias: Optional[torch.Tensor] = None, max_ctas: int = 0) -> None:
+    """x32 += a @ w^T + bias (fp32, in place); xb = bf16(x32); ss_out[m, j] = sum of x32[m, 256 j : 256 (j+1)]^2."""
+    _rows2d(a, "a", torch.bfloat16)
+    _rows2d(w, "w", torch.bfloat16)
+    _rows2d(x32, "x32", torch.float32)
+    _rows2d(xb, "xb", torch.bfloat16)
+    g, m, k, lda, ags = _geom(a)
+    gw, n, kw, ldw, wgs = _geom(w)
+    if gw != g or kw != k or n % 256 != 0:
+        raise ValueError("a and w disagree on groups / K, or N is not a multiple of 256")
+    gx, mx, nx, ldx, xgs = _geom(x32)
+    gb, mb, nb, ldxb, xbgs = _geom(xb)
+    if (gx, mx, nx) != (g, m, n) or (gb, mb, nb) != (g, m, n):
+        raise ValueError("x32 / xb must be [groups, M, N]")
+    if ss_out.dtype != torch.float32 or not ss_out.is_contiguous() or ss_out.numel() != g * m * (n // 256):
+        raise ValueError("ss_out must be contiguous fp32 [groups * M, N / 256]")
+    args = GemmArgs()
+    args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
+    args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
+    args.epi = 1
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != g * n or not bias.is_contiguous():
+            raise ValueError("bias must be contiguous fp32 [groups, N]")
+        args.bias = bias.data_ptr()
+    args.x32, args.xb, args.ldx, args.x_group_stride, args.ldxb, args.xb_group_stride = (
+        x32.data_ptr(), xb.data_ptr(), ldx, xgs, ldxb, xbgs)
+    args.ss_out = ss_out.data_ptr()
+    args.max_ctas = int(max_ctas)
+    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16(residual)")
+
+
+def resid_prepare(x_in: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss: torch.Tensor, *,
+                  bias: Optional[torch.Tensor] = None, gamma: Optional[torch.Tensor] = None, eps: float = 1e-12) -> None:
+    """x32 = y, xb = bf16(y), ss = partial sums of y^2 with y = [RMSNorm_gamma](x_in + bias)  (al_resid_prepare)."""
+    n, d = x_in.shape
+    for t, name in ((x_in, "x_in"), (x32, "x32")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (n, d):
+            raise ValueError(f"{name} must be a contiguous CUDA fp32 [rows, dim] tensor")
+    _check_bf16_rows(xb, "xb")
+    if ss.dtype != torch.float32 or not ss.is_contiguous() or ss.numel() % n != 0:
+        raise ValueError("ss must be contiguous fp32 [rows, parts]")
+    for v, name in ((bias, "bias"), (gamma, "gamma")):
+        if v is not None and (v.dtype != torch.float32 or v.numel() != d or not v.is_contiguous()):
+            raise ValueError(f"{name} must be contiguous fp32 [dim]")
+    _lib.check(_lib.lib().al_resid_prepare(x_in.data_ptr(), None if bias is None else bias.data_ptr(),
+                                           None if gamma is None else gamma.data_ptr(), x32.data_ptr(), xb.data_ptr(),
+                                           ss.data_ptr(), n, d, ss.numel() // n, float(eps), _stream()), "al_resid_prepare")

@@ -195,6 +195,71 @@ int al_gelu_bf16(void* x, int64_t n, void* stream);
 int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
                            int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
 
+/*
+ * al_gemm_bf16 -- K4: one nn.Linear (or a batch of `groups` of them) of the RoFormer mask network on the tcgen05
+ * tensor cores, with the row-wise work upstream runs around it folded into the epilogue (csrc/al_gemm.cu).
+ * Replaces, inside upstream BSRoformer / MelBandRoformer.forward (driven from the reference at
+ * modules/separator/stem_separator.py:281 under autocast, :106): Attention.to_qkv / to_gates / to_out,
+ * FeedForward's two Linear layers, the RMSNorm in front of them, rotary_embed.rotate_queries_or_keys, nn.GELU, the
+ * residual adds, and the per-band Linear layers of BandSplit / MaskEstimator (groups > 1).
+ *
+ *   acc[g][m, n] = sum_k A[g][m, k] * W[g][n, k]      A [groups][M, K] bf16 (row stride lda, group stride
+ *   a_group_stride, in elements), W [groups][N, K] bf16 (ldw, w_group_stride); fp32 accumulation.
+ *
+ * epi = AL_GEMM_EPI_BF16:  v = acc * rowscale[m] + bias[n];  rotary on columns < rot_cols;  act;  bf16 store.
+ *   rowscale[m] = ss_scale / max(sqrt(sum_p row_ss[m * ss_parts + p]), ss_eps) if row_ss != NULL, else 1
+ *     (RMSNorm(x) W^T = diag(rowscale) x (gamma (.) W)^T: the caller folds gamma into W once).
+ *   bias fp32 [groups][N] or NULL.  cos_sin fp32 [pos_mod][32][2] or NULL: column pair (2i, 2i+1) of each 64-wide
+ *     head turns by the angle of position (m / pos_div) % pos_mod (al_rotary_bf16 semantics); rot_cols % 64 == 0.
+ *   act: AL_GEMM_ACT_NONE / _GELU (exact erf form) / _TANH.
+ *   Output columns [i * out_split, (i + 1) * out_split) go to out[i] (row stride ldo[i], group stride
+ *     o_group_stride[i]); out_split = 0 means one output.  At most 4 outputs.
+ * epi = AL_GEMM_EPI_RESIDUAL (N % 256 == 0):  x32[m, n] += acc + bias[n] in place (fp32 residual stream),
+ *   xb[m, n] = bf16(x32[m, n]),  ss_out[m * (N / 256) + n / 256] = sum over that 256-column slab of x32[m, n]^2.
+ *
+ * K, lda, ldw, ldo, ldxb multiples of 8, ldx of 4, N of 8; all pointers 16-byte aligned.  max_ctas = 0 uses every SM.
+ */
+#define AL_GEMM_EPI_BF16 0
+#define AL_GEMM_EPI_RESIDUAL 1
+#define AL_GEMM_ACT_NONE 0
+#define AL_GEMM_ACT_GELU 1
+#define AL_GEMM_ACT_TANH 2
+
+typedef struct al_gemm_args {
+    const void* A;
+    const void* W;
+    int64_t M;
+    int32_t N, K, groups;
+    int64_t lda, a_group_stride, ldw, w_group_stride;
+    int32_t epi, act;
+    const float* bias;
+    const float* row_ss;
+    int32_t ss_parts;
+    float ss_scale, ss_eps;
+    const float* cos_sin;
+    int64_t pos_div;
+    int32_t pos_mod, rot_cols;
+    void* out[4];
+    int64_t ldo[4], o_group_stride[4];
+    int32_t out_split;
+    float* x32;
+    void* xb;
+    int64_t ldx, x_group_stride, ldxb, xb_group_stride;
+    float* ss_out;
+    int32_t max_ctas;
+} al_gemm_args;
+
+int al_gemm_bf16(const al_gemm_args* args, void* stream);
+
+/*
+ * al_resid_prepare -- start (or re-normalise) the fp32 residual stream the residual epilogue of al_gemm_bf16 keeps:
+ *   y = x_in (+ bias);  if gamma != NULL: y = F.normalize(y, dim=-1) * sqrt(dim) * gamma (upstream RMSNorm);
+ *   x32 = y,  xb = bf16(y),  ss[m * ss_parts + p] = sum of y[m, p * dim / ss_parts ...)^2.
+ * x_in fp32 [n_rows, dim] (may alias x32); dim a multiple of 8 * ss_parts, <= 2048.
+ */
+int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
+                     int64_t n_rows, int dim, int ss_parts, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,168 @@
+"""K4 parity: the tcgen05 GEMM (csrc/al_gemm.cu) through the C ABI against an fp32 torch reference of the same
+operator, computed from the same bf16-rounded operands.  Tolerances: the accumulation is fp32 on both sides, so
+the only differences are summation order (~1e-6 relative) and the final bf16 rounding of the stored result
+(half an ulp = 2^-9 relative), hence rtol 2^-8 on bf16 outputs and 2e-5 on the fp32 residual stream."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from audiolab_b200 import netops
+    return netops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def _close_bf16(got, ref, what):
+    got = got.float()
+    err = (got - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2e-5 * ref.abs().max().clamp(min=1e-6)
+    bad = (err > tol)
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} outside bf16 rounding, max err {float(err.max()):.3e}"
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 512), (1000, 1536, 512), (4097, 2048, 512),
+                                   (777, 512, 2048), (300, 128, 512), (300, 64, 192), (129, 1552, 512)])
+def test_gemm_plain(m, n, k):
+    netops = _cuda()
+    a = _rand((m, k), 1).bfloat16()
+    w = _rand((n, k), 2, k ** -0.5).bfloat16()
+    out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
+    netops.gemm_bf16(a, w, out)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    _close_bf16(out, ref, f"plain {m}x{n}x{k}")
+
+
+def test_gemm_many_tiles_persistent():
+    """More tiles than CTAs, restricted grid: every CTA walks several tiles through both accumulators."""
+    netops = _cuda()
+    m, n, k = 128 * 37 + 5, 1024, 512
+    a = _rand((m, k), 3).bfloat16()
+    w = _rand((n, k), 4, k ** -0.5).bfloat16()
+    out = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+    netops.gemm_bf16(a, w, out, max_ctas=7)
+    torch.cuda.synchronize()
+    _close_bf16(out, a.float() @ w.float().t(), "persistent")
+
+
+@pytest.mark.parametrize("act", [None, "gelu", "tanh"])
+def test_gemm_rowscale_bias_act(act):
+    netops = _cuda()
+    m, n, k = 1111, 2048, 512
+    x = _rand((m, k), 5, 3.0)
+    a = x.bfloat16()
+    w = _rand((n, k), 6, k ** -0.5).bfloat16()
+    bias = _rand((n,), 7, 0.5)
+    ss = torch.stack((x[:, :256].square().sum(-1), x[:, 256:].square().sum(-1)), dim=-1).contiguous()
+    out = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+    netops.gemm_bf16(a, w, out, bias=bias, row_ss=ss, ss_scale=math.sqrt(k), act=act)
+    torch.cuda.synchronize()
+    rs = math.sqrt(k) / x.square().sum(-1).sqrt().clamp(min=1e-12)
+    ref = (a.float() @ w.float().t()) * rs[:, None] + bias
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    elif act == "tanh":
+        ref = torch.tanh(ref)
+    _close_bf16(out, ref, f"rowscale+bias+{act}")
+
+
+@pytest.mark.parametrize("time_axis", [True, False])
+def test_gemm_qkv_rotary_split(time_axis):
+    """to_qkv + to_gates in one call: q, k rotated by the token position, v plain, gates with bias; 4 outputs."""
+    netops = _cuda()
+    b, t, f, heads, dh, d = 2, 37, 11, 8, 64, 512
+    m, inner = b * t * f, heads * dh
+    x = _rand((m, d), 8)
+    a = x.bfloat16()
+    w = _rand((3 * inner + 16, d), 9, d ** -0.5).bfloat16()
+    w[3 * inner + heads:] = 0
+    bias = torch.zeros(3 * inner + 16, device="cuda")
+    bias[3 * inner: 3 * inner + heads] = _rand((heads,), 10)
+    n_pos = t if time_axis else f
+    pos_div = f if time_axis else 1
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, dh, 2).float() / dh))
+    ang = torch.arange(n_pos).float()[:, None] * freqs[None, :]
+    cos_sin = torch.stack((ang.cos(), ang.sin()), dim=-1).contiguous().cuda()
+    q, k_, v = (torch.empty((m, inner), device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    gates = torch.empty((m, 16), device="cuda", dtype=torch.bfloat16)
+    netops.gemm_bf16(a, w, [q, k_, v, gates], bias=bias, cos_sin=cos_sin, pos_div=pos_div, pos_mod=n_pos,
+                     rot_cols=2 * inner, out_split=inner)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    pos = (torch.arange(m, device="cuda") // pos_div) % n_pos
+    c = cos_sin[pos, :, 0][:, None, :]
+    s = cos_sin[pos, :, 1][:, None, :]
+
+    def rot(z):
+        z = z.view(m, heads, dh // 2, 2)
+        return torch.stack((z[..., 0] * c - z[..., 1] * s, z[..., 1] * c + z[..., 0] * s), dim=-1).reshape(m, inner)
+
+    _close_bf16(q, rot(ref[:, :inner]), "q")
+    _close_bf16(k_, rot(ref[:, inner:2 * inner]), "k")
+    _close_bf16(v, ref[:, 2 * inner:3 * inner], "v")
+    _close_bf16(gates[:, :heads], ref[:, 3 * inner:3 * inner + heads], "gates")
+
+
+def test_gemm_strided_views_and_groups():
+    """Grouped call on strided operands: the per-band Linear layers (rows f::F of the token grid)."""
+    netops = _cuda()
+    bt, f, d, n = 333, 5, 512, 256
+    x = _rand((bt, f, d), 11).bfloat16()
+    w = _rand((f, n, d), 12, d ** -0.5).bfloat16()
+    bias = _rand((f, n), 13)
+    out = torch.empty((bt, f, n), device="cuda", dtype=torch.bfloat16)
+    netops.gemm_bf16(x.transpose(0, 1), w, out.transpose(0, 1), bias=bias, act="tanh")
+    torch.cuda.synchronize()
+    ref = torch.tanh(torch.einsum("mfk,fnk->mfn", x.float(), w.float()) + bias[None])
+    _close_bf16(out, ref, "grouped")
+
+
+@pytest.mark.parametrize("m,k,with_bias", [(128, 512, False), (1000, 512, True), (5000, 2048, True)])
+def test_gemm_residual_epilogue(m, k, with_bias):
+    netops = _cuda()
+    n = 512
+    a = _rand((m, k), 14).bfloat16()
+    w = _rand((n, k), 15, k ** -0.5).bfloat16()
+    bias = _rand((n,), 16) if with_bias else None
+    x0 = _rand((m, n), 17, 2.0)
+    x32 = x0.clone()
+    xb = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ss = torch.full((m, 2), float("nan"), device="cuda")
+    netops.gemm_bf16_residual(a, w, x32, xb, ss, bias=bias, max_ctas=5 if m > 1000 else 0)
+    torch.cuda.synchronize()
+    ref = x0 + a.float() @ w.float().t() + (bias if with_bias else 0.0)
+    assert torch.allclose(x32, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max())), float((x32 - ref).abs().max())
+    assert torch.equal(xb, x32.bfloat16()), "xb must be the bf16 rounding of the stored fp32 row"
+    ss_ref = torch.stack((x32[:, :256].square().sum(-1), x32[:, 256:].square().sum(-1)), dim=-1)
+    assert torch.allclose(ss, ss_ref, rtol=1e-5), float((ss - ss_ref).abs().max())
+
+
+def test_resid_prepare():
+    netops = _cuda()
+    m, d = 999, 512
+    x = _rand((m, d), 18, 2.0)
+    bias = _rand((d,), 19)
+    gamma = _rand((d,), 20).abs() + 0.5
+    for use_gamma in (False, True):
+        x32 = torch.empty_like(x)
+        xb = torch.empty((m, d), device="cuda", dtype=torch.bfloat16)
+        ss = torch.empty((m, 2), device="cuda")
+        netops.resid_prepare(x, x32, xb, ss, bias=bias, gamma=gamma if use_gamma else None)
+        torch.cuda.synchronize()
+        y = x + bias
+        if use_gamma:
+            y = torch.nn.functional.normalize(y, dim=-1) * math.sqrt(d) * gamma
+        assert torch.allclose(x32, y, rtol=1e-5, atol=1e-5)
+        assert torch.equal(xb, x32.bfloat16())
+        ss_ref = torch.stack((x32[:, :256].square().sum(-1), x32[:, 256:].square().sum(-1)), dim=-1)
+        assert torch.allclose(ss, ss_ref, rtol=1e-5)
