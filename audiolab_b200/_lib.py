@@ -42,6 +42,7 @@ SIGNATURES = {
                                   C.c_void_p]),
     "al_rotary_bf16": (C.c_int, [C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_int, C.c_int, c_i64, C.c_int, C.c_void_p]),
     "al_gate_sigmoid_bf16": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, C.c_int, C.c_int, C.c_void_p]),
+    "al_gate_sigmoid_ld_bf16": (C.c_int, [C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_int, C.c_int, C.c_void_p]),
     "al_gelu_bf16": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
     "al_band_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_int,
                                          C.c_int, C.c_int, C.c_float, C.c_void_p]),

@@ -19,6 +19,18 @@
 namespace al {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int sm_count() {
+    static std::atomic<int> cache[64];
+    int d = 0;
+    cudaGetDevice(&d);
+    int n = cache[d & 63].load(std::memory_order_relaxed);
+    if (n == 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+        if (n <= 0) n = 148;
+        cache[d & 63].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 }  // namespace al
 
 namespace {
@@ -50,13 +62,32 @@ struct al_plan {
     float2* d_ctw = nullptr;      // [(D-1)*513]
     float2* d_ctw_full = nullptr; // n_fft 2048 only: [1024] exp(-2 pi i k / 2048) (packed stereo fast path of K2)
     float2* d_ctw_half = nullptr; // n_fft 2048 only: [544] 0.5 * exp(-2 pi i k / 2048) (packed stereo fast path)
+    struct Env {
+        float* table = nullptr;
+        cudaEvent_t ready = nullptr;   // recorded on `stream` after the build
+        cudaStream_t stream = nullptr;
+        unsigned long long stamp = 0;  // LRU
+    };
+    static constexpr int kMaxEnv = 8;
     std::mutex mu;
-    std::map<int, float*> env;    // n_frames_total -> inv_env table
+    std::map<int, Env> env;       // n_frames_total -> 1 / sum(w^2) table (bounded LRU)
+    unsigned long long env_clock = 0;
+    int device = -1;              // device the tables live on
 };
+
+// A plan's tables live on the device that was current when it was created; launching with another current device
+// would hand its kernels foreign pointers.
+static int check_device(const al_plan* plan, const char* what) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != plan->device)
+        return fail(AL_E_ARG, "%s: the plan was created on device %d but device %d is current", what, plan->device, dev);
+    return AL_OK;
+}
 
 extern "C" {
 
-int al_version(void) { return 100; }
+int al_version(void) { return 110; }
 
 const char* al_last_error(void) { return g_err.c_str(); }
 
@@ -73,6 +104,7 @@ int al_plan_create(int n_fft, int hop, const float* window_host, int normalized,
     p->hop = hop;
     p->normalized = normalized ? 1 : 0;
     p->D = n_fft / 1024;
+    cudaGetDevice(&p->device);
     const int N = n_fft, D = p->D;
     const double kPi = 3.14159265358979323846;
     std::vector<float> raw(N), wa(N), ws(N);
@@ -135,7 +167,10 @@ int al_plan_destroy(al_plan* p) {
     cudaFree(p->d_ctw);
     cudaFree(p->d_ctw_half);
     cudaFree(p->d_ctw_full);
-    for (auto& kv : p->env) cudaFree(kv.second);
+    for (auto& kv : p->env) {
+        cudaFree(kv.second.table);
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+    }
     delete p;
     return AL_OK;
 }
@@ -146,6 +181,7 @@ int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch
             void* stream) {
     if (!plan || !track || !spec) return fail(AL_E_ARG, "al_stft: NULL argument");
     if (n_chunks == 0 || n_frames == 0) return AL_OK;
+    if (int rc = check_device(plan, "al_stft")) return rc;
     if (channels <= 0 || n_chunks < 0 || n_frames < 0 || chunk_len <= 0)
         return fail(AL_E_ARG, "al_stft: bad sizes (channels %d chunks %d frames %d chunk_len %d)", channels,
                     n_chunks, n_frames, chunk_len);
@@ -209,21 +245,45 @@ int al_stft(const al_plan* plan, const float* track, int64_t n_valid, int64_t ch
     return AL_OK;
 }
 
+// 1 / sum(w^2) tables, one per frame count, built on the CALLER's stream (no host synchronisation) and published to
+// other streams through an event.  The cache is bounded: a long-running process that sees a new MDX track length per
+// song (invert_stem's whole-track iSTFT) would otherwise grow by ~4 bytes per sample per distinct length.
 static int get_env(al_plan* plan, int n_frames_total, cudaStream_t stream, const float** out) {
     std::lock_guard<std::mutex> lk(plan->mu);
     auto it = plan->env.find(n_frames_total);
-    if (it != plan->env.end()) { *out = it->second; return AL_OK; }
+    if (it != plan->env.end()) {
+        it->second.stamp = ++plan->env_clock;
+        if (it->second.stream != stream) {
+            cudaError_t e = cudaStreamWaitEvent(stream, it->second.ready, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "al_istft: envelope wait");
+        }
+        *out = it->second.table;
+        return AL_OK;
+    }
+    while (plan->env.size() >= (size_t)al_plan::kMaxEnv) {
+        auto victim = plan->env.begin();
+        for (auto j = plan->env.begin(); j != plan->env.end(); ++j)
+            if (j->second.stamp < victim->second.stamp) victim = j;
+        cudaFree(victim->second.table);           // synchronises with every kernel that may still read the table
+        cudaEventDestroy(victim->second.ready);
+        plan->env.erase(victim);
+    }
     const long long total = (long long)(n_frames_total - 1) * plan->hop + plan->n_fft;
-    float* d = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d, total * sizeof(float));
+    al_plan::Env ent;
+    cudaError_t e = cudaMalloc((void**)&ent.table, total * sizeof(float));
     if (e != cudaSuccess) return cuda_fail(e, "al_istft: envelope alloc");
-    // built on the legacy default stream and synchronised so every later stream sees it
-    e = al::launch_env(plan->d_win_raw, plan->n_fft, plan->hop, n_frames_total, d, (cudaStream_t)0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
-    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(e, "al_istft: envelope build"); }
-    (void)stream;
-    plan->env[n_frames_total] = d;
-    *out = d;
+    e = cudaEventCreateWithFlags(&ent.ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = al::launch_env(plan->d_win_raw, plan->n_fft, plan->hop, n_frames_total, ent.table, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ent.ready, stream);
+    if (e != cudaSuccess) {
+        cudaFree(ent.table);
+        if (ent.ready) cudaEventDestroy(ent.ready);
+        return cuda_fail(e, "al_istft: envelope build");
+    }
+    ent.stream = stream;
+    ent.stamp = ++plan->env_clock;
+    plan->env[n_frames_total] = ent;
+    *out = ent.table;
     return AL_OK;
 }
 
@@ -235,6 +295,7 @@ int al_istft(const al_plan* plan_c, const float* spec, const float* mask, int la
     al_plan* plan = const_cast<al_plan*>(plan_c);
     if (!plan || !spec || !dst) return fail(AL_E_ARG, "al_istft: NULL argument");
     if (n_chunks == 0 || out_len == 0) return AL_OK;
+    if (int rc = check_device(plan, "al_istft")) return rc;
     if (n_chunks < 0 || stems <= 0 || channels <= 0 || n_frames_in <= 0 || out_len < 0 || frame_pad < 0)
         return fail(AL_E_ARG, "al_istft: bad sizes");
     if (layout < 0 || layout > 3) return fail(AL_E_ARG, "al_istft: bad layout %d", layout);
@@ -376,8 +437,19 @@ int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, 
     if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0)
         return fail(AL_E_ARG, "al_gate_sigmoid_bf16: bad sizes (dim_head must be a multiple of 8)");
     if ((reinterpret_cast<uintptr_t>(o) & 15) != 0) return fail(AL_E_ARG, "al_gate_sigmoid_bf16: o must be 16-byte aligned");
-    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, (cudaStream_t)stream);
+    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, heads, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_gate_sigmoid_bf16");
+    return AL_OK;
+}
+
+int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, void* stream) {
+    if (!o || !gates) return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0 || gate_ld < heads || gate_ld > (1 << 20))
+        return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: bad sizes (dim_head must be a multiple of 8, gate_ld >= heads)");
+    if ((reinterpret_cast<uintptr_t>(o) & 15) != 0) return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: o must be 16-byte aligned");
+    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, (int)gate_ld, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_gate_sigmoid_ld_bf16");
     return AL_OK;
 }
 

@@ -457,7 +457,7 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     if (c.M <= 0 || c.N <= 0 || c.K <= 0 || c.groups <= 0) return "bad sizes";
     if ((c.K & 7) != 0 || (c.lda & 7) != 0 || (c.ldw & 7) != 0) return "K, lda, ldw must be multiples of 8 (16-byte rows)";
     if ((reinterpret_cast<uintptr_t>(c.A) | reinterpret_cast<uintptr_t>(c.W)) & 15) return "A, W must be 16-byte aligned";
-    const int BN = c.epi == EPI_RES ? 256 : (c.N > 128 ? 256 : (c.N > 64 ? 128 : 64));
+    const int BN = c.epi == EPI_RES ? (c.N % 256 == 0 ? 256 : 128) : (c.N > 128 ? 256 : (c.N > 64 ? 128 : 64));
     GemmArgs g{};
     g.M = (int)c.M; g.N = c.N; g.K = c.K; g.groups = c.groups;
     g.m_tiles = (int)((c.M + BM - 1) / BM);
@@ -477,7 +477,7 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(W) failed";
     if (c.epi == EPI_RES) {
-        if (c.N % 256 != 0) return "residual epilogue needs N to be a multiple of 256";
+        if (c.N % 128 != 0) return "residual epilogue needs N to be a multiple of 128";
         if (!c.x32 || !c.xb) return "residual epilogue needs x32 and xb";
         if ((c.ldx & 3) != 0 || (c.ldxb & 7) != 0) return "ldx / ldxb must give 16-byte rows";
         if (!make_map(&tm.o[0], c.x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.N, c.M, c.groups, c.ldx, c.x_group_stride, 32, 32,
@@ -489,7 +489,8 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
         tm.o[2] = tm.o[1];
         tm.o[3] = tm.o[1];
         g.out_split = c.N;
-        *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
+        if (BN == 256) *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
+        else *cuda_err = launch_cfg<128, 4, EPI_RES>(tm, g, 4, stream);
         return *cuda_err == cudaSuccess ? nullptr : "launch failed";
     }
     // EPI_BF16

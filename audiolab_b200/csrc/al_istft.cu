@@ -367,11 +367,11 @@ static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStrea
     IstftParams p = p0;
     const int rows = n_chunks * p.stems * p.channels;
     const size_t smem = istft_tiling<D>(p, rows);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.mark();
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     istft_kernel<D><<<(unsigned)(rows * p.segs), UW * 32, smem, stream>>>(p);

@@ -412,13 +412,7 @@ static size_t ip_launch_shape(IstftPkParams& p, int n_chunks, int n_sm, int W) {
 
 cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
     IstftPkParams p = p0;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = sm_count();
     const int rows = n_chunks * p.stems;
     static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
     static const int ola_fast = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
@@ -428,15 +422,15 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     if (smem > cap) return cudaErrorInvalidValue;
 #define AL_IP_LAUNCH(MSK, WW, PP)                                                                                    \
     do {                                                                                                      \
-        static bool attr = false;                                                                             \
-        if (!attr) {                                                                                          \
+        static PerDeviceOnce attr;                                                                             \
+        if (attr.needed()) {                                                                                          \
             cudaError_t e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)cap);                                                   \
             if (e != cudaSuccess) return e;                                                                   \
             e = cudaFuncSetAttribute(istft_pk2_kernel<MSK, WW, PP>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
                                      cudaSharedmemCarveoutMaxShared);                                         \
             if (e != cudaSuccess) return e;                                                                   \
-            attr = true;                                                                                      \
+            attr.mark();                                                                                      \
         }                                                                                                     \
         istft_pk2_kernel<MSK, WW, PP><<<(unsigned)(rows * p.segs), WW * 32, smem, stream>>>(p);                 \
     } while (0)

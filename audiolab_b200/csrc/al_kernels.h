@@ -11,6 +11,23 @@ namespace al {
 
 void count_launch();
 
+// "Has this been done on the CURRENT device?"  Function attributes (the > 48 KB shared memory opt-in) and the SM
+// count are per device; a process that drives several GPUs must not reuse the first device's answers.
+struct PerDeviceOnce {
+    unsigned long long done = 0;
+    bool needed() const {
+        int d = 0;
+        cudaGetDevice(&d);
+        return ((__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull) == 0;
+    }
+    void mark() {
+        int d = 0;
+        cudaGetDevice(&d);
+        __atomic_fetch_or(&done, 1ull << (d & 63), __ATOMIC_RELEASE);
+    }
+};
+int sm_count();   // of the current device (cached per device)
+
 // [emul-begin]
 
 struct StftParams {
@@ -143,7 +160,7 @@ cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, 
                                 float scale, float eps, cudaStream_t stream);
 cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head,
                                long long pos_div, int pos_mod, cudaStream_t stream);
-cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld,
                              cudaStream_t stream);
 
 cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream);

@@ -145,12 +145,12 @@ cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_ro
 // o: [n_rows, heads * dim_head] bf16, gates: [n_rows, heads] bf16;  o[row, h, :] *= sigmoid(gates[row, h])
 __global__ void __launch_bounds__(256)
 gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates, long long n_vec, int vec_per_row,
-                 int heads, int dim_head) {
+                 int gate_ld, int dim_head) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vec) return;
     const long long row = i / vec_per_row;
     const int h = ((int)(i - row * vec_per_row) * 8) / dim_head;
-    const float g = __bfloat162float(gates[row * heads + h]);
+    const float g = __bfloat162float(gates[row * gate_ld + h]);
     const float sg = 1.f / (1.f + __expf(-g));
     float a[8];
     bf16x8_to_f32(o[i], a);
@@ -161,12 +161,12 @@ gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates,
 
 // [emul-end]
 
-cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head,
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld,
                              cudaStream_t stream) {
     const int vec_per_row = heads * dim_head / 8;
     const long long n_vec = n_rows * vec_per_row;
     gate_bf16_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
+        reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, gate_ld, dim_head);
     count_launch();
     return cudaGetLastError();
 }

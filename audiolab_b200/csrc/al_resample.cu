@@ -271,11 +271,11 @@ cudaError_t launch_resample(const float* in, long long in_stride, float* out, lo
     const int span_cap = (int)(((long long)kResTile * down) / up + tpp + 4);
     const size_t smem = ((size_t)tpp * up + span_cap) * sizeof(float);
     if (smem > 160 * 1024) return cudaErrorInvalidValue;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         cudaError_t e = cudaFuncSetAttribute(resample_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.mark();
     }
     dim3 grid((unsigned)((n_out + kResTile - 1) / kResTile), (unsigned)rows);
     resample_generic_kernel<<<grid, 256, smem, stream>>>(in, in_stride, out, out_stride, n_in, n_out, up, down, taps,

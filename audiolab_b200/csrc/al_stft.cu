@@ -199,11 +199,11 @@ static cudaError_t launch_stft_d(const StftParams& p0, int rows, cudaStream_t st
     constexpr int UW = Cfg<D>::UW;
     StftParams p = p0;
     const size_t smem = stft_tiling<D>(p);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         cudaError_t e = cudaFuncSetAttribute(stft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set.mark();
     }
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     stft_kernel<D><<<(unsigned)(rows * p.tiles), UW * 32, smem, stream>>>(p);

@@ -277,23 +277,17 @@ cudaError_t launch_stft_pk(const StftPkParams& p0, cudaStream_t stream) {
     const size_t cap = 227 * 1024;
     const size_t smem = pk_launch_shape(p);
     if (smem == 0) return cudaErrorInvalidValue;
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = sm_count();
     const bool full = p.n_bins_out == 1025 && p.zero_low_bins == 0;
     const unsigned grid = (unsigned)(p.total_tiles < n_sm ? p.total_tiles : n_sm);
 #define AL_PK_LAUNCH(L, F)                                                                                   \
     do {                                                                                                      \
-        static bool attr = false;                                                                             \
-        if (!attr) {                                                                                          \
+        static PerDeviceOnce attr;                                                                             \
+        if (attr.needed()) {                                                                                          \
             cudaError_t e = cudaFuncSetAttribute(stft_pk2_kernel<L, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  (int)cap);                                                   \
             if (e != cudaSuccess) return e;                                                                   \
-            attr = true;                                                                                      \
+            attr.mark();                                                                                      \
         }                                                                                                     \
         stft_pk2_kernel<L, F><<<grid, kPkThreads, smem, stream>>>(p);                                        \
     } while (0)

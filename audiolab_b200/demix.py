@@ -22,6 +22,8 @@ import random
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
+import collections
+
 import torch
 import torch.nn.functional as F
 
@@ -29,12 +31,31 @@ from . import spectral as sp
 from .configs import HTDemucsConfig, MdxConfig, RoformerConfig
 
 
+# Offset / multiplicity tables of a chunk schedule are tiny and repeat for every track of the same length: keep the
+# device copies (each torch.tensor(list, device=cuda) is a blocking pageable host-to-device copy).
+_DEV_TABLES: "collections.OrderedDict" = collections.OrderedDict()
+_DEV_TABLES_MAX = 256
+
+
+def _dev_table(v: Sequence[int], device, dtype) -> torch.Tensor:
+    key = (tuple(int(x) for x in v), str(device), dtype)
+    hit = _DEV_TABLES.get(key)
+    if hit is not None:
+        _DEV_TABLES.move_to_end(key)
+        return hit
+    t = torch.tensor(key[0], dtype=dtype, device=device)
+    _DEV_TABLES[key] = t
+    while len(_DEV_TABLES) > _DEV_TABLES_MAX:
+        _DEV_TABLES.popitem(last=False)
+    return t
+
+
 def _dev_i64(v: Sequence[int], device) -> torch.Tensor:
-    return torch.tensor(list(v), dtype=torch.int64, device=device)
+    return _dev_table(v, device, torch.int64)
 
 
 def _dev_i32(v: Sequence[int], device) -> torch.Tensor:
-    return torch.tensor(list(v), dtype=torch.int32, device=device)
+    return _dev_table(v, device, torch.int32)
 
 
 def _check_mix(mix: torch.Tensor, channels: int = 2) -> torch.Tensor:
@@ -164,7 +185,8 @@ class MdxDemixer:
         n_chunks = len(offs)
         spek = self.plan.stft(mix, chunk_len=chunk, n_chunks=n_chunks, off0=-trim, off_step=step,
                               n_frames=c.dim_t, layout=sp.CAC, n_bins_out=c.dim_f,
-                              zero_low_bins=0 if is_match_mix else c.zero_low_bins)
+                              zero_low_bins=c.zero_low_bins)   # upstream run_model zeroes the low bins before the
+                                                               # is_match_mix branch: the identity pass loses them too
         pred = spek if is_match_mix else self._net(spek)
         waves = self.plan.istft(pred, n_chunks=n_chunks, channels=2, layout=sp.CAC, out_len=chunk)
         wtab = tab_id = None

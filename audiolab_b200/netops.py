@@ -53,9 +53,14 @@ def rotary_(q: torch.Tensor, k: torch.Tensor, cos_sin: torch.Tensor, heads: int,
 def gate_sigmoid_(o: torch.Tensor, gates: torch.Tensor, heads: int, dim_head: int) -> None:
     """o[row, h, :] *= sigmoid(gates[row, h]) in place."""
     _check_bf16_rows(o, "o")
-    _check_bf16_rows(gates, "gates")
     if o.shape[1] != heads * dim_head or tuple(gates.shape) != (o.shape[0], heads):
         raise ValueError("o must be [rows, heads*dim_head] and gates [rows, heads]")
+    if gates.is_cuda and gates.dtype == torch.bfloat16 and gates.stride(1) == 1 and gates.stride(0) != heads:
+        # the gate columns of the fused to_qkv + to_gates GEMM output: a strided view
+        _lib.check(_lib.lib().al_gate_sigmoid_ld_bf16(o.data_ptr(), gates.data_ptr(), gates.stride(0), o.shape[0], heads,
+                                                      dim_head, _stream()), "al_gate_sigmoid_ld_bf16")
+        return
+    _check_bf16_rows(gates, "gates")
     _lib.check(_lib.lib().al_gate_sigmoid_bf16(o.data_ptr(), gates.data_ptr(), o.shape[0], heads, dim_head, _stream()),
                "al_gate_sigmoid_bf16")
 
@@ -182,23 +187,29 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Te
     _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16")
 
 
+def resid_slab(n: int) -> int:
+    """Columns per partial sum of squares of the residual epilogue (its N tile)."""
+    return 256 if n % 256 == 0 else 128
+
+
 def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss_out: torch.Tensor, *,
                        bias: Optional[torch.Tensor] = None, max_ctas: int = 0) -> None:
-    """x32 += a @ w^T + bias (fp32, in place); xb = bf16(x32); ss_out[m, j] = sum of x32[m, 256 j : 256 (j+1)]^2."""
+    """x32 += a @ w^T + bias (fp32, in place); xb = bf16(x32); ss_out[m, j] = sum of x32[m, S j : S (j+1)]^2 with
+    S = resid_slab(N)."""
     _rows2d(a, "a", torch.bfloat16)
     _rows2d(w, "w", torch.bfloat16)
     _rows2d(x32, "x32", torch.float32)
     _rows2d(xb, "xb", torch.bfloat16)
     g, m, k, lda, ags = _geom(a)
     gw, n, kw, ldw, wgs = _geom(w)
-    if gw != g or kw != k or n % 256 != 0:
-        raise ValueError("a and w disagree on groups / K, or N is not a multiple of 256")
+    if gw != g or kw != k or n % 128 != 0:
+        raise ValueError("a and w disagree on groups / K, or N is not a multiple of 128")
     gx, mx, nx, ldx, xgs = _geom(x32)
     gb, mb, nb, ldxb, xbgs = _geom(xb)
     if (gx, mx, nx) != (g, m, n) or (gb, mb, nb) != (g, m, n):
         raise ValueError("x32 / xb must be [groups, M, N]")
-    if ss_out.dtype != torch.float32 or not ss_out.is_contiguous() or ss_out.numel() != g * m * (n // 256):
-        raise ValueError("ss_out must be contiguous fp32 [groups * M, N / 256]")
+    if ss_out.dtype != torch.float32 or not ss_out.is_contiguous() or ss_out.numel() != g * m * (n // resid_slab(n)):
+        raise ValueError("ss_out must be contiguous fp32 [groups * M, N / resid_slab(N)]")
     args = GemmArgs()
     args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
     args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs

@@ -26,6 +26,7 @@ import os
 from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
+_TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 
 
 class RMSNorm(nn.Module):
@@ -301,6 +302,108 @@ class RoformerMaskNet(nn.Module):
             x2 = x2 + pending.to(x2.dtype)
         return x2.view(b, t, f, d)
 
+    # ---- bf16 inference path on the tcgen05 GEMM (csrc/al_gemm.cu): fp32 residual stream, RMSNorm / rotary / GELU /
+    # bias / residual adds folded into the GEMM epilogues ---------------------------------------------------------
+    def _tc_supported(self) -> bool:
+        """Shapes the fused epilogues cover: 64-wide heads (one rotary head per 64-column epilogue step), q / k / v
+        column blocks on N-tile boundaries, residual width on 128-column slabs."""
+        c = self.cfg
+        inner = c.heads * c.dim_head
+        return (_TC_GEMM and c.dim_head == 64 and inner % 256 == 0 and c.heads <= 16 and c.dim % 128 == 0
+                and c.dim % 8 == 0 and int(c.dim * c.ff_mult) % 8 == 0)
+
+    def _tc_pack(self, attn: Attention, ff: FeedForward):
+        """bf16 operands of one (attention, feed-forward) pair, made once: gamma of the pre-norms folded into the
+        columns of to_qkv / to_gates / ff.Linear1 (RMSNorm(x) W^T = diag(rowscale) x (gamma (.) W)^T), to_gates appended
+        to to_qkv as 16 extra output rows (8 real + zero padding) with its bias."""
+        params = (attn.norm.gamma, attn.to_qkv.weight, attn.to_gates.weight, attn.to_gates.bias, attn.to_out[0].weight,
+                  ff.net[0].gamma, ff.net[1].weight, ff.net[1].bias, ff.net[4].weight, ff.net[4].bias)
+        key = ("tc", id(attn))
+        ver = tuple(p._version for p in params) + (str(params[0].device),)
+        hit = self._bf16_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            h = attn.heads
+            g1 = attn.norm.gamma.detach().float()
+            wq = attn.to_qkv.weight.detach().float() * g1[None, :]
+            wg = attn.to_gates.weight.detach().float() * g1[None, :]
+            n3 = wq.shape[0]
+            w_qkvg = torch.zeros(n3 + 16, wq.shape[1], device=wq.device)
+            w_qkvg[:n3] = wq
+            w_qkvg[n3:n3 + h] = wg
+            b_qkvg = torch.zeros(n3 + 16, device=wq.device)
+            b_qkvg[n3:n3 + h] = attn.to_gates.bias.detach().float()
+            g2 = ff.net[0].gamma.detach().float()
+            pack = {
+                "w_qkvg": w_qkvg.to(self._fused_dtype).contiguous(), "b_qkvg": b_qkvg.contiguous(),
+                "w_out": attn.to_out[0].weight.detach().to(self._fused_dtype).contiguous(),
+                "w1": (ff.net[1].weight.detach().float() * g2[None, :]).to(self._fused_dtype).contiguous(),
+                "b1": ff.net[1].bias.detach().float().contiguous(),
+                "w2": ff.net[4].weight.detach().to(self._fused_dtype).contiguous(),
+                "b2": ff.net[4].bias.detach().float().contiguous(),
+            }
+        self._bf16_cache[key] = (ver, pack)
+        return pack
+
+    def _transformer_tc(self, st, tr: Transformer, geom, time_axis: bool):
+        from .. import netops
+        b, t, f = geom
+        x32, xb, ss, q, k, v, gates, hid = st
+        d = x32.shape[1]
+        scale = float(d) ** 0.5
+        for attn, ff in tr.layers:
+            h = attn.heads
+            dh = attn.to_qkv.weight.shape[0] // (3 * h)
+            inner = h * dh
+            pk = self._tc_pack(attn, ff)
+            rot = attn.rotary_embed
+            cs = None
+            if rot is not None:
+                cs = self._cos_sin(rot, t if time_axis else f, x32.device)
+            # to_qkv + to_gates of RMSNorm(x): row scale from the sums of squares the last residual epilogue left
+            netops.gemm_bf16(xb, pk["w_qkvg"], [q, k, v, gates], bias=pk["b_qkvg"], row_ss=ss, ss_scale=scale,
+                             cos_sin=cs, pos_div=(f if time_axis else 1), pos_mod=(t if time_axis else f),
+                             rot_cols=2 * inner if cs is not None else 0, out_split=inner)
+            shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
+            o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
+                                               v.view(shape).transpose(1, 2))
+            o = o.transpose(1, 2)
+            if not o.is_contiguous():
+                o = o.contiguous()
+            o2 = o.view(-1, inner)
+            netops.gate_sigmoid_(o2, gates[:, :h], h, dh)
+            netops.gemm_bf16_residual(o2, pk["w_out"], x32, xb, ss)                       # x += to_out(gated attention)
+            netops.gemm_bf16(xb, pk["w1"], hid, bias=pk["b1"], row_ss=ss, ss_scale=scale, act="gelu")
+            netops.gemm_bf16_residual(hid, pk["w2"], x32, xb, ss, bias=pk["b2"])          # x += ff(x)
+        if isinstance(tr.norm, RMSNorm):
+            netops.resid_prepare(x32, x32, xb, ss, gamma=tr.norm.gamma.detach().float())
+
+    def _axial_tc(self, x):
+        """bf16-operand twin of `_axial` (+ BS-RoFormer's final norm) on the tcgen05 GEMM.  The residual stream is fp32
+        (x32) with a bf16 shadow (xb) as the A operand of the next GEMM; every row-wise operator between two
+        contractions except the attention gate lives in a GEMM epilogue."""
+        from .. import netops
+        b, t, f, d = x.shape
+        m = b * t * f
+        dev = x.device
+        c = self.cfg
+        inner = c.heads * c.dim_head
+        x32 = torch.empty((m, d), device=dev, dtype=torch.float32)
+        xb = torch.empty((m, d), device=dev, dtype=self._fused_dtype)
+        ss = torch.empty((m, d // netops.resid_slab(d)), device=dev, dtype=torch.float32)
+        netops.resid_prepare(x.reshape(m, d).float().contiguous(), x32, xb, ss)
+        q, k, v = (torch.empty((m, inner), device=dev, dtype=self._fused_dtype) for _ in range(3))
+        gates = torch.empty((m, 16), device=dev, dtype=self._fused_dtype)
+        hid = torch.empty((m, int(d * c.ff_mult)), device=dev, dtype=self._fused_dtype)
+        st = (x32, xb, ss, q, k, v, gates, hid)
+        for time_transformer, freq_transformer in self.layers:
+            self._transformer_tc(st, time_transformer, (b, t, f), True)
+            self._transformer_tc(st, freq_transformer, (b, t, f), False)
+        if c.kind != "mel":
+            netops.resid_prepare(x32, x32, xb, ss, gamma=self.final_norm.gamma.detach().float())
+        return xb.view(b, t, f, d)
+
     def set_compute_dtype(self, dtype: torch.dtype) -> "RoformerMaskNet":
         self.compute_dtype = dtype
         return self
@@ -328,7 +431,7 @@ class RoformerMaskNet(nn.Module):
             x = self.band_split(x)
             if ac and x.is_cuda and self.compute_dtype == torch.bfloat16:
                 with torch.autocast("cuda", enabled=False):
-                    x = self._axial_fused(x)
+                    x = self._axial_tc(x) if self._tc_supported() else self._axial_fused(x)
             else:
                 x = self._axial(x)
                 if c.kind != "mel":

@@ -113,6 +113,39 @@ class Separator:
                 "AUDIOLAB_B200_RANDOM_INIT=1 to run with seeded random weights)")
         return None
 
+    def _demucs_state_dict_or_none(self, path: str):
+        """Weights of an HTDemucs model name.  Upstream names are bag-of-models ``.yaml`` files
+        (``models: [<signature>, ...]``, optional ``weights:``) next to ``<signature>.th`` packages.  A single-model
+        bag (htdemucs_6s, htdemucs) is resolved to its ``.th`` file; a real bag (htdemucs_ft: four fine-tuned models,
+        one per source) is NOT averaged here -- it raises instead of silently running something else.  A missing file
+        falls back to seeded random weights only with allow_random_init."""
+        if path.endswith(".yaml") and os.path.exists(path):
+            import yaml
+            with open(path) as fh:
+                bag = yaml.safe_load(fh) or {}
+            sigs = list(bag.get("models") or [])
+            if len(sigs) != 1:
+                raise NotImplementedError(
+                    f"{path}: bag of {len(sigs)} models (per-source weighted average, demucs.apply.BagOfModels) is not "
+                    "implemented; use a single-model bag (htdemucs.yaml, htdemucs_6s.yaml)")
+            th = os.path.join(os.path.dirname(path), f"{sigs[0]}.th")
+            if not os.path.exists(th):
+                matches = [f for f in os.listdir(os.path.dirname(path)) if f.startswith(str(sigs[0])) and f.endswith(".th")]
+                if not matches:
+                    raise FileNotFoundError(f"{path} names model {sigs[0]!r} but no {sigs[0]}*.th file is beside it")
+                th = os.path.join(os.path.dirname(path), matches[0])
+            path = th
+        if os.path.exists(path) and not path.endswith(".yaml"):
+            pkg = torch.load(path, map_location="cpu", weights_only=True)
+            if isinstance(pkg, dict) and "state" in pkg:          # demucs.states package: {klass, args, kwargs, state}
+                pkg = pkg["state"]
+            return pkg.get("state_dict", pkg) if isinstance(pkg, dict) else pkg
+        if not self.allow_random_init:
+            raise FileNotFoundError(
+                f"{path} not found and allow_random_init is False (set allow_random_init=True or "
+                "AUDIOLAB_B200_RANDOM_INIT=1 to run with seeded random weights)")
+        return None
+
     def load_model(self, model_filename: str = "model_bs_roformer_ep_368_sdr_12.9628.ckpt"):
         arch = _arch_of(model_filename)
         path = os.path.join(self.model_file_dir, model_filename)
@@ -167,9 +200,11 @@ class Separator:
             cfg = HTDemucsConfig(num_sources=6 if six else 4, shifts=shifts, overlap=float(self.demucs_params["overlap"]))
             cfg = replace(cfg, **ov)
             if net is None:
-                self._state_dict_or_none(path)
+                sd = self._demucs_state_dict_or_none(path)
                 torch.manual_seed(4321)
                 net = HTDemucsCore(num_sources=cfg.num_sources)
+                if sd is not None:
+                    net.load_state_dict(sd, strict=True)
             net = net.to(self.torch_device).eval()
             autocast = self.use_autocast
 

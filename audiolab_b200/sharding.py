@@ -80,28 +80,41 @@ def plan_chunk_ranges(offsets: Sequence[int], chunk_len: int, n_total: int, worl
     return out
 
 
-def exchange_halo(halo_out: Optional[torch.Tensor], halo_in: Optional[torch.Tensor], rank: int,
-                  right: Optional[int], left: Optional[int], group=None) -> None:
-    """One neighbour exchange: send `halo_out` to `right`, receive `halo_in` from `left` (in place)."""
+def start_halo_exchange(halo_out: Optional[torch.Tensor], halo_in: Optional[torch.Tensor], right: Optional[int],
+                        left: Optional[int], group=None) -> list:
+    """Post one neighbour exchange without waiting: send `halo_out` to `right`, receive `halo_in` from `left` (in
+    place).  Both operations go out as ONE group (a single NCCL kernel per rank, no send-before-receive chain along
+    the ranks); returns the requests to `wait()` on before `halo_in` is read."""
     ops = []
     if right is not None and halo_out is not None and halo_out.numel():
         ops.append(dist.P2POp(dist.isend, halo_out, right, group))
     if left is not None and halo_in is not None and halo_in.numel():
         ops.append(dist.P2POp(dist.irecv, halo_in, left, group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    return list(dist.batch_isend_irecv(ops)) if ops else []
+
+
+def exchange_halo(halo_out: Optional[torch.Tensor], halo_in: Optional[torch.Tensor], rank: int,
+                  right: Optional[int], left: Optional[int], group=None) -> None:
+    """Blocking form of `start_halo_exchange`."""
+    for req in start_halo_exchange(halo_out, halo_in, right, left, group):
+        req.wait()
 
 
 def sharded_ola(chunk_waves_fn: Callable[[int, int], torch.Tensor], gather_fn: Callable[..., torch.Tensor],
                 offsets: Sequence[int], chunk_len: int, n_total: int, rows: int, rank: int, world_size: int,
-                device, group=None) -> Tuple[Optional[torch.Tensor], ChunkRange]:
-    """Chunk-range sharded demix + overlap-add.
+                device, group=None, stats: Optional[dict] = None) -> Tuple[Optional[torch.Tensor], ChunkRange]:
+    """Chunk-range sharded demix + overlap-add, with the halo exchange overlapped with the interior chunks.
 
-    chunk_waves_fn(c0, c1) -> [c1-c0, rows, chunk_len] chunk outputs of the owned chunks.
+    chunk_waves_fn(c0, c1) -> [c1-c0, rows, chunk_len] chunk outputs of chunks [c0, c1).
     gather_fn(waves, c0, c1, p0, p1, halo_in, raw_out) -> [rows, p1-p0]: ascending-chunk weighted sum
         over chunks [0, c1) with data only for [c0, c1) (normalised unless raw_out).
-    Returns (owned span [rows, p1-p0] or None for an idle rank, its ChunkRange).
+    Order of work on a rank: (1) the TAIL chunks -- the ones that reach past the owned span -- are evaluated first and
+    their raw partial sums over the neighbour's head are posted (isend) together with the receive of this rank's own
+    head halo; (2) the interior chunks are evaluated while the exchange is in flight; (3) wait, then the ascending
+    gather of the owned span continues the left neighbour's partial sums.  The order in which chunks are EVALUATED does
+    not enter the result: the gather always sums in ascending chunk order.
+    Returns (owned span [rows, p1-p0] or None for an idle rank, its ChunkRange).  `stats` (optional dict) receives
+    halo_bytes_out / halo_bytes_in / tail_chunks.
     """
     plan = plan_chunk_ranges(offsets, chunk_len, n_total, world_size)
     me = plan[rank]
@@ -111,12 +124,28 @@ def sharded_ola(chunk_waves_fn: Callable[[int, int], torch.Tensor], gather_fn: C
     pos = live.index(rank)
     left = live[pos - 1] if pos > 0 else None
     right = live[pos + 1] if pos + 1 < len(live) else None
-    waves = chunk_waves_fn(me.c0, me.c1)
+    # first chunk whose samples reach past the owned span
+    ct = me.c1
+    if right is not None and me.halo_out:
+        while ct > me.c0 and offsets[ct - 1] + chunk_len > me.p1:
+            ct -= 1
+    tail = chunk_waves_fn(ct, me.c1) if ct < me.c1 else None
     halo_out = None
     if right is not None and me.halo_out:
-        halo_out = gather_fn(waves, me.c0, me.c1, me.p1, me.p1 + me.halo_out, None, True).contiguous()
+        halo_out = gather_fn(tail, ct, me.c1, me.p1, me.p1 + me.halo_out, None, True).contiguous()
     halo_in = torch.empty((rows, me.halo_in), dtype=torch.float32, device=device) if me.halo_in else None
-    exchange_halo(halo_out, halo_in, rank, right, left, group)
+    reqs = start_halo_exchange(halo_out, halo_in, right, left, group)
+    if stats is not None:
+        stats["halo_bytes_out"] = 0 if halo_out is None else halo_out.numel() * 4
+        stats["halo_bytes_in"] = 0 if halo_in is None else halo_in.numel() * 4
+        stats["tail_chunks"] = me.c1 - ct
+    if ct > me.c0:
+        head = chunk_waves_fn(me.c0, ct)
+        waves = head if tail is None else torch.cat((head, tail), dim=0)
+    else:
+        waves = tail
+    for req in reqs:
+        req.wait()
     parts = []
     if me.halo_in:
         parts.append(gather_fn(waves, me.c0, me.c1, me.p0, me.p0 + me.halo_in, halo_in, False))
@@ -133,7 +162,7 @@ class ShardedRoformerDemixer:
         self.demixer, self.rank, self.world_size, self.group = demixer, rank, world_size, group
 
     @torch.no_grad()
-    def demix_span(self, mix: torch.Tensor):
+    def demix_span(self, mix: torch.Tensor, stats: Optional[dict] = None):
         """Every rank holds `mix` [s, n]; returns (owned span [stems*s, p1-p0] or None, ChunkRange)."""
         from . import spectral as sp
         from .demix import _dev_i32, _dev_i64, roformer_schedule
@@ -158,7 +187,7 @@ class ShardedRoformerDemixer:
                                  out=_ShiftedOut(out, p0))
             return out
 
-        return sharded_ola(waves_fn, gather_fn, offs, C, n, rows, self.rank, self.world_size, dev, self.group)
+        return sharded_ola(waves_fn, gather_fn, offs, C, n, rows, self.rank, self.world_size, dev, self.group, stats)
 
 
 class _ShiftedOut:

@@ -191,6 +191,8 @@ int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, i
 int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int heads, int dim_head, int64_t pos_div,
                    int pos_mod, void* stream);
 int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream);
+/* as al_gate_sigmoid_bf16 with a row stride: gates[row * gate_ld + h] (the gate columns of the fused to_qkv + to_gates GEMM) */
+int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, void* stream);
 int al_gelu_bf16(void* x, int64_t n, void* stream);
 int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
                            int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
@@ -214,8 +216,9 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
  *   act: AL_GEMM_ACT_NONE / _GELU (exact erf form) / _TANH.
  *   Output columns [i * out_split, (i + 1) * out_split) go to out[i] (row stride ldo[i], group stride
  *     o_group_stride[i]); out_split = 0 means one output.  At most 4 outputs.
- * epi = AL_GEMM_EPI_RESIDUAL (N % 256 == 0):  x32[m, n] += acc + bias[n] in place (fp32 residual stream),
- *   xb[m, n] = bf16(x32[m, n]),  ss_out[m * (N / 256) + n / 256] = sum over that 256-column slab of x32[m, n]^2.
+ * epi = AL_GEMM_EPI_RESIDUAL (N % 128 == 0):  x32[m, n] += acc + bias[n] in place (fp32 residual stream),
+ *   xb[m, n] = bf16(x32[m, n]),  ss_out[m * (N / S) + n / S] = sum over that S-column slab of x32[m, n]^2, with the
+ *   slab width S = 256 if N % 256 == 0, else 128.
  *
  * K, lda, ldw, ldo, ldxb multiples of 8, ldx of 4, N of 8; all pointers 16-byte aligned.  max_ctas = 0 uses every SM.
  */

@@ -181,9 +181,10 @@ def test_orchestrator_rejects_out_of_scope_options():
     from audiolab_b200.orchestrator import separate_music
     with pytest.raises(NotImplementedError):
         separate_music({"/tmp/x": []}, reverb_removal="All")
-    with pytest.raises(NotImplementedError):
-        separate_music({"/tmp/x": []}, vocals_only=False)
+    with pytest.raises(NotImplementedError):          # MDX23C is the 4th model of the reference's list
+        separate_music({"/tmp/x": []}, ensemble_strength=4)
     assert separate_music({"/tmp/x": ["/nonexistent.wav"]}) == []
+    assert separate_music({"/tmp/x": ["/nonexistent.wav"]}, vocals_only=False) == []
 
 
 def test_separator_arch_resolution():

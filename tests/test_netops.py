@@ -253,3 +253,80 @@ def test_band_attention_kernel(cuda, F_, H, n_seq):
     ref_rotary_(qr, kr, cs, H, 64, 1, F_)
     ref = ref_band_attention(qr, kr, v, n_seq, F_, H, 64, gates).float()
     assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())
+
+
+# ---- host logic of the tcgen05 path (nets/roformer.py::_axial_tc) with the GEMM replaced by its torch definition ----
+def ref_gemm_bf16(a, w, outs, *, bias=None, row_ss=None, ss_scale=1.0, ss_eps=1e-12, cos_sin=None, pos_div=1, pos_mod=1,
+                  rot_cols=0, act=None, out_split=0, max_ctas=0):
+    if isinstance(outs, torch.Tensor):
+        outs = [outs]
+    y = a.float() @ w.float().t()
+    m, n = y.shape
+    if row_ss is not None:
+        y = y * (ss_scale / row_ss.view(m, -1).sum(-1).sqrt().clamp(min=ss_eps))[:, None]
+    if bias is not None:
+        y = y + bias
+    if cos_sin is not None:
+        assert rot_cols % 64 == 0 and tuple(cos_sin.shape) == (pos_mod, 32, 2)
+        pos = (torch.arange(m) // pos_div) % pos_mod
+        c, s = cos_sin[pos][:, None, :, 0], cos_sin[pos][:, None, :, 1]
+        z = y[:, :rot_cols].reshape(m, rot_cols // 64, 32, 2)
+        y = torch.cat((torch.stack((z[..., 0] * c - z[..., 1] * s, z[..., 1] * c + z[..., 0] * s), dim=-1).reshape(m, rot_cols),
+                       y[:, rot_cols:]), dim=1)
+    if act == "gelu":
+        y = F.gelu(y)
+    elif act == "tanh":
+        y = torch.tanh(y)
+    split = out_split or n
+    for i, o in enumerate(outs):
+        o.copy_(y[:, i * split: i * split + o.shape[1]].to(o.dtype))
+
+
+def ref_gemm_bf16_residual(a, w, x32, xb, ss_out, *, bias=None, max_ctas=0):
+    import audiolab_b200.netops as netops
+    y = x32 + a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    x32.copy_(y)
+    xb.copy_(y.to(xb.dtype))
+    slab = netops.resid_slab(y.shape[1])
+    ss_out.copy_(y.view(y.shape[0], -1, slab).square().sum(-1))
+
+
+def ref_resid_prepare(x_in, x32, xb, ss, *, bias=None, gamma=None, eps=1e-12):
+    y = x_in if bias is None else x_in + bias
+    if gamma is not None:
+        y = F.normalize(y, dim=-1) * (y.shape[-1] ** 0.5) * gamma
+    y = y.clone()
+    x32.copy_(y)
+    xb.copy_(y.to(xb.dtype))
+    ss.copy_(y.view(y.shape[0], ss.shape[1], -1).square().sum(-1))
+
+
+@pytest.mark.parametrize("kind", ["bs", "mel"])
+def test_tc_axial_host_logic_matches_module_path(kind, monkeypatch):
+    """`_axial_tc`: gamma folded into the weights + row scale in the consumer's epilogue, to_gates riding on to_qkv,
+    rotary in the epilogue, fp32 residual stream -- with the kernels replaced by fp32 torch definitions the result must
+    equal the upstream-shaped module path."""
+    import audiolab_b200.netops as netops
+    torch.manual_seed(0)
+    kw = dict(dim=128, depth=2, heads=4, dim_head=64, chunk_size=441 * 12)
+    cfg = RoformerConfig(**kw) if kind == "bs" else RoformerConfig(kind="mel", num_bands=20, **kw)
+    net = RoformerMaskNet(cfg).eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    assert net._tc_supported()
+    monkeypatch.setattr(netops, "gemm_bf16", ref_gemm_bf16)
+    monkeypatch.setattr(netops, "gemm_bf16_residual", ref_gemm_bf16_residual)
+    monkeypatch.setattr(netops, "resid_prepare", ref_resid_prepare)
+    monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    net._fused_dtype = torch.float32
+    b, t, f = 2, 13, len(net.band_split.dim_inputs)
+    x = torch.randn(b, t, f, cfg.dim)
+    with torch.no_grad():
+        ref = net._axial(x.clone())
+        if kind != "mel":
+            ref = net.final_norm(ref)
+        got = net._axial_tc(x.clone())
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))

@@ -6,9 +6,12 @@ import math
 import sys
 import time
 
+import os
+
 import torch
 
-from audiolab_b200 import netops
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from audiolab_b200 import netops  # noqa: E402
 
 
 def describe(out, ref, name):
