@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128)
 band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o,
                       const __nv_bfloat16* __restrict__ gates, const float2* __restrict__ cos_sin, int F, int H,
-                      float scale) {
+                      float scale, int gate_ld) {
     __shared__ __align__(16) __nv_bfloat16 Qs[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Ks[kBaF * kBaLd];
     __shared__ __align__(16) __nv_bfloat16 Vs[kBaF * kBaLd];
@@ -152,8 +152,9 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     if (gates) {   // upstream Attention: out * to_gates(x).sigmoid(), gates [n_seq * F, H]; folded into the normalisation
         const long long t0 = (long long)s * F + r0;
-        if (r0 < F) inv0 *= 1.f / (1.f + __expf(-__bfloat162float(gates[t0 * H + h])));
-        if (r0 + 8 < F) inv1 *= 1.f / (1.f + __expf(-__bfloat162float(gates[(t0 + 8) * H + h])));
+        const long long gld = gate_ld > 0 ? gate_ld : H;                 // row stride of the gate matrix
+        if (r0 < F) inv0 *= 1.f / (1.f + __expf(-__bfloat162float(gates[t0 * gld + h])));
+        if (r0 + 8 < F) inv1 *= 1.f / (1.f + __expf(-__bfloat162float(gates[(t0 + 8) * gld + h])));
     }
     // ---- O = P V -------------------------------------------------------------------------------------------------
     const unsigned short* vs16 = reinterpret_cast<const unsigned short*>(Vs);
@@ -186,14 +187,14 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 // [emul-end]
 
 cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
-                                  long long n_seq, int F, int heads, float scale, cudaStream_t stream) {
+                                  long long n_seq, int F, int heads, float scale, int gate_ld, cudaStream_t stream) {
     if (n_seq <= 0) return cudaSuccess;
     const long long ctas = n_seq * heads;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
     band_attn_bf16_kernel<<<(unsigned)ctas, 128, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
         reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
-        reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, heads, scale);
+        reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, heads, scale, gate_ld);
     count_launch();
     return cudaGetLastError();
 }

@@ -463,8 +463,8 @@ int al_gelu_bf16(void* x, int64_t n, void* stream) {
     return AL_OK;
 }
 
-int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
-                           int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream) {
+int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
+                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream) {
     if (!q || !k || !v || !o) return fail(AL_E_ARG, "al_band_attention_bf16: NULL argument");
     if (n_seq == 0) return AL_OK;
     if (n_seq < 0 || heads <= 0) return fail(AL_E_ARG, "al_band_attention_bf16: bad sizes");
@@ -473,7 +473,10 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
     if (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
           reinterpret_cast<uintptr_t>(o)) & 15) != 0)
         return fail(AL_E_ARG, "al_band_attention_bf16: pointers must be 16-byte aligned");
-    cudaError_t e = al::launch_band_attn_bf16(q, k, v, o, gates, cos_sin, n_seq, seq_len, heads, scale, (cudaStream_t)stream);
+    if (gates && gate_ld != 0 && (gate_ld < heads || gate_ld > (1 << 20)))
+        return fail(AL_E_ARG, "al_band_attention_bf16: gate_ld %lld must be 0 (= heads) or >= heads", (long long)gate_ld);
+    cudaError_t e = al::launch_band_attn_bf16(q, k, v, o, gates, cos_sin, n_seq, seq_len, heads, scale, (int)gate_ld,
+                                              (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_band_attention_bf16");
     return AL_OK;
 }

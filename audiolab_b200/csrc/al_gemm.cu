@@ -8,8 +8,9 @@
 //   warp 1     MMA      : one thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) from shared-memory descriptors
 //                         into one of TWO accumulators in tensor memory; tcgen05.commit releases ring slots and
 //                         publishes the finished accumulator
-//   warps 2..5 epilogue : tcgen05.ld of their 32-lane quadrant, the fused epilogue in registers, swizzled staging in
-//                         shared memory and TMA stores; accumulator t+1 is being computed while t is drained
+//   warps 2..9 epilogue : tcgen05.ld of their 32-lane quadrant (two warps per quadrant split the columns), the fused
+//                         epilogue in registers on the packed fp32 pipe, swizzled staging in shared memory and TMA
+//                         stores; accumulator t+1 is being computed while t is drained
 //
 // Fused epilogues (what the reference runs as separate PyTorch kernels between two GEMMs):
 //   EPI_BF16 : v = acc * rowscale[m] + bias[n]  -> optional rotary embedding on column pairs -> optional GELU / tanh
@@ -18,7 +19,7 @@
 //              (gamma is folded into W once on the host).  The output columns may be routed to up to 4 tensors
 //              (q / k / v / gates).
 //   EPI_RES  : x32 += acc + bias (fp32 residual stream, read and written in place through TMA), xb = bf16(x32) (the
-//              next GEMM's A operand), ss[m][n_tile] = partial sum of squares of the new row (the next rowscale).
+//              next GEMM's A operand), ss[m][n_tile][half] = partial sums of squares of the new row (the next rowscale).
 //
 // Reference call site accelerated: modules/separator/stem_separator.py:281 (separator.separate -> model forward under
 // autocast, :106); upstream module tree restated in nets/roformer.py.
@@ -39,14 +40,15 @@ namespace tc {
 constexpr int BM = 128;          // rows of A per tile = tensor memory lanes
 constexpr int BK = 64;           // bf16 elements per 128-byte swizzled row
 constexpr int UK = 16;           // K of one tcgen05.mma kind::f16
-constexpr int kThreads = 192;    // 6 warps
-constexpr int kEpiWarps = 4;
-constexpr int kResSlots = 4;     // EPI_RES: ring of 32-column fp32 chunks in flight per epilogue warp
+constexpr int kThreads = 320;    // 10 warps: TMA producer, MMA issuer, 8 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kResSlots = 2;     // EPI_RES: ring of 32-column fp32 chunks per epilogue warp
 
 struct Tmaps {
     CUtensorMap a, b;
     CUtensorMap o[4];   // EPI_BF16: outputs (bf16, box 64 x 32, 128-byte swizzle)
-                        // EPI_RES : o[0] = x32 (fp32, box 32 x 32, 128-byte swizzle), o[1] = xb (bf16, box 32 x 32, 64-byte swizzle)
+                        // EPI_RES : o[0] = x32 (fp32, box 32 x 32, 128-byte swizzle), o[1] = xb (bf16, box 32 x 32, 64-byte
+                        //           swizzle), o[2] = x32 again with a 64 x 128 box for the L2 prefetch
 };
 
 template <int BN, int STAGES, int EPI>
@@ -54,7 +56,7 @@ struct SmemLayout {
     static constexpr int kA = BM * BK * 2;                    // 16 KB
     static constexpr int kB = BN * BK * 2;
     static constexpr int kStage = kA + kB;
-    static constexpr int kEpiPerWarp = EPI == EPI_RES ? (kResSlots * 4096 + 2 * 2048) : (2 * 4096);
+    static constexpr int kEpiPerWarp = EPI == EPI_RES ? (kResSlots * 4096 + 2048) : 4096;
     static constexpr int kEpiOff = STAGES * kStage;
     static constexpr int kBarOff = kEpiOff + kEpiWarps * kEpiPerWarp;
     static constexpr int kNumBars = 2 * STAGES + 4 + kEpiWarps * kResSlots;
@@ -123,6 +125,12 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
                 const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+                if constexpr (EPI == EPI_RES) {
+                    // the fp32 residual tile this accumulator will be added to: into L2 now, so that the epilogue's
+                    // small ring of TMA loads sees L2 latency, not HBM latency
+#pragma unroll
+                    for (int c = 0; c < BN / 64; ++c) tma_prefetch_3d(&tm.o[2], n_blk * BN + c * 64, m_blk * BM, grp);
+                }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_arrive_expect_tx(full_bar(stage), (uint32_t)L::kStage);
@@ -170,15 +178,20 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
         }
     } else {
         // ================================= epilogue warps =================================
-        const int ew = warp - 2;                 // 0..3: private staging buffers / barriers
-        const int q = warp & 3;                  // tensor memory lane quadrant this warp may access
+        // 8 warps: warp w may touch tensor memory lanes 32 (w % 4) .. + 31 only, so two warps share a lane quadrant
+        // and split the accumulator's columns (half 0 / half 1).  Two warps per scheduler keep the issue slots busy
+        // while one of them waits on tcgen05.ld / shared memory / the TMA store.
+        const int ew = warp - 2;                 // 0..7: private staging buffers / barriers
+        const int q = warp & 3;                  // tensor memory lane quadrant
+        const int half = ew >> 2;                // which half of the N tile
         const uint32_t ebuf = base + L::kEpiOff + (uint32_t)ew * L::kEpiPerWarp;
         unsigned char* ebuf_ptr = base_ptr + L::kEpiOff + ew * L::kEpiPerWarp;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 
         if constexpr (EPI == EPI_BF16) {
+            constexpr int kWarpCols = BN / 2 >= 64 ? BN / 2 : 64;      // columns per warp, in 64-column steps
+            const int wcol0 = half * kWarpCols;                         // first column of this warp inside the tile
             int it = 0;
-            int buf = 0;
             for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
                 const int grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
@@ -194,45 +207,56 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     for (int p = 0; p < g.ss_parts; ++p) ss += __ldg(g.row_ss + grow * g.ss_parts + p);
                     rs = g.ss_scale / fmaxf(sqrtf(ss), g.ss_eps);
                 }
+                const float2 rs2 = make_float2(rs, rs);
                 int pos = 0;
                 if (g.cos_sin != nullptr) pos = (int)((row / g.pos_div) % g.pos_mod);
                 const int n0 = n_blk * BN;
                 const int n_cols = min(BN, g.N - n0);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                const int steps = (n_cols + 63) >> 6;
+                int steps = 0;
+                if (wcol0 < BN && wcol0 < n_cols) steps = (min(n_cols - wcol0, kWarpCols) + 63) >> 6;
+                if (steps == 0) {                                   // nothing of this tile is ours (ragged / narrow tile)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
                 for (int st = 0; st < steps; ++st) {
                     uint32_t r[2][32];
-                    const uint32_t ta = lane_taddr + (uint32_t)(acc * BN + st * 64);
+                    const int tcol = wcol0 + st * 64;
+                    const uint32_t ta = lane_taddr + (uint32_t)(acc * BN + tcol);
                     tmem_ld_32x32(ta, r[0]);
-                    if (BN >= 64) tmem_ld_32x32(ta + 32, r[1]);
+                    tmem_ld_32x32(ta + 32, r[1]);
                     tmem_wait_ld();
-                    if (st == steps - 1) {                      // accumulator fully read: hand it back to the MMA warp
+                    if (st == steps - 1) {                      // our part of the accumulator is in registers
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(acc));
                     }
-                    const int col0 = n0 + st * 64;
+                    const int col0 = n0 + tcol;
                     const bool rot = g.cos_sin != nullptr && col0 < g.rot_cols;
-                    // the staging buffer about to be written was handed to a TMA store two steps ago
-                    if (lane == 0) bulk_wait_read<1>();
+                    // the staging buffer is still being read by the TMA store of the previous step
+                    if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    unsigned char* sb = ebuf_ptr + buf * 4096 + lane * 128;
+                    unsigned char* sb = ebuf_ptr + lane * 128;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        if (BN < 64 && h == 1) break;
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[h][j]) * rs;
+                        float2 v[16];
                         if (g.bias != nullptr) {
                             const float4* bp = reinterpret_cast<const float4*>(g.bias + (long long)grp * g.N + col0 + h * 32);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                if (col0 + h * 32 + j * 4 < g.N) {
-                                    const float4 b = __ldg(bp + j);
-                                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                                }
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (col0 + h * 32 + j * 4 < g.N) b = __ldg(bp + j);
+                                v[2 * j] = __ffma2_rn(make_float2(__uint_as_float(r[h][4 * j]), __uint_as_float(r[h][4 * j + 1])), rs2,
+                                                      make_float2(b.x, b.y));
+                                v[2 * j + 1] = __ffma2_rn(make_float2(__uint_as_float(r[h][4 * j + 2]), __uint_as_float(r[h][4 * j + 3])),
+                                                          rs2, make_float2(b.z, b.w));
                             }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                v[j] = __fmul2_rn(make_float2(__uint_as_float(r[h][2 * j]), __uint_as_float(r[h][2 * j + 1])), rs2);
                         }
                         if (rot) {
                             // pair (2i, 2i+1) of a 64-wide head turns by pos * freq_i; a 64-column step is one head
@@ -240,27 +264,25 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 c = __ldg(cp + j);          // (cos, sin) of pairs 2j, 2j+1 of this half
-                                const float a0 = v[4 * j], a1 = v[4 * j + 1], b0 = v[4 * j + 2], b1 = v[4 * j + 3];
-                                v[4 * j] = a0 * c.x - a1 * c.y;
-                                v[4 * j + 1] = a1 * c.x + a0 * c.y;
-                                v[4 * j + 2] = b0 * c.z - b1 * c.w;
-                                v[4 * j + 3] = b1 * c.z + b0 * c.w;
+                                const float2 a = v[2 * j], b = v[2 * j + 1];
+                                v[2 * j] = make_float2(a.x * c.x - a.y * c.y, a.y * c.x + a.x * c.y);
+                                v[2 * j + 1] = make_float2(b.x * c.z - b.y * c.w, b.y * c.z + b.x * c.w);
                             }
                         }
                         if (g.act == ACT_GELU) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                            for (int j = 0; j < 16; ++j) v[j] = gelu_erf2(v[j]);
                         } else if (g.act == ACT_TANH) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+                            for (int j = 0; j < 16; ++j) v[j] = make_float2(tanh_fast(v[j].x), tanh_fast(v[j].y));
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint4 u;
-                            u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-                            u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                            u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            u.x = pack_bf16(v[4 * j].x, v[4 * j].y);
+                            u.y = pack_bf16(v[4 * j + 1].x, v[4 * j + 1].y);
+                            u.z = pack_bf16(v[4 * j + 2].x, v[4 * j + 2].y);
+                            u.w = pack_bf16(v[4 * j + 3].x, v[4 * j + 3].y);
                             const int chunk = h * 4 + j;                 // 16-byte chunk of the 128-byte row
                             *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
                         }
@@ -269,51 +291,58 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     __syncwarp();
                     if (lane == 0) {
                         const int oi = col0 / g.out_split;
-                        tma_store_3d(&tm.o[oi], ebuf + (uint32_t)buf * 4096, col0 - oi * g.out_split, row0, grp);
+                        tma_store_3d(&tm.o[oi], ebuf, col0 - oi * g.out_split, row0, grp);
                         bulk_commit();
                     }
-                    buf ^= 1;
                 }
             }
             if (lane == 0) bulk_wait<0>();
         } else {
             // ---------------- EPI_RES: x32 += acc + bias ; xb = bf16(x32) ; ss partials ----------------
-            constexpr int CH = BN / 32;
+            // Each warp streams the 32-column chunks of its half of the tile: the fp32 residual chunk arrives by TMA
+            // (prefetched into L2 by the producer warp when the tile's main loop started) into a 2-slot ring, is
+            // updated in place and leaves by TMA together with its bf16 image.
+            constexpr int CH = BN / 64;                                 // chunks per tile per warp
             const int n_my = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
             const long long n_chunks = (long long)n_my * CH;
-            auto coords = [&](long long gc, int& grp, int& row0, int& col0) {
+            auto coords = [&](long long gc, int& grp, int& row0, int& col0, int& tcol) {
                 const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
                 const int tile = (int)blockIdx.x + it * (int)gridDim.x;
                 grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
                 const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
                 row0 = m_blk * BM + q * 32;
-                col0 = n_blk * BN + c * 32;
+                tcol = half * (BN / 2) + c * 32;
+                col0 = n_blk * BN + tcol;
             };
             auto issue_load = [&](long long gc) {
-                int grp, row0, col0;
-                coords(gc, grp, row0, col0);
+                int grp, row0, col0, tcol;
+                coords(gc, grp, row0, col0, tcol);
                 const int slot = (int)(gc & (kResSlots - 1));
                 mbar_arrive_expect_tx(res_bar(ew, slot), 4096u);
                 tma_load_3d(ebuf + (uint32_t)slot * 4096, &tm.o[0], res_bar(ew, slot), col0, row0, grp);
             };
-            if (lane == 0)
-                for (long long gc = 0; gc < kResSlots - 1 && gc < n_chunks; ++gc) issue_load(gc);
+            if (lane == 0 && n_chunks > 0) issue_load(0);
             float ss = 0.f;
             for (long long gc = 0; gc < n_chunks; ++gc) {
                 const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-                int grp, row0, col0;
-                coords(gc, grp, row0, col0);
+                int grp, row0, col0, tcol;
+                coords(gc, grp, row0, col0, tcol);
                 if (c == 0) {
                     mbar_wait(tfull_bar(acc), acc_phase);
                     tc_fence_after();
                     ss = 0.f;
                 }
                 uint32_t r[32];
-                tmem_ld_32x32(lane_taddr + (uint32_t)(acc * BN + c * 32), r);
+                tmem_ld_32x32(lane_taddr + (uint32_t)(acc * BN + tcol), r);
                 const int slot = (int)(gc & (kResSlots - 1));
+                if (lane == 0) {
+                    bulk_wait_read<0>();                      // chunk gc-1's stores have read their buffers
+                    if (gc + 1 < n_chunks) issue_load(gc + 1);
+                }
+                __syncwarp();
                 mbar_wait(res_bar(ew, slot), (uint32_t)(gc / kResSlots) & 1u);
                 tmem_wait_ld();
                 if (c == CH - 1) {
@@ -322,7 +351,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
                 unsigned char* rb = ebuf_ptr + slot * 4096 + lane * 128;
-                unsigned char* xb = ebuf_ptr + kResSlots * 4096 + (int)(gc & 1) * 2048 + lane * 64;
+                unsigned char* xb = ebuf_ptr + kResSlots * 4096 + lane * 64;
                 const float* bias = g.bias != nullptr ? g.bias + (long long)grp * g.N + col0 : nullptr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -359,15 +388,13 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_3d(&tm.o[0], ebuf + (uint32_t)slot * 4096, col0, row0, grp);
-                    tma_store_3d(&tm.o[1], ebuf + (uint32_t)(kResSlots * 4096 + (int)(gc & 1) * 2048), col0, row0, grp);
+                    tma_store_3d(&tm.o[1], ebuf + (uint32_t)(kResSlots * 4096), col0, row0, grp);
                     bulk_commit();
-                    bulk_wait_read<1>();                      // chunk gc-1's stores have read their buffers
-                    if (gc + kResSlots - 1 < n_chunks) issue_load(gc + kResSlots - 1);
                 }
-                __syncwarp();
                 if (c == CH - 1 && g.ss_out != nullptr) {
+                    // the two warps of a lane quadrant each hold half of the slab's sum: [row][n_tile][half]
                     const long long row = (long long)row0 + lane;
-                    if (row < g.M) g.ss_out[((long long)grp * g.M + row) * g.n_tiles + (col0 / BN)] = ss;
+                    if (row < g.M) g.ss_out[(((long long)grp * g.M + row) * g.n_tiles + (col0 / BN)) * 2 + half] = ss;
                 }
             }
             if (lane == 0) bulk_wait<0>();
@@ -486,7 +513,9 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
         if (!make_map(&tm.o[1], c.xb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.N, c.M, c.groups, c.ldxb, c.xb_group_stride, 32, 32,
                       CU_TENSOR_MAP_SWIZZLE_64B))
             return "cuTensorMapEncodeTiled(xb) failed";
-        tm.o[2] = tm.o[1];
+        if (!make_map(&tm.o[2], c.x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.N, c.M, c.groups, c.ldx, c.x_group_stride, 64, BM,
+                      CU_TENSOR_MAP_SWIZZLE_NONE))
+            return "cuTensorMapEncodeTiled(x32 prefetch) failed";
         tm.o[3] = tm.o[1];
         g.out_split = c.N;
         if (BN == 256) *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);

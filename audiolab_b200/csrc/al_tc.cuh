@@ -87,6 +87,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Pull the box at these coordinates into L2 (no shared memory, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
@@ -196,6 +202,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
     p = fmaf(p, t, -1.6279250383377075f);
     const float erf_abs = 1.0f - fast_ex2(p * t);
     return 0.5f * fmaf(ax, erf_abs, x);
+}
+// Two elements at a time on the packed fp32 pipe (FFMA2 / FMUL2): relu(x) - 0.5 |x| 2^(t P(t)) is the same function.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    float2 t = __fmul2_rn(ax, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+    t.x = fminf(t.x, 4.0f);
+    t.y = fminf(t.y, 4.0f);
+    float2 p = make_float2(1.4203174214344472e-4f, 1.4203174214344472e-4f);
+    p = __ffma2_rn(p, t, make_float2(-3.6642320919781923e-3f, -3.6642320919781923e-3f));
+    p = __ffma2_rn(p, t, make_float2(3.089611791074276e-2f, 3.089611791074276e-2f));
+    p = __ffma2_rn(p, t, make_float2(-1.496993899345398e-1f, -1.496993899345398e-1f));
+    p = __ffma2_rn(p, t, make_float2(-9.181655049324036e-1f, -9.181655049324036e-1f));
+    p = __ffma2_rn(p, t, make_float2(-1.6279250383377075f, -1.6279250383377075f));
+    const float2 pt = __fmul2_rn(p, t);
+    const float2 e = make_float2(fast_ex2(pt.x), fast_ex2(pt.y));
+    const float2 h = __fmul2_rn(ax, make_float2(-0.5f, -0.5f));
+    return __ffma2_rn(h, e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 // tanh(x) = 1 - 2 / (1 + e^(2x)), two MUFU ops, ~1e-7 absolute
 __device__ __forceinline__ float tanh_fast(float x) {

@@ -86,16 +86,18 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
         _check_bf16_rows(t, name)
     if q.shape != k.shape or q.shape != v.shape or tuple(q.shape) != (n_seq * seq_len, heads * dim_head):
         raise ValueError("q, k, v must be [n_seq * seq_len, heads * dim_head]")
+    gate_ld = 0
     if gates is not None:
-        _check_bf16_rows(gates, "gates")
-        if tuple(gates.shape) != (q.shape[0], heads):
-            raise ValueError("gates must be [n_seq * seq_len, heads]")
+        if (not gates.is_cuda or gates.dtype != torch.bfloat16 or tuple(gates.shape) != (q.shape[0], heads)
+                or gates.stride(1) != 1):
+            raise ValueError("gates must be a CUDA bf16 [n_seq * seq_len, heads] tensor with unit column stride")
+        gate_ld = gates.stride(0)
     if cos_sin is not None and (cos_sin.dtype != torch.float32 or tuple(cos_sin.shape) != (seq_len, dim_head // 2, 2)
                                 or not cos_sin.is_contiguous() or not cos_sin.is_cuda):
         raise ValueError("cos_sin must be a contiguous CUDA fp32 [seq_len, dim_head/2, 2] tensor")
     o = torch.empty_like(q)
     _lib.check(_lib.lib().al_band_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
-                                                 None if gates is None else gates.data_ptr(),
+                                                 None if gates is None else gates.data_ptr(), int(gate_ld),
                                                  None if cos_sin is None else cos_sin.data_ptr(), int(n_seq), int(seq_len),
                                                  int(heads), int(dim_head), float(dim_head) ** -0.5, _stream()),
                "al_band_attention_bf16")
@@ -188,8 +190,8 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Te
 
 
 def resid_slab(n: int) -> int:
-    """Columns per partial sum of squares of the residual epilogue (its N tile)."""
-    return 256 if n % 256 == 0 else 128
+    """Columns per partial sum of squares of the residual epilogue (half of its N tile: one epilogue warp's share)."""
+    return 128 if n % 256 == 0 else 64
 
 
 def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss_out: torch.Tensor, *,

@@ -26,6 +26,7 @@ import os
 from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
+_BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "0") == "1"   # band-axis attention kernel inside the tc path
 _TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 
 
@@ -365,14 +366,18 @@ class RoformerMaskNet(nn.Module):
             netops.gemm_bf16(xb, pk["w_qkvg"], [q, k, v, gates], bias=pk["b_qkvg"], row_ss=ss, ss_scale=scale,
                              cos_sin=cs, pos_div=(f if time_axis else 1), pos_mod=(t if time_axis else f),
                              rot_cols=2 * inner if cs is not None else 0, out_split=inner)
-            shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
-            o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
-                                               v.view(shape).transpose(1, 2))
-            o = o.transpose(1, 2)
-            if not o.is_contiguous():
-                o = o.contiguous()
-            o2 = o.view(-1, inner)
-            netops.gate_sigmoid_(o2, gates[:, :h], h, dh)
+            if not time_axis and _BAND_ATTN_TC and f <= 64:
+                # band axis (<= 64 tokens per sequence): our kernel (csrc/al_attn.cu), sigmoid gate folded into its epilogue
+                o2 = netops.band_attention(q, k, v, b * t, f, h, dh, gates=gates[:, :h])
+            else:
+                shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
+                o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
+                                                   v.view(shape).transpose(1, 2))
+                o = o.transpose(1, 2)
+                if not o.is_contiguous():
+                    o = o.contiguous()
+                o2 = o.view(-1, inner)
+                netops.gate_sigmoid_(o2, gates[:, :h], h, dh)
             netops.gemm_bf16_residual(o2, pk["w_out"], x32, xb, ss)                       # x += to_out(gated attention)
             netops.gemm_bf16(xb, pk["w1"], hid, bias=pk["b1"], row_ss=ss, ss_scale=scale, act="gelu")
             netops.gemm_bf16_residual(hid, pk["w2"], x32, xb, ss, bias=pk["b2"])          # x += ff(x)

@@ -182,7 +182,8 @@ int al_sub(const float* a, const float* b, float* out, int64_t n, void* stream);
  *   x [n] bf16, n a multiple of 8.
  * al_band_attention_bf16 -- upstream Attention.forward of the frequency (band-axis) transformer:
  *   softmax(q k^T * scale) v per (sequence, head); q, k, v, o [n_seq * seq_len, heads * 64] bf16, token (s, f) in row
- *   s * seq_len + f; seq_len <= 64, dim_head = 64.  gates (nullable) [n_seq * seq_len, heads] bf16: o *= sigmoid(gate);
+ *   s * seq_len + f; seq_len <= 64, dim_head = 64.  gates (nullable) [n_seq * seq_len, heads] bf16 with row stride gate_ld
+ *   (0 = heads): o *= sigmoid(gate);
  *   cos_sin (nullable) [seq_len, 32, 2] fp32: q and k are rotated by their band position first (al_rotary_bf16 semantics).  Opt-in on the host side (AUDIOLAB_B200_BAND_ATTN=1); the default
  *   calls the library attention (cuDNN through PyTorch).
  */
@@ -194,8 +195,8 @@ int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, 
 /* as al_gate_sigmoid_bf16 with a row stride: gates[row * gate_ld + h] (the gate columns of the fused to_qkv + to_gates GEMM) */
 int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, void* stream);
 int al_gelu_bf16(void* x, int64_t n, void* stream);
-int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
-                           int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
+int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
+                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
 
 /*
  * al_gemm_bf16 -- K4: one nn.Linear (or a batch of `groups` of them) of the RoFormer mask network on the tcgen05
@@ -218,7 +219,7 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
  *     o_group_stride[i]); out_split = 0 means one output.  At most 4 outputs.
  * epi = AL_GEMM_EPI_RESIDUAL (N % 128 == 0):  x32[m, n] += acc + bias[n] in place (fp32 residual stream),
  *   xb[m, n] = bf16(x32[m, n]),  ss_out[m * (N / S) + n / S] = sum over that S-column slab of x32[m, n]^2, with the
- *   slab width S = 256 if N % 256 == 0, else 128.
+ *   slab width S = 128 if N % 256 == 0, else 64.
  *
  * K, lda, ldw, ldo, ldxb multiples of 8, ldx of 4, N of 8; all pointers 16-byte aligned.  max_ctas = 0 uses every SM.
  */

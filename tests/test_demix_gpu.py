@@ -257,7 +257,7 @@ def test_separate_process_audio_end_to_end(cuda, tmp_path, monkeypatch):
     res = w.process_audio([project_files.ProjectFiles(str(src))], callback=lambda f, d, t: seen.append(f))
     assert len(res) == 1 and seen[0] == 0 and seen[-1] == 1.0
     outs = sorted(os.path.basename(p) for p in res[0].last_outputs)
-    assert outs == ["track_(Instrumental).wav", "track_(Vocals).wav"]
+    assert outs == ["track__(Instrumental).wav", "track__(Vocals).wav"]   # `{base}__{label}.wav`, stem_separator.py:667
     v, sr = read_wav(res[0].last_outputs[0])
     assert sr == 44100 and v.shape == (2, 88200) and np.isfinite(v).all() and np.abs(v).max() <= 1.0 + 1e-6
 

@@ -127,23 +127,24 @@ def test_gemm_strided_views_and_groups():
     _close_bf16(out, ref, "grouped")
 
 
-@pytest.mark.parametrize("m,k,with_bias", [(128, 512, False), (1000, 512, True), (5000, 2048, True)])
-def test_gemm_residual_epilogue(m, k, with_bias):
+@pytest.mark.parametrize("m,k,with_bias,n", [(128, 512, False, 512), (1000, 512, True, 512), (5000, 2048, True, 512),
+                                               (700, 384, True, 384)])
+def test_gemm_residual_epilogue(m, k, with_bias, n):
     netops = _cuda()
-    n = 512
     a = _rand((m, k), 14).bfloat16()
     w = _rand((n, k), 15, k ** -0.5).bfloat16()
     bias = _rand((n,), 16) if with_bias else None
     x0 = _rand((m, n), 17, 2.0)
     x32 = x0.clone()
     xb = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ss = torch.full((m, 2), float("nan"), device="cuda")
+    parts = n // netops.resid_slab(n)
+    ss = torch.full((m, parts), float("nan"), device="cuda")
     netops.gemm_bf16_residual(a, w, x32, xb, ss, bias=bias, max_ctas=5 if m > 1000 else 0)
     torch.cuda.synchronize()
     ref = x0 + a.float() @ w.float().t() + (bias if with_bias else 0.0)
     assert torch.allclose(x32, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max())), float((x32 - ref).abs().max())
     assert torch.equal(xb, x32.bfloat16()), "xb must be the bf16 rounding of the stored fp32 row"
-    ss_ref = torch.stack((x32[:, :256].square().sum(-1), x32[:, 256:].square().sum(-1)), dim=-1)
+    ss_ref = x32.view(m, parts, -1).square().sum(-1)
     assert torch.allclose(ss, ss_ref, rtol=1e-5), float((ss - ss_ref).abs().max())
 
 

@@ -105,7 +105,7 @@ extern "C" void emul_band_attn(const void* q, const void* k, const void* v, void
     emul_launch(dim3(n_seq * H), dim3(128), [&] {
         band_attn_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                               reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
-                              reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, H, scale);
+                              reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, H, scale, 0);
     });
 }
 

@@ -79,7 +79,7 @@ def main():
         x0 = torch.randn(m, n, device=dev)
         x32 = x0.clone()
         xb = torch.full((m, n), float("nan"), device=dev, dtype=torch.bfloat16)
-        ss = torch.zeros(m, 2, device=dev)
+        ss = torch.zeros(m, n // netops.resid_slab(n), device=dev)
         netops.gemm_bf16_residual(a, w, x32, xb, ss)
         torch.cuda.synchronize()
         ref = x0 + a.float() @ w.float().t()
@@ -98,7 +98,7 @@ def main():
         if kind.endswith("res"):
             x32 = torch.randn(M, n, device=dev)
             xb = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
-            ss = torch.empty(M, 2, device=dev)
+            ss = torch.empty(M, n // netops.resid_slab(n), device=dev)
             t = timed(lambda: netops.gemm_bf16_residual(a, w, x32, xb, ss))
             xres = torch.randn(M, n, device=dev).bfloat16()
             t_ref = timed(lambda: xres.addmm_(a, w.t()))
