@@ -26,7 +26,7 @@ import os
 from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
-_BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "0") == "1"   # band-axis attention kernel inside the tc path
+_BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "1") != "0"   # band-axis attention kernel inside the tc path (default)
 _TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 
 

@@ -176,11 +176,21 @@ class Separator:
                             zero_low_bins=3)
             cfg = replace(cfg, **ov)
             if net is None:
-                if not self.allow_random_init:
-                    raise FileNotFoundError(f"{path}: ONNX import is out of scope; pass model_overrides[...]['net'] "
-                                            "or allow_random_init=True")
-                torch.manual_seed(4321)
-                net = TfcTdfNet(cfg.dim_f)
+                # No onnxruntime / onnx importer here (handlers/patch_separate.py:45-63 runs the .onnx through ORT).  A
+                # released model is taken as a converted state dict `<name>.pt` / `.pth` next to the `.onnx` name (KUIELab
+                # module names, nets/tfc_tdf.py::ConvTdfNet); otherwise seeded random weights of the released shape.
+                from .nets.tfc_tdf import ConvTdfNet
+                stem = os.path.splitext(path)[0]
+                converted = next((stem + ext for ext in (".pt", ".pth", ".ckpt") if os.path.exists(stem + ext)), None)
+                if converted is not None:
+                    sd = torch.load(converted, map_location="cpu", weights_only=True)
+                    net = ConvTdfNet.from_state_dict(sd.get("state_dict", sd) if isinstance(sd, dict) else sd, cfg.dim_f)
+                elif not self.allow_random_init:
+                    raise FileNotFoundError(f"{path}: no ONNX importer in this build and no converted state dict "
+                                            f"({stem}.pt); pass model_overrides[...]['net'] or allow_random_init=True")
+                else:
+                    torch.manual_seed(4321)
+                    net = ConvTdfNet(cfg.dim_f) if self.mdx_params.get("full_size_net", True) else TfcTdfNet(cfg.dim_f)
             net = net.to(self.torch_device).eval()
             inst.segment_size, inst.dim_t = seg, cfg.dim_t
             autocast = self.use_autocast

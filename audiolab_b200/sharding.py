@@ -144,8 +144,15 @@ def sharded_ola(chunk_waves_fn: Callable[[int, int], torch.Tensor], gather_fn: C
         waves = head if tail is None else torch.cat((head, tail), dim=0)
     else:
         waves = tail
+    timed = stats is not None and stats.get("time_wait") and torch.device(device).type == "cuda" and reqs
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     for req in reqs:
         req.wait()
+    if timed:
+        e1.record()
+        stats.setdefault("wait_events", []).append((e0, e1))
     parts = []
     if me.halo_in:
         parts.append(gather_fn(waves, me.c0, me.c1, me.p0, me.p0 + me.halo_in, halo_in, False))
