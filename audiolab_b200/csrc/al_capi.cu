@@ -484,12 +484,23 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
 int al_gemm_bf16(const al_gemm_args* a, void* stream) {
     if (!a || !a->A || !a->W) return fail(AL_E_ARG, "al_gemm_bf16: NULL argument");
     if (a->M == 0) return AL_OK;
-    if (a->epi != AL_GEMM_EPI_BF16 && a->epi != AL_GEMM_EPI_RESIDUAL) return fail(AL_E_ARG, "al_gemm_bf16: bad epi %d", a->epi);
+    if (a->epi != AL_GEMM_EPI_BF16 && a->epi != AL_GEMM_EPI_RESIDUAL && a->epi != AL_GEMM_EPI_GLU)
+        return fail(AL_E_ARG, "al_gemm_bf16: bad epi %d", a->epi);
     cudaError_t ce = cudaSuccess;
     const char* msg = al::launch_gemm_bf16(*a, (cudaStream_t)stream, &ce);
     if (!msg) return AL_OK;
     if (ce != cudaSuccess) return cuda_fail(ce, "al_gemm_bf16");
     return fail(AL_E_ARG, "al_gemm_bf16: %s", msg);
+}
+
+int al_band_norm(const float* x, int64_t ldx, const float* gamma, const int32_t* band_off, int n_bands, void* out, int64_t ldo,
+                 int64_t n_rows, float eps, void* stream) {
+    if (!x || !gamma || !band_off || !out) return fail(AL_E_ARG, "al_band_norm: NULL argument");
+    if (n_rows == 0) return AL_OK;
+    if (n_rows < 0 || n_bands <= 0 || n_bands > 1024 || ldx <= 0 || ldo <= 0) return fail(AL_E_ARG, "al_band_norm: bad sizes");
+    cudaError_t e = al::launch_band_norm(x, ldx, gamma, band_off, n_bands, out, ldo, n_rows, eps, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "al_band_norm");
+    return AL_OK;
 }
 
 int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,

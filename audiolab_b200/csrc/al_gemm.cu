@@ -18,6 +18,8 @@
 //              left behind: RMSNorm(x) W^T = diag(rowscale) x (gamma (.) W)^T, so the normalisation pass disappears
 //              (gamma is folded into W once on the host).  The output columns may be routed to up to 4 tensors
 //              (q / k / v / gates).
+//   EPI_GLU  : W's rows interleaved (a_i, b_i): out[m, i] = (acc_2i + bias_2i) * sigmoid(acc_2i+1 + bias_2i+1), fp32 -- the
+//              second Linear + GLU of the mask estimator, written straight into the mask tensor.
 //   EPI_RES  : x32 += acc + bias (fp32 residual stream, read and written in place through TMA), xb = bf16(x32) (the
 //              next GEMM's A operand), ss[m][n_tile][half] = partial sums of squares of the new row (the next rowscale).
 //
@@ -125,7 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
                 const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
-                if constexpr (EPI == EPI_RES) {
+                if (EPI == EPI_RES && g.accumulate != 0) {
                     // the fp32 residual tile this accumulator will be added to: into L2 now, so that the epilogue's
                     // small ring of TMA loads sees L2 latency, not HBM latency
 #pragma unroll
@@ -188,7 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
         unsigned char* ebuf_ptr = base_ptr + L::kEpiOff + ew * L::kEpiPerWarp;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 
-        if constexpr (EPI == EPI_BF16) {
+        if constexpr (EPI != EPI_RES) {
             constexpr int kWarpCols = BN / 2 >= 64 ? BN / 2 : 64;      // columns per warp, in 64-column steps
             const int wcol0 = half * kWarpCols;                         // first column of this warp inside the tile
             int it = 0;
@@ -200,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 const int row0 = m_blk * BM + q * 32;
                 const long long row = (long long)row0 + lane;
-                const long long grow = (long long)grp * g.M + row;      // row of the per-row side inputs
+                const long long grow = (long long)grp * g.side_gs + row * g.side_rs;   // row of the per-row side inputs
                 float rs = 1.f;
                 if (g.row_ss != nullptr && row < g.M) {
                     float ss = 0.f;
@@ -276,22 +278,40 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = make_float2(tanh_fast(v[j].x), tanh_fast(v[j].y));
                         }
+                        if constexpr (EPI == EPI_GLU) {
+                            // W's rows were interleaved on the host: column 2i = a_i, 2i + 1 = b_i; out_i = a_i sigmoid(b_i), fp32
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16(v[4 * j].x, v[4 * j].y);
-                            u.y = pack_bf16(v[4 * j + 1].x, v[4 * j + 1].y);
-                            u.z = pack_bf16(v[4 * j + 2].x, v[4 * j + 2].y);
-                            u.w = pack_bf16(v[4 * j + 3].x, v[4 * j + 3].y);
-                            const int chunk = h * 4 + j;                 // 16-byte chunk of the 128-byte row
-                            *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+                            for (int j = 0; j < 4; ++j) {
+                                float4 u;
+                                u.x = v[4 * j].x * sigmoid_fast(v[4 * j].y);
+                                u.y = v[4 * j + 1].x * sigmoid_fast(v[4 * j + 1].y);
+                                u.z = v[4 * j + 2].x * sigmoid_fast(v[4 * j + 2].y);
+                                u.w = v[4 * j + 3].x * sigmoid_fast(v[4 * j + 3].y);
+                                const int chunk = h * 4 + j;             // 16 outputs of this half = 4 chunks of the 128-byte row
+                                *reinterpret_cast<float4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 u;
+                                u.x = pack_bf16(v[4 * j].x, v[4 * j].y);
+                                u.y = pack_bf16(v[4 * j + 1].x, v[4 * j + 1].y);
+                                u.z = pack_bf16(v[4 * j + 2].x, v[4 * j + 2].y);
+                                u.w = pack_bf16(v[4 * j + 3].x, v[4 * j + 3].y);
+                                const int chunk = h * 4 + j;             // 16-byte chunk of the 128-byte row
+                                *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
+                            }
                         }
                     }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        const int oi = col0 / g.out_split;
-                        tma_store_3d(&tm.o[oi], ebuf, col0 - oi * g.out_split, row0, grp);
+                        if constexpr (EPI == EPI_GLU) {
+                            tma_store_3d(&tm.o[0], ebuf, col0 >> 1, row0, grp);
+                        } else {
+                            const int oi = col0 / g.out_split;
+                            tma_store_3d(&tm.o[oi], ebuf, col0 - oi * g.out_split, row0, grp);
+                        }
                         bulk_commit();
                     }
                 }
@@ -322,7 +342,8 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 mbar_arrive_expect_tx(res_bar(ew, slot), 4096u);
                 tma_load_3d(ebuf + (uint32_t)slot * 4096, &tm.o[0], res_bar(ew, slot), col0, row0, grp);
             };
-            if (lane == 0 && n_chunks > 0) issue_load(0);
+            const bool acc_in = g.accumulate != 0;               // 0: x32 = acc + bias (the stream starts here), no residual read
+            if (lane == 0 && n_chunks > 0 && acc_in) issue_load(0);
             float ss = 0.f;
             for (long long gc = 0; gc < n_chunks; ++gc) {
                 const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
@@ -340,10 +361,10 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int slot = (int)(gc & (kResSlots - 1));
                 if (lane == 0) {
                     bulk_wait_read<0>();                      // chunk gc-1's stores have read their buffers
-                    if (gc + 1 < n_chunks) issue_load(gc + 1);
+                    if (gc + 1 < n_chunks && acc_in) issue_load(gc + 1);
                 }
                 __syncwarp();
-                mbar_wait(res_bar(ew, slot), (uint32_t)(gc / kResSlots) & 1u);
+                if (acc_in) mbar_wait(res_bar(ew, slot), (uint32_t)(gc / kResSlots) & 1u);
                 tmem_wait_ld();
                 if (c == CH - 1) {
                     tc_fence_before();
@@ -356,7 +377,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4* p = reinterpret_cast<float4*>(rb + ((j ^ (lane & 7)) << 4));
-                    float4 x = *p;
+                    float4 x = acc_in ? *p : make_float4(0.f, 0.f, 0.f, 0.f);
                     x.x += __uint_as_float(r[4 * j]);
                     x.y += __uint_as_float(r[4 * j + 1]);
                     x.z += __uint_as_float(r[4 * j + 2]);
@@ -394,7 +415,8 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 if (c == CH - 1 && g.ss_out != nullptr) {
                     // the two warps of a lane quadrant each hold half of the slab's sum: [row][n_tile][half]
                     const long long row = (long long)row0 + lane;
-                    if (row < g.M) g.ss_out[(((long long)grp * g.M + row) * g.n_tiles + (col0 / BN)) * 2 + half] = ss;
+                    if (row < g.M)
+                        g.ss_out[(((long long)grp * g.side_gs + row * g.side_rs) * g.n_tiles + (col0 / BN)) * 2 + half] = ss;
                 }
             }
             if (lane == 0) bulk_wait<0>();
@@ -495,6 +517,9 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     g.rot_cols = c.rot_cols; g.act = c.act;
     g.ss_out = c.ss_out;
     g.max_ctas = c.max_ctas;
+    g.side_rs = c.side_row_stride > 0 ? c.side_row_stride : 1;
+    g.side_gs = c.side_row_stride > 0 ? c.side_group_stride : c.M;
+    g.accumulate = c.no_accumulate ? 0 : 1;
     if ((long long)g.m_tiles * g.n_tiles * g.groups > 0x7fffffffll) return "too many tiles";
     Tmaps tm;
     if (!make_map(&tm.a, c.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
@@ -520,6 +545,22 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
         g.out_split = c.N;
         if (BN == 256) *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
         else *cuda_err = launch_cfg<128, 4, EPI_RES>(tm, g, 4, stream);
+        return *cuda_err == cudaSuccess ? nullptr : "launch failed";
+    }
+    if (c.epi == EPI_GLU) {
+        if ((c.N & 15) != 0) return "GLU epilogue needs N to be a multiple of 16 (interleaved (a, b) rows)";
+        if (!c.out[0] || (reinterpret_cast<uintptr_t>(c.out[0]) & 15) != 0 || (c.ldo[0] & 3) != 0)
+            return "GLU epilogue needs a 16-byte aligned fp32 output";
+        const int out_cols = c.out_split > 0 ? c.out_split : c.N / 2;     // columns that exist in the output (<= N / 2)
+        if (out_cols > c.N / 2) return "GLU epilogue: out_split (valid output columns) exceeds N / 2";
+        if (!make_map(&tm.o[0], c.out[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_cols, c.M, c.groups, c.ldo[0], c.o_group_stride[0],
+                      32, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+            return "cuTensorMapEncodeTiled(glu out) failed";
+        tm.o[1] = tm.o[2] = tm.o[3] = tm.o[0];
+        g.out_split = c.N;
+        if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_GLU>(tm, g, 5, stream);
+        else if (BN == 128) *cuda_err = launch_cfg<128, 6, EPI_GLU>(tm, g, 6, stream);
+        else *cuda_err = launch_cfg<64, 8, EPI_GLU>(tm, g, 7, stream);
         return *cuda_err == cudaSuccess ? nullptr : "launch failed";
     }
     // EPI_BF16

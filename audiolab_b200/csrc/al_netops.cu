@@ -262,6 +262,40 @@ cudaError_t launch_resid_prepare(const float* x_in, const float* bias, const flo
     return cudaGetLastError();
 }
 
+// [emul-begin]
+// Per-band RMSNorm of the band-split input (upstream BandSplit: RMSNorm(d_j) in front of each band's Linear): one CTA per
+// row; the row is read once, each warp normalises whole bands (sum of squares over the band's d_j elements, lanes
+// strided), and the bf16 result is the A operand of the grouped band-split GEMM.
+__global__ void __launch_bounds__(256)
+band_norm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const int* __restrict__ band_off,
+                 int n_bands, __nv_bfloat16* __restrict__ out, long long ldo, float eps) {
+    const long long row = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const float* xr = x + row * ldx;
+    __nv_bfloat16* orow = out + row * ldo;
+    for (int j = warp; j < n_bands; j += n_warps) {
+        const int a = __ldg(band_off + j), b = __ldg(band_off + j + 1);
+        float ss = 0.f;
+        for (int i = a + lane; i < b; i += 32) {
+            const float v = xr[i];
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float inv = sqrtf((float)(b - a)) / fmaxf(sqrtf(ss), eps);
+        for (int i = a + lane; i < b; i += 32) orow[i] = __float2bfloat16_rn(xr[i] * inv * __ldg(gamma + i));
+    }
+}
+// [emul-end]
+
+cudaError_t launch_band_norm(const float* x, long long ldx, const float* gamma, const int* band_off, int n_bands, void* out,
+                             long long ldo, long long n_rows, float eps, cudaStream_t stream) {
+    band_norm_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(x, ldx, gamma, band_off, n_bands,
+                                                           reinterpret_cast<__nv_bfloat16*>(out), ldo, eps);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // x: [n] bf16, exact (erf) GELU in place -- upstream FeedForward's nn.GELU() between its two Linear layers
 // (SURVEY.md A.4).  erff costs ~30 issue slots per element, which makes the straightforward kernel
 // issue-bound at half the HBM rate (profiles/r01d).  A bf16 -> bf16 function has only 65536 inputs: the

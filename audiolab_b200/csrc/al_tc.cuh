@@ -226,5 +226,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return 1.0f - 2.0f * fast_rcp(1.0f + e);
 }
 
+__device__ __forceinline__ float sigmoid_fast(float x) { return fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f)); }
+
 }  // namespace tc
 }  // namespace al

@@ -122,7 +122,8 @@ class GemmArgs(_C.Structure):
         ("out_split", _C.c_int32),
         ("x32", _C.c_void_p), ("xb", _C.c_void_p),
         ("ldx", _C.c_int64), ("x_group_stride", _C.c_int64), ("ldxb", _C.c_int64), ("xb_group_stride", _C.c_int64),
-        ("ss_out", _C.c_void_p), ("max_ctas", _C.c_int32),
+        ("ss_out", _C.c_void_p), ("max_ctas", _C.c_int32), ("no_accumulate", _C.c_int32),
+        ("side_row_stride", _C.c_int64), ("side_group_stride", _C.c_int64),
     ]
 
 
@@ -194,8 +195,58 @@ def resid_slab(n: int) -> int:
     return 128 if n % 256 == 0 else 64
 
 
+def gemm_bf16_glu(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+                  max_ctas: int = 0) -> None:
+    """out[..., m, i] = (a @ w^T + bias)[2i] * sigmoid((a @ w^T + bias)[2i + 1]) in fp32 (al_gemm_bf16, EPI_GLU): w's rows
+    (and bias) are ALREADY interleaved (a_0, b_0, a_1, b_1, ...), see `interleave_glu`.  a [M, K] / [G, M, K] bf16,
+    w [N, K] / [G, N, K] bf16, out fp32 [M, N / 2] / [G, M, N / 2] (may be a strided view into the mask tensor)."""
+    _rows2d(a, "a", torch.bfloat16)
+    _rows2d(w, "w", torch.bfloat16)
+    _rows2d(out, "out", torch.float32)
+    g, m, k, lda, ags = _geom(a)
+    gw, n, kw, ldw, wgs = _geom(w)
+    go, mo, no, ldo, ogs = _geom(out)
+    if gw != g or kw != k or (go, mo) != (g, m) or n % 16 != 0 or not (n // 2 - 8 < no <= n // 2):
+        raise ValueError("a / w / out disagree on groups, M, K, or N is not the output width rounded up to a multiple of 16")
+    args = GemmArgs()
+    args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
+    args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
+    args.epi = 2
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != g * n or not bias.is_contiguous():
+            raise ValueError("bias must be contiguous fp32 [groups, N] (interleaved like w's rows)")
+        args.bias = bias.data_ptr()
+    args.out[0], args.ldo[0], args.o_group_stride[0] = out.data_ptr(), ldo, ogs
+    args.out_split = no                 # valid output columns (w may carry zero rows up to a multiple of 16)
+    args.max_ctas = int(max_ctas)
+    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16(glu)")
+
+
+def interleave_glu(t: torch.Tensor) -> torch.Tensor:
+    """Rows (dim -2 of a weight, or the last dim of a bias) [a_0 .. a_{h-1}, b_0 .. b_{h-1}] -> [a_0, b_0, a_1, b_1, ...]:
+    nn.GLU's two halves side by side, as the GLU epilogue of the GEMM wants them."""
+    if t.dim() == 1:
+        h = t.shape[0] // 2
+        return torch.stack((t[:h], t[h:]), dim=1).reshape(-1).contiguous()
+    h = t.shape[-2] // 2
+    return torch.stack((t[..., :h, :], t[..., h:, :]), dim=-2).reshape(*t.shape[:-2], 2 * h, t.shape[-1]).contiguous()
+
+
+def band_norm(x: torch.Tensor, gamma: torch.Tensor, band_off: torch.Tensor, out: torch.Tensor, eps: float = 1e-12) -> None:
+    """Per-band RMSNorm (upstream BandSplit): out[:, off_j:off_{j+1}] = bf16(normalize(x[:, off_j:off_{j+1}]) * sqrt(d_j) *
+    gamma[off_j:off_{j+1}]).  x fp32 [rows, >= off_last] (row stride free), out bf16 likewise, band_off int32 device."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a CUDA fp32 [rows, cols] tensor with unit column stride")
+    if out.dtype != torch.bfloat16 or out.dim() != 2 or out.stride(1) != 1 or out.shape[0] != x.shape[0]:
+        raise ValueError("out must be bf16 [rows, cols] with unit column stride")
+    if band_off.dtype != torch.int32 or not band_off.is_contiguous() or gamma.dtype != torch.float32 or not gamma.is_contiguous():
+        raise ValueError("band_off must be contiguous int32, gamma contiguous fp32")
+    _lib.check(_lib.lib().al_band_norm(x.data_ptr(), x.stride(0), gamma.data_ptr(), band_off.data_ptr(), band_off.numel() - 1,
+                                       out.data_ptr(), out.stride(0), x.shape[0], float(eps), _stream()), "al_band_norm")
+
+
 def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss_out: torch.Tensor, *,
-                       bias: Optional[torch.Tensor] = None, max_ctas: int = 0) -> None:
+                       bias: Optional[torch.Tensor] = None, max_ctas: int = 0, accumulate: bool = True) -> None:
     """x32 += a @ w^T + bias (fp32, in place); xb = bf16(x32); ss_out[m, j] = sum of x32[m, S j : S (j+1)]^2 with
     S = resid_slab(N)."""
     _rows2d(a, "a", torch.bfloat16)
@@ -210,7 +261,16 @@ def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: 
     gb, mb, nb, ldxb, xbgs = _geom(xb)
     if (gx, mx, nx) != (g, m, n) or (gb, mb, nb) != (g, m, n):
         raise ValueError("x32 / xb must be [groups, M, N]")
-    if ss_out.dtype != torch.float32 or not ss_out.is_contiguous() or ss_out.numel() != g * m * (n // resid_slab(n)):
+    parts = n // resid_slab(n)
+    side_rs = side_gs = 0
+    if ss_out.dtype != torch.float32:
+        raise ValueError("ss_out must be fp32")
+    if ss_out.dim() == 3:
+        # [groups, M, parts] view into a token-ordered array (band-grouped calls): strides in units of `parts`
+        if tuple(ss_out.shape) != (g, m, parts) or ss_out.stride(2) != 1 or ss_out.stride(0) % parts or ss_out.stride(1) % parts:
+            raise ValueError("ss_out view must be [groups, M, parts] with strides that are multiples of parts")
+        side_gs, side_rs = ss_out.stride(0) // parts, ss_out.stride(1) // parts
+    elif not ss_out.is_contiguous() or ss_out.numel() != g * m * parts:
         raise ValueError("ss_out must be contiguous fp32 [groups * M, N / resid_slab(N)]")
     args = GemmArgs()
     args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
@@ -224,6 +284,8 @@ def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: 
         x32.data_ptr(), xb.data_ptr(), ldx, xgs, ldxb, xbgs)
     args.ss_out = ss_out.data_ptr()
     args.max_ctas = int(max_ctas)
+    args.no_accumulate = 0 if accumulate else 1
+    args.side_row_stride, args.side_group_stride = side_rs, side_gs
     _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16(residual)")
 
 

@@ -27,6 +27,7 @@ from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
 _BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "1") != "0"   # band-axis attention kernel inside the tc path (default)
+_GROUPED = os.environ.get("AUDIOLAB_B200_GROUPED", "1") != "0"   # band split / mask estimator as grouped tcgen05 GEMMs
 _TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 
 
@@ -384,30 +385,150 @@ class RoformerMaskNet(nn.Module):
         if isinstance(tr.norm, RMSNorm):
             netops.resid_prepare(x32, x32, xb, ss, gamma=tr.norm.gamma.detach().float())
 
+    # ---- band split / mask estimator as grouped GEMMs (BS-RoFormer; bands of equal width form one grouped call) ----------
+    def _band_classes(self):
+        """[(f0, f1, d, off)]: maximal runs of consecutive bands with the same input width d, and the column offset of the
+        run in the 'b t (f s c)' feature row."""
+        dims = list(self.band_split.dim_inputs)
+        out, off, f0 = [], 0, 0
+        while f0 < len(dims):
+            f1 = f0
+            while f1 < len(dims) and dims[f1] == dims[f0]:
+                f1 += 1
+            out.append((f0, f1, dims[f0], off))
+            off += (f1 - f0) * dims[f0]
+            f0 = f1
+        return out
+
+    def _grouped_supported(self) -> bool:
+        c = self.cfg
+        if c.kind == "mel" or c.mask_estimator_depth != 2 or not self._tc_supported():
+            return False
+        for f0, f1, d, off in self._band_classes():
+            # TMA: 16-byte aligned bases and group strides; a lone band may be padded up to a multiple of 8 columns
+            if off % 8 != 0 or d % 4 != 0 or (f1 - f0 > 1 and d % 8 != 0):
+                return False
+        return True
+
+    def _grouped_pack(self):
+        key = ("grouped",)
+        params = list(self.band_split.parameters()) + list(self.mask_estimators.parameters())
+        ver = tuple(p._version for p in params) + (str(params[0].device),)
+        hit = self._bf16_cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        from .. import netops
+        dt, dev = self._fused_dtype, params[0].device
+        classes = self._band_classes()
+        total = sum((f1 - f0) * d for f0, f1, d, _ in classes)
+        with torch.no_grad():
+            offs = [0]
+            for d in self.band_split.dim_inputs:
+                offs.append(offs[-1] + d)
+            pack = {
+                "total": total, "ld": (total + 7) // 8 * 8 + 8,          # A rows: zero padding behind the last band
+                "band_off": torch.tensor(offs, dtype=torch.int32, device=dev),
+                "gamma": torch.cat([f[0].gamma.detach().float() for f in self.band_split.to_features]).contiguous(),
+                "split": [], "est": [],
+            }
+            for f0, f1, d, off in classes:
+                k = (d + 7) // 8 * 8
+                w = torch.zeros((f1 - f0, self.cfg.dim, k), device=dev)
+                for j in range(f0, f1):
+                    w[j - f0, :, :d] = self.band_split.to_features[j][1].weight.detach().float()
+                b = torch.stack([self.band_split.to_features[j][1].bias.detach().float() for j in range(f0, f1)])
+                pack["split"].append((f0, f1, k, off, w.to(dt).contiguous(), b.contiguous()))
+            for est in self.mask_estimators:
+                lin1 = [m[0][0] for m in est.to_freqs]
+                lin2 = [m[0][2] for m in est.to_freqs]
+                w1 = torch.stack([l.weight.detach().float() for l in lin1]).to(dt).contiguous()        # [F, hidden, dim]
+                b1 = torch.stack([l.bias.detach().float() for l in lin1]).contiguous()
+                second = []
+                for f0, f1, d, off in classes:
+                    n = (2 * d + 15) // 16 * 16
+                    w2 = torch.zeros((f1 - f0, n, w1.shape[1]), device=dev)
+                    b2 = torch.zeros((f1 - f0, n), device=dev)
+                    for j in range(f0, f1):
+                        w2[j - f0, : 2 * d] = netops.interleave_glu(lin2[j].weight.detach().float())
+                        b2[j - f0, : 2 * d] = netops.interleave_glu(lin2[j].bias.detach().float())
+                    second.append((f0, f1, d, off, w2.to(dt).contiguous(), b2.contiguous()))
+                pack["est"].append((w1, b1, second))
+        self._bf16_cache[key] = (ver, pack)
+        return pack
+
+    def _band_split_tc(self, feats: torch.Tensor, st) -> None:
+        """feats fp32 [b*t, (f s c)] -> the residual stream (x32, xb, ss) of `st`: per-band RMSNorm (al_band_norm), then one
+        grouped GEMM per run of equal-width bands whose residual epilogue STARTS the fp32 stream (no read of x32)."""
+        from .. import netops
+        pk = self._grouped_pack()
+        x32, xb, ss = st[0], st[1], st[2]
+        bt = feats.shape[0]
+        nb, d = len(self.band_split.dim_inputs), x32.shape[1]
+        key = ("xn", bt, str(feats.device))
+        xn = self._rot_cache.get(key)
+        if xn is None:
+            xn = torch.zeros((bt, pk["ld"]), device=feats.device, dtype=self._fused_dtype)   # padding columns stay zero
+            self._rot_cache[key] = xn
+        netops.band_norm(feats, pk["gamma"], pk["band_off"], xn)
+        x3, xb3, ss3 = x32.view(bt, nb, d), xb.view(bt, nb, d), ss.view(bt, nb, -1)
+        for f0, f1, k, off, w, b in pk["split"]:
+            a = xn.as_strided((f1 - f0, bt, k), (k if f1 - f0 > 1 else 0, xn.stride(0), 1), off)
+            netops.gemm_bf16_residual(a, w, x3[:, f0:f1].transpose(0, 1), xb3[:, f0:f1].transpose(0, 1),
+                                      ss3[:, f0:f1].transpose(0, 1), bias=b, accumulate=False)
+
+    def _mask_estimate_tc(self, xb: torch.Tensor, b: int, t: int) -> torch.Tensor:
+        """xb bf16 [b*t*F, dim] (final-normed) -> masks fp32 [b, n, t, (f s c)]: per stem one grouped GEMM for the first
+        Linear + tanh of all bands, then one grouped GEMM per run of equal-width bands whose epilogue applies the GLU and
+        writes fp32 straight into the mask tensor."""
+        from .. import netops
+        pk = self._grouped_pack()
+        bt = b * t
+        nb, d = len(self.band_split.dim_inputs), xb.shape[1]
+        a1 = xb.view(bt, nb, d).transpose(0, 1)                                   # [F, bt, dim], strided
+        outs = []
+        for w1, b1, second in pk["est"]:
+            hid = torch.empty((nb, bt, w1.shape[1]), device=xb.device, dtype=self._fused_dtype)
+            netops.gemm_bf16(a1, w1, hid, bias=b1, act="tanh")
+            m = torch.empty((bt, pk["total"]), device=xb.device, dtype=torch.float32)
+            for f0, f1, dd, off, w2, b2 in second:
+                out = m.as_strided((f1 - f0, bt, dd), (dd if f1 - f0 > 1 else 0, m.stride(0), 1), off)
+                netops.gemm_bf16_glu(hid[f0:f1], w2, out, bias=b2)
+            outs.append(m.view(b, t, -1))
+        return torch.stack(outs, dim=1) if len(outs) > 1 else outs[0].unsqueeze(1)
+
+    def _tc_state(self, m: int, dev):
+        from .. import netops
+        c = self.cfg
+        d, inner = c.dim, c.heads * c.dim_head
+        dt = self._fused_dtype
+        x32 = torch.empty((m, d), device=dev, dtype=torch.float32)
+        xb = torch.empty((m, d), device=dev, dtype=dt)
+        ss = torch.empty((m, d // netops.resid_slab(d)), device=dev, dtype=torch.float32)
+        q, k, v = (torch.empty((m, inner), device=dev, dtype=dt) for _ in range(3))
+        gates = torch.empty((m, 16), device=dev, dtype=dt)
+        hid = torch.empty((m, int(d * c.ff_mult)), device=dev, dtype=dt)
+        return (x32, xb, ss, q, k, v, gates, hid)
+
+    def _layers_tc(self, st, geom) -> torch.Tensor:
+        """All axial transformer pairs (+ BS-RoFormer's final norm) on a prepared state; returns the bf16 shadow."""
+        from .. import netops
+        for time_transformer, freq_transformer in self.layers:
+            self._transformer_tc(st, time_transformer, geom, True)
+            self._transformer_tc(st, freq_transformer, geom, False)
+        x32, xb, ss = st[0], st[1], st[2]
+        if self.cfg.kind != "mel":
+            netops.resid_prepare(x32, x32, xb, ss, gamma=self.final_norm.gamma.detach().float())
+        return xb
+
     def _axial_tc(self, x):
         """bf16-operand twin of `_axial` (+ BS-RoFormer's final norm) on the tcgen05 GEMM.  The residual stream is fp32
         (x32) with a bf16 shadow (xb) as the A operand of the next GEMM; every row-wise operator between two
-        contractions except the attention gate lives in a GEMM epilogue."""
+        contractions except the time-axis attention gate lives in a GEMM epilogue."""
         from .. import netops
         b, t, f, d = x.shape
-        m = b * t * f
-        dev = x.device
-        c = self.cfg
-        inner = c.heads * c.dim_head
-        x32 = torch.empty((m, d), device=dev, dtype=torch.float32)
-        xb = torch.empty((m, d), device=dev, dtype=self._fused_dtype)
-        ss = torch.empty((m, d // netops.resid_slab(d)), device=dev, dtype=torch.float32)
-        netops.resid_prepare(x.reshape(m, d).float().contiguous(), x32, xb, ss)
-        q, k, v = (torch.empty((m, inner), device=dev, dtype=self._fused_dtype) for _ in range(3))
-        gates = torch.empty((m, 16), device=dev, dtype=self._fused_dtype)
-        hid = torch.empty((m, int(d * c.ff_mult)), device=dev, dtype=self._fused_dtype)
-        st = (x32, xb, ss, q, k, v, gates, hid)
-        for time_transformer, freq_transformer in self.layers:
-            self._transformer_tc(st, time_transformer, (b, t, f), True)
-            self._transformer_tc(st, freq_transformer, (b, t, f), False)
-        if c.kind != "mel":
-            netops.resid_prepare(x32, x32, xb, ss, gamma=self.final_norm.gamma.detach().float())
-        return xb.view(b, t, f, d)
+        st = self._tc_state(b * t * f, x.device)
+        netops.resid_prepare(x.reshape(b * t * f, d).float().contiguous(), st[0], st[1], st[2])
+        return self._layers_tc(st, (b, t, f)).view(b, t, f, d)
 
     def set_compute_dtype(self, dtype: torch.dtype) -> "RoformerMaskNet":
         self.compute_dtype = dtype
@@ -427,6 +548,15 @@ class RoformerMaskNet(nn.Module):
         b, t, f, s = spec.shape
         feats = torch.view_as_real(spec).reshape(b, t, f * s * 2)          # 'b t (f s c)', zero-copy
         ac = self.compute_dtype != torch.float32
+        on_dev = spec.is_cuda or self._fused_dtype == torch.float32        # (fp32 "fused dtype": the CPU host-logic tests)
+        if ac and on_dev and self.compute_dtype == torch.bfloat16 and _GROUPED and self._grouped_supported():
+            # everything on the tcgen05 GEMM: band split -> fp32 residual stream -> transformers -> mask estimator (fp32 out)
+            nb = len(self.band_split.dim_inputs)
+            st = self._tc_state(b * t * nb, spec.device)
+            self._band_split_tc(feats.reshape(b * t, -1), st)
+            xb = self._layers_tc(st, (b, t, nb))
+            m = self._mask_estimate_tc(xb, b, t)                            # fp32 [b, n, t, (f s c)]
+            return torch.view_as_complex(m.reshape(b, m.shape[1], t, f, s, 2))
         with torch.autocast("cuda", dtype=self.compute_dtype, enabled=ac):
             if c.kind == "mel":
                 rows = torch.view_as_real(spec).reshape(b, t, f * s, 2)

@@ -221,10 +221,20 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
  *   xb[m, n] = bf16(x32[m, n]),  ss_out[m * (N / S) + n / S] = sum over that S-column slab of x32[m, n]^2, with the
  *   slab width S = 128 if N % 256 == 0, else 64.
  *
+ * epi = AL_GEMM_EPI_GLU (N % 16 == 0):  the caller interleaves W's rows as (a_0, b_0, a_1, b_1, ...) (and bias likewise);
+ *   out[0][m, i] = (acc[m, 2i] + bias[2i]) * sigmoid(acc[m, 2i+1] + bias[2i+1]) in FP32, N / 2 columns (row stride ldo[0] in
+ *   floats; out_split > 0 = number of output columns that exist, when W carries zero rows up to the multiple of 16) --
+ *   upstream MaskEstimator's last Linear + nn.GLU, written straight into the mask tensor.
+ *
  * K, lda, ldw, ldo, ldxb multiples of 8, ldx of 4, N of 8; all pointers 16-byte aligned.  max_ctas = 0 uses every SM.
+ *
+ * al_band_norm -- upstream BandSplit's per-band RMSNorm: for each band j, out[m, off_j : off_{j+1}] =
+ *   bf16(F.normalize(x[m, off_j : off_{j+1}]) * sqrt(off_{j+1} - off_j) * gamma[off_j : off_{j+1}]); x fp32 (row stride ldx),
+ *   out bf16 (row stride ldo), band_off DEVICE int32 [n_bands + 1].  The A operand of the grouped band-split GEMM.
  */
 #define AL_GEMM_EPI_BF16 0
 #define AL_GEMM_EPI_RESIDUAL 1
+#define AL_GEMM_EPI_GLU 2
 #define AL_GEMM_ACT_NONE 0
 #define AL_GEMM_ACT_GELU 1
 #define AL_GEMM_ACT_TANH 2
@@ -251,9 +261,14 @@ typedef struct al_gemm_args {
     int64_t ldx, x_group_stride, ldxb, xb_group_stride;
     float* ss_out;
     int32_t max_ctas;
+    int32_t no_accumulate;        /* EPI_RESIDUAL: 1 = x32 = acc + bias (start of the stream, x32 is not read) */
+    int64_t side_row_stride;      /* 0 = default (row_ss / ss_out indexed by group * M + row); else the row index of the per-row */
+    int64_t side_group_stride;    /*   side arrays is group * side_group_stride + row * side_row_stride (band-grouped calls)  */
 } al_gemm_args;
 
 int al_gemm_bf16(const al_gemm_args* args, void* stream);
+int al_band_norm(const float* x, int64_t ldx, const float* gamma, const int32_t* band_off, int n_bands, void* out, int64_t ldo,
+                 int64_t n_rows, float eps, void* stream);
 
 /*
  * al_resid_prepare -- start (or re-normalise) the fp32 residual stream the residual epilogue of al_gemm_bf16 keeps:

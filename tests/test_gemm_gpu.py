@@ -167,3 +167,94 @@ def test_resid_prepare():
         assert torch.equal(xb, x32.bfloat16())
         ss_ref = torch.stack((x32[:, :256].square().sum(-1), x32[:, 256:].square().sum(-1)), dim=-1)
         assert torch.allclose(ss, ss_ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n_out,groups", [(8, 3), (48, 2), (96, 1), (516, 1), (512, 1)])
+def test_gemm_glu_epilogue(n_out, groups):
+    """Second Linear + GLU of the mask estimator: interleaved (a, b) rows, fp32 output written into a strided view."""
+    netops = _cuda()
+    m, k = 777, 2048
+    n_pad = (2 * n_out + 15) // 16 * 16
+    a = _rand((groups, m, k), 30).bfloat16()
+    w_full = _rand((groups, 2 * n_out, k), 31, k ** -0.5)
+    bias_full = _rand((groups, 2 * n_out), 32)
+    w = torch.zeros((groups, n_pad, k), device="cuda")
+    b = torch.zeros((groups, n_pad), device="cuda")
+    for g in range(groups):
+        w[g, : 2 * n_out] = netops.interleave_glu(w_full[g])
+        b[g, : 2 * n_out] = netops.interleave_glu(bias_full[g])
+    w = w.bfloat16()
+    total = groups * n_out + 12
+    buf = torch.full((m, total), float("nan"), device="cuda")
+    out = buf.as_strided((groups, m, n_out), (n_out if groups > 1 else 0, total, 1), 4)
+    netops.gemm_bf16_glu(a, w, out, bias=b)
+    torch.cuda.synchronize()
+    y = torch.einsum("gmk,gnk->gmn", a.float(), w_full.bfloat16().float()) + bias_full[:, None, :]
+    ref = y[..., :n_out] * torch.sigmoid(y[..., n_out:])
+    got = buf[:, 4: 4 + groups * n_out].reshape(m, groups, n_out).transpose(0, 1)
+    assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max())), float((got - ref).abs().max())
+    assert torch.isnan(buf[:, :4]).all() and torch.isnan(buf[:, 4 + groups * n_out:]).all(), "wrote outside its columns"
+
+
+def test_band_norm_and_grouped_stream_start():
+    """al_band_norm + the grouped band-split GEMM whose residual epilogue starts the fp32 stream (no read of x32), on the
+    strided per-band views of the token-ordered buffers."""
+    netops = _cuda()
+    bt, dim = 555, 512
+    widths = [8, 8, 8, 16, 16, 516]
+    offs = [0]
+    for d in widths:
+        offs.append(offs[-1] + d)
+    total = offs[-1]
+    x = _rand((bt, total), 40, 2.0)
+    gamma = _rand((total,), 41).abs() + 0.5
+    ld = (total + 7) // 8 * 8 + 8
+    xn = torch.zeros((bt, ld), device="cuda", dtype=torch.bfloat16)
+    netops.band_norm(x, gamma, torch.tensor(offs, dtype=torch.int32, device="cuda"), xn)
+    torch.cuda.synchronize()
+    ref_n = torch.zeros((bt, total), device="cuda")
+    for a, b in zip(offs[:-1], offs[1:]):
+        ref_n[:, a:b] = torch.nn.functional.normalize(x[:, a:b], dim=-1) * math.sqrt(b - a) * gamma[a:b]
+    _close_bf16(xn[:, :total], ref_n, "band_norm")
+    assert float(xn[:, total:].abs().max()) == 0.0
+    nb = len(widths)
+    parts = dim // netops.resid_slab(dim)
+    x32 = torch.full((bt, nb, dim), float("nan"), device="cuda")
+    xb = torch.empty((bt, nb, dim), device="cuda", dtype=torch.bfloat16)
+    ss = torch.empty((bt, nb, parts), device="cuda")
+    ref = torch.empty((bt, nb, dim), device="cuda")
+    for f0, f1 in ((0, 3), (3, 5), (5, 6)):
+        d = widths[f0]
+        k = (d + 7) // 8 * 8
+        w = torch.zeros((f1 - f0, dim, k), device="cuda")
+        w[:, :, :d] = _rand((f1 - f0, dim, d), 42 + f0, d ** -0.5)
+        w = w.bfloat16()
+        bias = _rand((f1 - f0, dim), 50 + f0)
+        a = xn.as_strided((f1 - f0, bt, k), (k if f1 - f0 > 1 else 0, ld, 1), offs[f0])
+        netops.gemm_bf16_residual(a, w, x32[:, f0:f1].transpose(0, 1), xb[:, f0:f1].transpose(0, 1),
+                                  ss[:, f0:f1].transpose(0, 1), bias=bias, accumulate=False)
+        ref[:, f0:f1] = (torch.einsum("gmk,gnk->mgn", a.float(), w.float()) + bias[None])
+    torch.cuda.synchronize()
+    assert torch.allclose(x32, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max())), float((x32 - ref).abs().max())
+    assert torch.equal(xb, x32.bfloat16())
+    assert torch.allclose(ss, x32.view(bt, nb, parts, -1).square().sum(-1), rtol=1e-5)
+
+
+def test_roformer_mask_all_tc_path_vs_fp32_modules():
+    """mask() on the all-tcgen05 path (band split -> transformers -> mask estimator) against the fp32 module path of the same
+    network: bf16 operand rounding only (relative L2 error of the mask < 1.5 %)."""
+    _cuda()
+    from audiolab_b200.configs import RoformerConfig
+    from audiolab_b200.nets.roformer import RoformerMaskNet
+    torch.manual_seed(4321)
+    cfg = RoformerConfig(dim=128, depth=2, heads=4, dim_head=64, chunk_size=441 * 40)
+    net = RoformerMaskNet(cfg).cuda().eval()
+    assert net._grouped_supported()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    spec = torch.view_as_complex(torch.randn((3, 41, 1025, 2, 2), generator=g)).cuda()
+    ref = net.set_compute_dtype(torch.float32).mask(spec)
+    got = net.set_compute_dtype(torch.bfloat16).mask(spec)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    rel = float((torch.view_as_real(got) - torch.view_as_real(ref)).norm() / torch.view_as_real(ref).norm())
+    assert rel < 1.5e-2, rel

@@ -321,6 +321,9 @@ def test_tc_axial_host_logic_matches_module_path(kind, monkeypatch):
     monkeypatch.setattr(netops, "gemm_bf16_residual", ref_gemm_bf16_residual)
     monkeypatch.setattr(netops, "resid_prepare", ref_resid_prepare)
     monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    monkeypatch.setattr(netops, "band_attention",
+                        lambda q, k, v, n_seq, seq_len, heads, dh, gates=None, cos_sin=None:
+                        ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates))
     net._fused_dtype = torch.float32
     b, t, f = 2, 13, len(net.band_split.dim_inputs)
     x = torch.randn(b, t, f, cfg.dim)
@@ -329,4 +332,79 @@ def test_tc_axial_host_logic_matches_module_path(kind, monkeypatch):
         if kind != "mel":
             ref = net.final_norm(ref)
         got = net._axial_tc(x.clone())
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def ref_band_norm(x, gamma, band_off, out, eps=1e-12):
+    offs = band_off.tolist()
+    for a, b in zip(offs[:-1], offs[1:]):
+        seg = x[:, a:b]
+        out[:, a:b] = (F.normalize(seg, dim=-1, eps=eps) * ((b - a) ** 0.5) * gamma[a:b]).to(out.dtype)
+
+
+def ref_gemm_bf16_glu(a, w, out, *, bias=None, max_ctas=0):
+    y = torch.einsum("gmk,gnk->gmn", a.float(), w.float()) if a.dim() == 3 else a.float() @ w.float().t()
+    if bias is not None:
+        y = y + (bias[:, None, :] if a.dim() == 3 else bias)
+    z = y[..., 0::2] * torch.sigmoid(y[..., 1::2])
+    out.copy_(z[..., : out.shape[-1]])
+
+
+def ref_gemm_any(a, w, outs, **kw):
+    if a.dim() == 3:
+        bias = kw.pop("bias", None)
+        for g in range(a.shape[0]):
+            ref_gemm_bf16(a[g], w[g], [o[g] for o in ([outs] if isinstance(outs, torch.Tensor) else outs)],
+                          bias=None if bias is None else bias[g], **kw)
+    else:
+        ref_gemm_bf16(a, w, outs, **kw)
+
+
+def ref_gemm_residual_any(a, w, x32, xb, ss_out, *, bias=None, max_ctas=0, accumulate=True):
+    import audiolab_b200.netops as netops
+    if a.dim() == 2:
+        a, w, x32, xb, ss_out = a[None], w[None], x32[None], xb[None], ss_out.view(1, x32.shape[0], -1)
+        bias = None if bias is None else bias[None]
+    slab = netops.resid_slab(x32.shape[-1])
+    for g in range(a.shape[0]):
+        y = a[g].float() @ w[g].float().t()
+        if accumulate:
+            y = y + x32[g]
+        if bias is not None:
+            y = y + bias[g]
+        x32[g].copy_(y)
+        xb[g].copy_(y.to(xb.dtype))
+        ss_out[g].copy_(y.view(y.shape[0], -1, slab).square().sum(-1))
+
+
+def test_tc_grouped_band_split_and_mask_estimator_host_logic(monkeypatch):
+    """The all-tcgen05 `mask()` path of BS-RoFormer: per-band RMSNorm kernel + grouped band-split GEMMs that start the fp32
+    stream, grouped mask-estimator GEMMs with the GLU epilogue writing into the mask tensor (interleaved / zero-padded
+    weights, strided views per run of equal-width bands) -- against the upstream-shaped module path."""
+    import audiolab_b200.netops as netops
+    torch.manual_seed(0)
+    # band widths 2,2,2,4,4,5 (the lone 5-wide band exercises the K / N padding, like the 129-bin band of the real model)
+    cfg = RoformerConfig(dim=128, depth=1, heads=4, dim_head=64, chunk_size=441 * 12, stft_n_fft=36,
+                         freqs_per_bands=(2, 2, 2, 4, 4, 5), num_stems=2)
+    net = RoformerMaskNet(cfg).eval()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    assert net._grouped_supported()
+    monkeypatch.setattr(netops, "gemm_bf16", ref_gemm_any)
+    monkeypatch.setattr(netops, "gemm_bf16_residual", ref_gemm_residual_any)
+    monkeypatch.setattr(netops, "gemm_bf16_glu", ref_gemm_bf16_glu)
+    monkeypatch.setattr(netops, "band_norm", ref_band_norm)
+    monkeypatch.setattr(netops, "resid_prepare", ref_resid_prepare)
+    monkeypatch.setattr(netops, "gate_sigmoid_", ref_gate_)
+    monkeypatch.setattr(netops, "band_attention",
+                        lambda q, k, v, n_seq, seq_len, heads, dh, gates=None, cos_sin=None:
+                        ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates))
+    b, t, f, s = 2, 7, 19, 2
+    spec = torch.randn(b, t, f, s, dtype=torch.complex64)
+    ref = net.mask(spec.clone())                                    # module path (compute dtype fp32)
+    net._fused_dtype = torch.float32
+    net.set_compute_dtype(torch.bfloat16)                           # selects the tc path; the stand-ins compute in fp32
+    got = net.mask(spec.clone())
+    assert got.shape == ref.shape == (b, 2, t, f, s)
     assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
