@@ -190,7 +190,11 @@ class Separator:
                                             f"({stem}.pt); pass model_overrides[...]['net'] or allow_random_init=True")
                 else:
                     torch.manual_seed(4321)
-                    net = ConvTdfNet(cfg.dim_f) if self.mdx_params.get("full_size_net", True) else TfcTdfNet(cfg.dim_f)
+                    full = self.mdx_params.get("full_size_net", True)
+                    if full and cfg.dim_t % 32 != 0:
+                        raise ValueError(f"segment_size {cfg.dim_t}: the released (L = 11) TFC-TDF net halves the time axis 5 times; "
+                                         "use a multiple of 32 (default 256), or mdx_params['full_size_net'] = False")
+                    net = ConvTdfNet(cfg.dim_f) if full else TfcTdfNet(cfg.dim_f)
             net = net.to(self.torch_device).eval()
             inst.segment_size, inst.dim_t = seg, cfg.dim_t
             autocast = self.use_autocast

@@ -747,7 +747,9 @@ def run_ours(args) -> None:
                          "note": ("linear layers: al_gemm_bf16 (hand-written tcgen05 / TMA / TMEM GEMM, RMSNorm + rotary + GELU "
                                   "+ bias + fp32 residual fused into the epilogues); attention: "
                                   + ("al_band_attention (band axis) + cuDNN SDPA (time axis)" if rof._BAND_ATTN_TC else "cuDNN SDPA")
-                                  + "; band split / mask estimator under bf16 autocast") if tc else
+                                  + ("; band split / mask estimator: grouped al_gemm_bf16 (GLU epilogue, fp32 mask)"
+                                     if rof._GROUPED and inst.demixer.net._grouped_supported() else
+                                     "; band split / mask estimator under bf16 autocast")) if tc else
                                  "dense layers via cuBLAS / cuDNN SDPA (AUDIOLAB_B200_TC_GEMM=0 comparison path)"},
         }
         if shard_info is not None:
