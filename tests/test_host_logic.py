@@ -252,3 +252,27 @@ def test_mdx_secondary_stem_by_spectral_inversion_host_logic(monkeypatch):
     assert float(d.invert_stem(mix, mix).abs().max()) <= 1e-5
     back = d.invert_stem(mix, torch.zeros_like(mix))
     assert float((back[:, 1024:-1024] - mix[:, 1024:-1024]).abs().max()) <= 1e-4
+
+
+def test_gemm_args_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of `al_gemm_args` (netops.GemmArgs) against the C header, field by field (gcc, no GPU)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from audiolab_b200.netops import GemmArgs
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    fields = [f[0] for f in GemmArgs._fields_]
+    src = tmp_path / "layout.c"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{root}/include/audiolab_b200.h"', 'int main(void) {',
+             '  printf("%zu\\n", sizeof(al_gemm_args));']
+    lines += [f'  printf("%zu\\n", offsetof(al_gemm_args, {f}));' for f in fields]
+    lines += ['  return 0; }']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(GemmArgs)
+    assert out[1:] == [getattr(GemmArgs, f).offset for f in fields]
