@@ -46,6 +46,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// F16 = the q / k / v / o / gates tensors are IEEE half instead of bfloat16 (the fp16-operand mode of the network):
+// the same kernel with mma.sync ... f16.f16 and half conversions.  The host emulation runs the bfloat16 form only.
+#ifndef AL_CPU_EMUL
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float f16_bits_to_f32(unsigned short v) {
+    float r;
+    asm("{.reg .f16 h; mov.b16 h, %1; cvt.f32.f16 %0, h;}" : "=f"(r) : "h"(v));
+    return r;
+}
+#else
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) { mma_bf16_16816(d, a, b); }
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) { return pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float f16_bits_to_f32(unsigned short v) { return __uint_as_float((unsigned)v << 16); }
+#endif
+template <bool F16>
+__device__ __forceinline__ void mma_h16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    if (F16) mma_f16_16816(d, a, b); else mma_bf16_16816(d, a, b);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) { return F16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ float h16_bits_to_f32(unsigned short v) {
+    return F16 ? f16_bits_to_f32(v) : __uint_as_float((unsigned)v << 16);
+}
+
 // 8 bf16 = 4 (even, odd) pairs, each turned by its (cos, sin): fp32 inside, rounded back to bf16 like rotary_bf16_kernel
 __device__ __forceinline__ uint4 rotate_bf16x8(uint4 u, const float2* __restrict__ cs) {
     uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -58,6 +92,7 @@ __device__ __forceinline__ uint4 rotate_bf16x8(uint4 u, const float2* __restrict
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128)
 band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o,
@@ -115,7 +150,7 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
             uint32_t b[2];
             b[0] = *reinterpret_cast<const uint32_t*>(kp + ks * 16);
             b[1] = *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8);
-            mma_bf16_16816(sc[nt], qa[ks], b);
+            mma_h16<F16>(sc[nt], qa[ks], b);
         }
     }
     // ---- softmax over the keys (columns); keys >= F are masked out ------------------------------------------------
@@ -142,8 +177,8 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
         const float e2 = __expf(sc[nt][2] - mx1), e3 = __expf(sc[nt][3] - mx1);
         sum0 += e0 + e1;
         sum1 += e2 + e3;
-        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(e0, e1);         // a0 / a2: row r0,     cols (+8 for the odd tile)
-        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(e2, e3);         // a1 / a3: row r0 + 8
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_h16x2<F16>(e0, e1);         // a0 / a2: row r0,     cols (+8 for the odd tile)
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_h16x2<F16>(e2, e3);         // a1 / a3: row r0 + 8
     }
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
     sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
@@ -153,8 +188,9 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     if (gates) {   // upstream Attention: out * to_gates(x).sigmoid(), gates [n_seq * F, H]; folded into the normalisation
         const long long t0 = (long long)s * F + r0;
         const long long gld = gate_ld > 0 ? gate_ld : H;                 // row stride of the gate matrix
-        if (r0 < F) inv0 *= 1.f / (1.f + __expf(-__bfloat162float(gates[t0 * gld + h])));
-        if (r0 + 8 < F) inv1 *= 1.f / (1.f + __expf(-__bfloat162float(gates[(t0 + 8) * gld + h])));
+        const unsigned short* g16 = reinterpret_cast<const unsigned short*>(gates);
+        if (r0 < F) inv0 *= 1.f / (1.f + __expf(-h16_bits_to_f32<F16>(g16[t0 * gld + h])));
+        if (r0 + 8 < F) inv1 *= 1.f / (1.f + __expf(-h16_bits_to_f32<F16>(g16[(t0 + 8) * gld + h])));
     }
     // ---- O = P V -------------------------------------------------------------------------------------------------
     const unsigned short* vs16 = reinterpret_cast<const unsigned short*>(Vs);
@@ -170,10 +206,10 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
             uint32_t b[2];
             b[0] = (uint32_t)vs16[k0 * kBaLd + n] | ((uint32_t)vs16[(k0 + 1) * kBaLd + n] << 16);
             b[1] = (uint32_t)vs16[(k0 + 8) * kBaLd + n] | ((uint32_t)vs16[(k0 + 9) * kBaLd + n] << 16);
-            mma_bf16_16816(oc, pa[ks], b);
+            mma_h16<F16>(oc, pa[ks], b);
         }
-        *reinterpret_cast<uint32_t*>(orow + r0 * kBaLd + nt * 8 + c2) = pack_bf16x2(oc[0] * inv0, oc[1] * inv0);
-        *reinterpret_cast<uint32_t*>(orow + (r0 + 8) * kBaLd + nt * 8 + c2) = pack_bf16x2(oc[2] * inv1, oc[3] * inv1);
+        *reinterpret_cast<uint32_t*>(orow + r0 * kBaLd + nt * 8 + c2) = pack_h16x2<F16>(oc[0] * inv0, oc[1] * inv0);
+        *reinterpret_cast<uint32_t*>(orow + (r0 + 8) * kBaLd + nt * 8 + c2) = pack_h16x2<F16>(oc[2] * inv1, oc[3] * inv1);
     }
     __syncwarp();
     // ---- the warp's 16 rows leave as 16-byte vectors ---------------------------------------------------------------
@@ -187,14 +223,19 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 // [emul-end]
 
 cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
-                                  long long n_seq, int F, int heads, float scale, int gate_ld, cudaStream_t stream) {
+                                  long long n_seq, int F, int heads, float scale, int gate_ld, int fp16, cudaStream_t stream) {
     if (n_seq <= 0) return cudaSuccess;
     const long long ctas = n_seq * heads;
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    band_attn_bf16_kernel<<<(unsigned)ctas, 128, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-        reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
-        reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, heads, scale, gate_ld);
+    if (fp16 && cos_sin) return cudaErrorInvalidValue;   // the in-kernel rotary staging is bfloat16-only (the GEMM epilogue rotates)
+    auto* qp = reinterpret_cast<const __nv_bfloat16*>(q);
+    auto* kp = reinterpret_cast<const __nv_bfloat16*>(k);
+    auto* vp = reinterpret_cast<const __nv_bfloat16*>(v);
+    auto* op = reinterpret_cast<__nv_bfloat16*>(o);
+    auto* gp = reinterpret_cast<const __nv_bfloat16*>(gates);
+    auto* cs = reinterpret_cast<const float2*>(cos_sin);
+    if (fp16) band_attn_bf16_kernel<true><<<(unsigned)ctas, 128, 0, stream>>>(qp, kp, vp, op, gp, cs, F, heads, scale, gate_ld);
+    else band_attn_bf16_kernel<false><<<(unsigned)ctas, 128, 0, stream>>>(qp, kp, vp, op, gp, cs, F, heads, scale, gate_ld);
     count_launch();
     return cudaGetLastError();
 }

@@ -437,18 +437,19 @@ int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, 
     if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0)
         return fail(AL_E_ARG, "al_gate_sigmoid_bf16: bad sizes (dim_head must be a multiple of 8)");
     if ((reinterpret_cast<uintptr_t>(o) & 15) != 0) return fail(AL_E_ARG, "al_gate_sigmoid_bf16: o must be 16-byte aligned");
-    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, heads, (cudaStream_t)stream);
+    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, heads, 0, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_gate_sigmoid_bf16");
     return AL_OK;
 }
 
-int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, void* stream) {
+int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, int fp16,
+                            void* stream) {
     if (!o || !gates) return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: NULL argument");
     if (n_rows == 0) return AL_OK;
     if (n_rows < 0 || heads <= 0 || dim_head <= 0 || (dim_head & 7) != 0 || gate_ld < heads || gate_ld > (1 << 20))
         return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: bad sizes (dim_head must be a multiple of 8, gate_ld >= heads)");
     if ((reinterpret_cast<uintptr_t>(o) & 15) != 0) return fail(AL_E_ARG, "al_gate_sigmoid_ld_bf16: o must be 16-byte aligned");
-    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, (int)gate_ld, (cudaStream_t)stream);
+    cudaError_t e = al::launch_gate_bf16(o, gates, n_rows, heads, dim_head, (int)gate_ld, fp16, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_gate_sigmoid_ld_bf16");
     return AL_OK;
 }
@@ -464,7 +465,8 @@ int al_gelu_bf16(void* x, int64_t n, void* stream) {
 }
 
 int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
-                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream) {
+                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, int fp16,
+                           void* stream) {
     if (!q || !k || !v || !o) return fail(AL_E_ARG, "al_band_attention_bf16: NULL argument");
     if (n_seq == 0) return AL_OK;
     if (n_seq < 0 || heads <= 0) return fail(AL_E_ARG, "al_band_attention_bf16: bad sizes");
@@ -475,7 +477,8 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
         return fail(AL_E_ARG, "al_band_attention_bf16: pointers must be 16-byte aligned");
     if (gates && gate_ld != 0 && (gate_ld < heads || gate_ld > (1 << 20)))
         return fail(AL_E_ARG, "al_band_attention_bf16: gate_ld %lld must be 0 (= heads) or >= heads", (long long)gate_ld);
-    cudaError_t e = al::launch_band_attn_bf16(q, k, v, o, gates, cos_sin, n_seq, seq_len, heads, scale, (int)gate_ld,
+    if (fp16 && cos_sin) return fail(AL_E_UNSUPPORTED, "al_band_attention_bf16: cos_sin (in-kernel rotary) is bfloat16-only");
+    cudaError_t e = al::launch_band_attn_bf16(q, k, v, o, gates, cos_sin, n_seq, seq_len, heads, scale, (int)gate_ld, fp16,
                                               (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_band_attention_bf16");
     return AL_OK;
@@ -494,17 +497,17 @@ int al_gemm_bf16(const al_gemm_args* a, void* stream) {
 }
 
 int al_band_norm(const float* x, int64_t ldx, const float* gamma, const int32_t* band_off, int n_bands, void* out, int64_t ldo,
-                 int64_t n_rows, float eps, void* stream) {
+                 int64_t n_rows, float eps, int out_fp16, void* stream) {
     if (!x || !gamma || !band_off || !out) return fail(AL_E_ARG, "al_band_norm: NULL argument");
     if (n_rows == 0) return AL_OK;
     if (n_rows < 0 || n_bands <= 0 || n_bands > 1024 || ldx <= 0 || ldo <= 0) return fail(AL_E_ARG, "al_band_norm: bad sizes");
-    cudaError_t e = al::launch_band_norm(x, ldx, gamma, band_off, n_bands, out, ldo, n_rows, eps, (cudaStream_t)stream);
+    cudaError_t e = al::launch_band_norm(x, ldx, gamma, band_off, n_bands, out, ldo, n_rows, eps, out_fp16, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_band_norm");
     return AL_OK;
 }
 
 int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
-                     int64_t n_rows, int dim, int ss_parts, float eps, void* stream) {
+                     int64_t n_rows, int dim, int ss_parts, float eps, int xb_fp16, void* stream) {
     if (!x_in || !x32 || !xb || !ss) return fail(AL_E_ARG, "al_resid_prepare: NULL argument");
     if (n_rows == 0) return AL_OK;
     if (n_rows < 0 || dim <= 0 || dim > 2048 || ss_parts <= 0 || ss_parts > 8 || dim % (8 * ss_parts) != 0)
@@ -512,7 +515,7 @@ int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, f
     if (((reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(x32) | reinterpret_cast<uintptr_t>(xb) |
           reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(gamma)) & 15) != 0)
         return fail(AL_E_ARG, "al_resid_prepare: pointers must be 16-byte aligned");
-    cudaError_t e = al::launch_resid_prepare(x_in, bias, gamma, x32, xb, ss, n_rows, dim, ss_parts, eps, (cudaStream_t)stream);
+    cudaError_t e = al::launch_resid_prepare(x_in, bias, gamma, x32, xb, ss, n_rows, dim, ss_parts, eps, xb_fp16, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "al_resid_prepare");
     return AL_OK;
 }

@@ -66,7 +66,7 @@ struct SmemLayout {
     static constexpr int kDynamic = kTotal + 1024;            // slack for the manual 1024-byte alignment
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
     using L = SmemLayout<BN, STAGES, EPI>;
@@ -154,7 +154,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int n_blk = rem % g.n_tiles;
                 int n_cur = g.N - n_blk * BN;
                 n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
-                const uint32_t idesc = umma_idesc_bf16(BM, n_cur);
+                const uint32_t idesc = umma_idesc_16bit(BM, n_cur, F16);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
@@ -294,10 +294,10 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 uint4 u;
-                                u.x = pack_bf16(v[4 * j].x, v[4 * j].y);
-                                u.y = pack_bf16(v[4 * j + 1].x, v[4 * j + 1].y);
-                                u.z = pack_bf16(v[4 * j + 2].x, v[4 * j + 2].y);
-                                u.w = pack_bf16(v[4 * j + 3].x, v[4 * j + 3].y);
+                                u.x = pack16<F16>(v[4 * j].x, v[4 * j].y);
+                                u.y = pack16<F16>(v[4 * j + 1].x, v[4 * j + 1].y);
+                                u.z = pack16<F16>(v[4 * j + 2].x, v[4 * j + 2].y);
+                                u.w = pack16<F16>(v[4 * j + 3].x, v[4 * j + 3].y);
                                 const int chunk = h * 4 + j;             // 16-byte chunk of the 128-byte row
                                 *reinterpret_cast<uint4*>(sb + ((chunk ^ (lane & 7)) << 4)) = u;
                             }
@@ -399,10 +399,10 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 u;
-                    u.x = pack_bf16(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
-                    u.y = pack_bf16(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-                    u.z = pack_bf16(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-                    u.w = pack_bf16(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                    u.x = pack16<F16>(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+                    u.y = pack16<F16>(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                    u.z = pack16<F16>(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                    u.w = pack16<F16>(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
                     *reinterpret_cast<uint4*>(xb + ((j ^ ((lane >> 1) & 3)) << 4)) = u;   // 64-byte swizzle
                 }
                 fence_proxy_async();
@@ -463,7 +463,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, in
 
 struct DevInfo {
     int n_sm = 0;
-    bool attr[8] = {};
+    bool attr[16] = {};
 };
 static DevInfo& dev_info(int dev) {
     static DevInfo info[64];
@@ -477,8 +477,8 @@ static DevInfo& dev_info(int dev) {
     return d;
 }
 
-template <int BN, int STAGES, int EPI>
-static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
+template <int BN, int STAGES, int EPI, bool F16>
+static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES, EPI>;
     static_assert(L::kDynamic <= 232448, "shared memory budget");
     int dev = 0;
@@ -486,16 +486,21 @@ static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cuda
     if (e != cudaSuccess) return e;
     DevInfo& d = dev_info(dev);
     if (!d.attr[slot]) {
-        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return e;
         d.attr[slot] = true;
     }
     const int total = g.m_tiles * g.n_tiles * g.groups;
     int grid = total < d.n_sm ? total : d.n_sm;
     if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kThreads, L::kDynamic, stream>>>(tm, g);
+    gemm_bf16_kernel<BN, STAGES, EPI, F16><<<grid, kThreads, L::kDynamic, stream>>>(tm, g);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int BN, int STAGES, int EPI>
+static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
+    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true>(tm, g, slot + 8, stream) : launch_cfg1<BN, STAGES, EPI, false>(tm, g, slot, stream);
 }
 
 }  // namespace tc
@@ -520,12 +525,14 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     g.side_rs = c.side_row_stride > 0 ? c.side_row_stride : 1;
     g.side_gs = c.side_row_stride > 0 ? c.side_group_stride : c.M;
     g.accumulate = c.no_accumulate ? 0 : 1;
+    g.fp16 = c.operand_fp16 ? 1 : 0;
+    const CUtensorMapDataType dt16 = c.operand_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if ((long long)g.m_tiles * g.n_tiles * g.groups > 0x7fffffffll) return "too many tiles";
     Tmaps tm;
-    if (!make_map(&tm.a, c.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
+    if (!make_map(&tm.a, c.A, dt16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(A) failed";
-    if (!make_map(&tm.b, c.W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, BN,
+    if (!make_map(&tm.b, c.W, dt16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, BN,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(W) failed";
     if (c.epi == EPI_RES) {
@@ -535,7 +542,7 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
         if (!make_map(&tm.o[0], c.x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.N, c.M, c.groups, c.ldx, c.x_group_stride, 32, 32,
                       CU_TENSOR_MAP_SWIZZLE_128B))
             return "cuTensorMapEncodeTiled(x32) failed";
-        if (!make_map(&tm.o[1], c.xb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.N, c.M, c.groups, c.ldxb, c.xb_group_stride, 32, 32,
+        if (!make_map(&tm.o[1], c.xb, dt16, 2, c.N, c.M, c.groups, c.ldxb, c.xb_group_stride, 32, 32,
                       CU_TENSOR_MAP_SWIZZLE_64B))
             return "cuTensorMapEncodeTiled(xb) failed";
         if (!make_map(&tm.o[2], c.x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.N, c.M, c.groups, c.ldx, c.x_group_stride, 64, BM,
@@ -578,7 +585,7 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
         if (!o) return "missing output tensor";
         if ((reinterpret_cast<uintptr_t>(o) & 15) != 0 || (c.ldo[src] & 7) != 0) return "outputs need 16-byte aligned rows";
         const int cols = (src == n_out - 1) ? c.N - split * (n_out - 1) : split;
-        if (!make_map(&tm.o[i], o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cols, c.M, c.groups, c.ldo[src],
+        if (!make_map(&tm.o[i], o, dt16, 2, cols, c.M, c.groups, c.ldo[src],
                       c.o_group_stride[src], 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
             return "cuTensorMapEncodeTiled(out) failed";
     }

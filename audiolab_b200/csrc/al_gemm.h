@@ -29,15 +29,16 @@ struct GemmArgs {
     int max_ctas;
     long long side_rs, side_gs;   // per-row side arrays (row_ss, ss_out): row index = group * side_gs + row * side_rs
     int accumulate;               // EPI_RES: 0 = start the stream (no residual read)
+    int fp16;                     // 16-bit operands / outputs are IEEE half instead of bfloat16
 };
 
 // Returns NULL on success, else a static message (and the CUDA error, if that is what failed, in *cuda_err).
 const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t* cuda_err);
 
 cudaError_t launch_band_norm(const float* x, long long ldx, const float* gamma, const int* band_off, int n_bands, void* out,
-                             long long ldo, long long n_rows, float eps, cudaStream_t stream);
+                             long long ldo, long long n_rows, float eps, int fp16, cudaStream_t stream);
 
 cudaError_t launch_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
-                                 long long n_rows, int dim, int ss_parts, float eps, cudaStream_t stream);
+                                 long long n_rows, int dim, int ss_parts, float eps, int fp16, cudaStream_t stream);
 
 }  // namespace al

@@ -160,12 +160,12 @@ cudaError_t launch_rmsnorm_bf16(void* x, const float* gamma, const float* bias, 
                                 float scale, float eps, cudaStream_t stream);
 cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_rows, int heads, int dim_head,
                                long long pos_div, int pos_mod, cudaStream_t stream);
-cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld,
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld, int fp16,
                              cudaStream_t stream);
 
 cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream);
 cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
-                                  long long n_seq, int F, int heads, float scale, int gate_ld, cudaStream_t stream);
+                                  long long n_seq, int F, int heads, float scale, int gate_ld, int fp16, cudaStream_t stream);
 
 cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
                        cudaStream_t stream);

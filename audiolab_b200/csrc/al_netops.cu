@@ -37,6 +37,51 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
     return u;
 }
 
+// The same for a 16-bit format chosen at compile time: F16 = IEEE half (saturating to +-65504), else bfloat16.
+#ifndef AL_CPU_EMUL
+__device__ __forceinline__ float2 half2_bits_to_f32(unsigned u) {
+    float2 r;
+    asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(r.x), "=f"(r.y) : "r"(u));
+    return r;
+}
+__device__ __forceinline__ unsigned f32_to_half2_bits(float lo, float hi) {
+    unsigned r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+#else   // the host emulation only runs the bfloat16 instantiations
+__device__ __forceinline__ float2 half2_bits_to_f32(unsigned) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ unsigned f32_to_half2_bits(float, float) { return 0u; }
+#endif
+template <bool F16>
+__device__ __forceinline__ float2 h16x2_to_f32(unsigned u) {
+    if (F16) return half2_bits_to_f32(u);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
+}
+template <bool F16>
+__device__ __forceinline__ unsigned f32_to_h16x2(float lo, float hi) {
+    if (F16) return f32_to_half2_bits(lo, hi);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&h);
+}
+template <bool F16>
+__device__ __forceinline__ void h16x8_to_f32(const uint4 u, float (&f)[8]) {
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = h16x2_to_f32<F16>(w[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+template <bool F16>
+__device__ __forceinline__ uint4 f32_to_h16x8(const float (&f)[8]) {
+    return make_uint4(f32_to_h16x2<F16>(f[0], f[1]), f32_to_h16x2<F16>(f[2], f[3]), f32_to_h16x2<F16>(f[4], f[5]),
+                      f32_to_h16x2<F16>(f[6], f[7]));
+}
+template <bool F16>
+__device__ __forceinline__ float h16_to_f32(unsigned short v) { return h16x2_to_f32<F16>((unsigned)v).x; }
+
 // One warp per row; the row stays in registers between the reduction and the scaling pass.
 template <int MAXC>   // chunks of 256 elements held in registers (dim <= 256 * MAXC)
 __global__ void __launch_bounds__(256)
@@ -143,30 +188,35 @@ cudaError_t launch_rotary_bf16(void* q, void* k, const float* cs, long long n_ro
 
 // [emul-begin]
 // o: [n_rows, heads * dim_head] bf16, gates: [n_rows, heads] bf16;  o[row, h, :] *= sigmoid(gates[row, h])
+template <bool F16>
 __global__ void __launch_bounds__(256)
-gate_bf16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates, long long n_vec, int vec_per_row,
-                 int gate_ld, int dim_head) {
+gate_h16_kernel(uint4* __restrict__ o, const __nv_bfloat16* __restrict__ gates, long long n_vec, int vec_per_row,
+                int gate_ld, int dim_head) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_vec) return;
     const long long row = i / vec_per_row;
     const int h = ((int)(i - row * vec_per_row) * 8) / dim_head;
-    const float g = __bfloat162float(gates[row * gate_ld + h]);
+    const float g = h16_to_f32<F16>(reinterpret_cast<const unsigned short*>(gates)[row * gate_ld + h]);
     const float sg = 1.f / (1.f + __expf(-g));
     float a[8];
-    bf16x8_to_f32(o[i], a);
+    h16x8_to_f32<F16>(o[i], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] *= sg;
-    o[i] = f32_to_bf16x8(a);
+    o[i] = f32_to_h16x8<F16>(a);
 }
 
 // [emul-end]
 
-cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld,
+cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int heads, int dim_head, int gate_ld, int fp16,
                              cudaStream_t stream) {
     const int vec_per_row = heads * dim_head / 8;
     const long long n_vec = n_rows * vec_per_row;
-    gate_bf16_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, gate_ld, dim_head);
+    if (fp16)
+        gate_h16_kernel<true><<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, gate_ld, dim_head);
+    else
+        gate_h16_kernel<false><<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, gate_ld, dim_head);
     count_launch();
     return cudaGetLastError();
 }
@@ -175,7 +225,7 @@ cudaError_t launch_gate_bf16(void* o, const void* gates, long long n_rows, int h
 // Start / re-normalise the fp32 residual stream of the tcgen05 path (al_gemm.cu EPI_RES keeps it afterwards):
 // y = x_in (+ bias) (then RMSNorm if gamma);  x32 = y, xb = bf16(y), ss[row][p] = partial sums of y^2.
 // One warp per row; lane l owns elements [c * 256 + 8 l, + 8) of chunk c.
-template <int MAXC>
+template <int MAXC, bool F16>
 __global__ void __launch_bounds__(256)
 resid_prepare_kernel(const float* __restrict__ x_in, const float* __restrict__ bias, const float* __restrict__ gamma,
                      float* __restrict__ x32, __nv_bfloat16* __restrict__ xb, float* __restrict__ ss_out,
@@ -242,7 +292,7 @@ resid_prepare_kernel(const float* __restrict__ x_in, const float* __restrict__ b
         if (e < dim) {
             o32[e >> 2] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
             o32[(e >> 2) + 1] = make_float4(v[c][4], v[c][5], v[c][6], v[c][7]);
-            ob[e >> 3] = f32_to_bf16x8(v[c]);
+            ob[e >> 3] = f32_to_h16x8<F16>(v[c]);
         }
     }
 }
@@ -250,14 +300,16 @@ resid_prepare_kernel(const float* __restrict__ x_in, const float* __restrict__ b
 // [emul-end]
 
 cudaError_t launch_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
-                                 long long n_rows, int dim, int ss_parts, float eps, cudaStream_t stream) {
+                                 long long n_rows, int dim, int ss_parts, float eps, int fp16, cudaStream_t stream) {
     const int wpb = 8;
     const unsigned grid = (unsigned)((n_rows + wpb - 1) / wpb);
     auto* ob = reinterpret_cast<__nv_bfloat16*>(xb);
     const float scale = sqrtf((float)dim);
-    if (dim <= 512) resid_prepare_kernel<2><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
-    else if (dim <= 1024) resid_prepare_kernel<4><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
-    else resid_prepare_kernel<8><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps);
+#define AL_RP_LAUNCH(C, H) resid_prepare_kernel<C, H><<<grid, wpb * 32, 0, stream>>>(x_in, bias, gamma, x32, ob, ss, n_rows, dim, ss_parts, scale, eps)
+    if (dim <= 512) { if (fp16) AL_RP_LAUNCH(2, true); else AL_RP_LAUNCH(2, false); }
+    else if (dim <= 1024) { if (fp16) AL_RP_LAUNCH(4, true); else AL_RP_LAUNCH(4, false); }
+    else { if (fp16) AL_RP_LAUNCH(8, true); else AL_RP_LAUNCH(8, false); }
+#undef AL_RP_LAUNCH
     count_launch();
     return cudaGetLastError();
 }
@@ -266,6 +318,7 @@ cudaError_t launch_resid_prepare(const float* x_in, const float* bias, const flo
 // Per-band RMSNorm of the band-split input (upstream BandSplit: RMSNorm(d_j) in front of each band's Linear): one CTA per
 // row; the row is read once, each warp normalises whole bands (sum of squares over the band's d_j elements, lanes
 // strided), and the bf16 result is the A operand of the grouped band-split GEMM.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 band_norm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma, const int* __restrict__ band_off,
                  int n_bands, __nv_bfloat16* __restrict__ out, long long ldo, float eps) {
@@ -283,15 +336,17 @@ band_norm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         const float inv = sqrtf((float)(b - a)) / fmaxf(sqrtf(ss), eps);
-        for (int i = a + lane; i < b; i += 32) orow[i] = __float2bfloat16_rn(xr[i] * inv * __ldg(gamma + i));
+        unsigned short* o16 = reinterpret_cast<unsigned short*>(orow);
+        for (int i = a + lane; i < b; i += 32) o16[i] = (unsigned short)(f32_to_h16x2<F16>(xr[i] * inv * __ldg(gamma + i), 0.f) & 0xFFFFu);
     }
 }
 // [emul-end]
 
 cudaError_t launch_band_norm(const float* x, long long ldx, const float* gamma, const int* band_off, int n_bands, void* out,
-                             long long ldo, long long n_rows, float eps, cudaStream_t stream) {
-    band_norm_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(x, ldx, gamma, band_off, n_bands,
-                                                           reinterpret_cast<__nv_bfloat16*>(out), ldo, eps);
+                             long long ldo, long long n_rows, float eps, int fp16, cudaStream_t stream) {
+    auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (fp16) band_norm_kernel<true><<<(unsigned)n_rows, 256, 0, stream>>>(x, ldx, gamma, band_off, n_bands, o, ldo, eps);
+    else band_norm_kernel<false><<<(unsigned)n_rows, 256, 0, stream>>>(x, ldx, gamma, band_off, n_bands, o, ldo, eps);
     count_launch();
     return cudaGetLastError();
 }

@@ -158,6 +158,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// same with the A / B format selectable: 0 = IEEE half (f16), 1 = bfloat16 -- both kind::f16, same rate
+__device__ __forceinline__ uint32_t umma_idesc_16bit(int m, int n, bool f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -179,6 +184,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// IEEE half pair; saturates to +-65504 instead of producing inf (half has 5 exponent bits)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) { return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
 __device__ __forceinline__ float fast_ex2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -52,14 +52,15 @@ def rotary_(q: torch.Tensor, k: torch.Tensor, cos_sin: torch.Tensor, heads: int,
 
 def gate_sigmoid_(o: torch.Tensor, gates: torch.Tensor, heads: int, dim_head: int) -> None:
     """o[row, h, :] *= sigmoid(gates[row, h]) in place."""
-    _check_bf16_rows(o, "o")
     if o.shape[1] != heads * dim_head or tuple(gates.shape) != (o.shape[0], heads):
         raise ValueError("o must be [rows, heads*dim_head] and gates [rows, heads]")
-    if gates.is_cuda and gates.dtype == torch.bfloat16 and gates.stride(1) == 1 and gates.stride(0) != heads:
-        # the gate columns of the fused to_qkv + to_gates GEMM output: a strided view
+    if (gates.is_cuda and o.is_cuda and o.dtype in HALF_DTYPES and o.dim() == 2 and o.is_contiguous() and gates.stride(1) == 1
+            and (gates.stride(0) != heads or o.dtype == torch.float16)):
+        # the gate columns of the fused to_qkv + to_gates GEMM output (a strided view), bf16 or fp16
         _lib.check(_lib.lib().al_gate_sigmoid_ld_bf16(o.data_ptr(), gates.data_ptr(), gates.stride(0), o.shape[0], heads,
-                                                      dim_head, _stream()), "al_gate_sigmoid_ld_bf16")
+                                                      dim_head, _half_kind(o, gates), _stream()), "al_gate_sigmoid_ld_bf16")
         return
+    _check_bf16_rows(o, "o")
     _check_bf16_rows(gates, "gates")
     _lib.check(_lib.lib().al_gate_sigmoid_bf16(o.data_ptr(), gates.data_ptr(), o.shape[0], heads, dim_head, _stream()),
                "al_gate_sigmoid_bf16")
@@ -83,14 +84,18 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
     sigmoid(gates) per (token, head); with `cos_sin` [seq_len, dim_head/2, 2] fp32, q and k are rotated by their position in
     the sequence first (rotary_ semantics, without modifying q / k).  Returns a new [n_seq * seq_len, heads * dim_head] tensor."""
     for t, name in ((q, "q"), (k, "k"), (v, "v")):
-        _check_bf16_rows(t, name)
+        if not t.is_cuda:
+            raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if t.dtype not in HALF_DTYPES or t.dim() != 2 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous bf16 / fp16 [rows, cols] tensor")
+    fp16 = _half_kind(q, k, v)
     if q.shape != k.shape or q.shape != v.shape or tuple(q.shape) != (n_seq * seq_len, heads * dim_head):
         raise ValueError("q, k, v must be [n_seq * seq_len, heads * dim_head]")
     gate_ld = 0
     if gates is not None:
-        if (not gates.is_cuda or gates.dtype != torch.bfloat16 or tuple(gates.shape) != (q.shape[0], heads)
+        if (not gates.is_cuda or gates.dtype != q.dtype or tuple(gates.shape) != (q.shape[0], heads)
                 or gates.stride(1) != 1):
-            raise ValueError("gates must be a CUDA bf16 [n_seq * seq_len, heads] tensor with unit column stride")
+            raise ValueError("gates must be a CUDA [n_seq * seq_len, heads] tensor of q's dtype with unit column stride")
         gate_ld = gates.stride(0)
     if cos_sin is not None and (cos_sin.dtype != torch.float32 or tuple(cos_sin.shape) != (seq_len, dim_head // 2, 2)
                                 or not cos_sin.is_contiguous() or not cos_sin.is_cuda):
@@ -99,7 +104,7 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
     _lib.check(_lib.lib().al_band_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                                  None if gates is None else gates.data_ptr(), int(gate_ld),
                                                  None if cos_sin is None else cos_sin.data_ptr(), int(n_seq), int(seq_len),
-                                                 int(heads), int(dim_head), float(dim_head) ** -0.5, _stream()),
+                                                 int(heads), int(dim_head), float(dim_head) ** -0.5, fp16, _stream()),
                "al_band_attention_bf16")
     return o
 
@@ -123,17 +128,27 @@ class GemmArgs(_C.Structure):
         ("x32", _C.c_void_p), ("xb", _C.c_void_p),
         ("ldx", _C.c_int64), ("x_group_stride", _C.c_int64), ("ldxb", _C.c_int64), ("xb_group_stride", _C.c_int64),
         ("ss_out", _C.c_void_p), ("max_ctas", _C.c_int32), ("no_accumulate", _C.c_int32),
-        ("side_row_stride", _C.c_int64), ("side_group_stride", _C.c_int64),
+        ("side_row_stride", _C.c_int64), ("side_group_stride", _C.c_int64), ("operand_fp16", _C.c_int32),
     ]
 
 
 ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
+HALF_DTYPES = (torch.bfloat16, torch.float16)     # 16-bit operand formats of the tcgen05 path (same tensor-core rate)
+
+
+def _half_kind(*tensors) -> int:
+    """0 = bfloat16, 1 = IEEE half; every 16-bit tensor of one call must agree."""
+    kinds = {t.dtype for t in tensors}
+    if len(kinds) != 1 or next(iter(kinds)) not in HALF_DTYPES:
+        raise ValueError(f"the 16-bit tensors of one call must all be bfloat16 or all be float16, got {sorted(map(str, kinds))}")
+    return 1 if next(iter(kinds)) == torch.float16 else 0
 
 
 def _rows2d(t: torch.Tensor, name: str, dtype) -> None:
     if not t.is_cuda:
         raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
-    if t.dtype != dtype or t.dim() not in (2, 3) or t.stride(-1) != 1:
+    ok = t.dtype in dtype if isinstance(dtype, tuple) else t.dtype == dtype
+    if not ok or t.dim() not in (2, 3) or t.stride(-1) != 1:
         raise ValueError(f"{name} must be a {dtype} [rows, cols] or [groups, rows, cols] tensor with unit column stride")
 
 
@@ -154,13 +169,14 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Te
     row_ss [M(, G), parts] fp32 turns on the folded RMSNorm row scale ss_scale / max(sqrt(sum row_ss), ss_eps)."""
     if isinstance(outs, torch.Tensor):
         outs = [outs]
-    _rows2d(a, "a", torch.bfloat16)
-    _rows2d(w, "w", torch.bfloat16)
+    _rows2d(a, "a", HALF_DTYPES)
+    _rows2d(w, "w", HALF_DTYPES)
     g, m, k, lda, ags = _geom(a)
     gw, n, kw, ldw, wgs = _geom(w)
     if gw != g or kw != k:
         raise ValueError("a and w disagree on groups / K")
     args = GemmArgs()
+    args.operand_fp16 = _half_kind(a, w, *outs)
     args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
     args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
     args.epi, args.act = 0, ACT[act]
@@ -180,7 +196,7 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Te
     if len(outs) > 4:
         raise ValueError("at most 4 outputs")
     for i, o in enumerate(outs):
-        _rows2d(o, f"outs[{i}]", torch.bfloat16)
+        _rows2d(o, f"outs[{i}]", HALF_DTYPES)
         go, mo, _, ldo, ogs = _geom(o)
         if go != g or mo != m:
             raise ValueError("outputs disagree with a on groups / M")
@@ -200,8 +216,8 @@ def gemm_bf16_glu(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: 
     """out[..., m, i] = (a @ w^T + bias)[2i] * sigmoid((a @ w^T + bias)[2i + 1]) in fp32 (al_gemm_bf16, EPI_GLU): w's rows
     (and bias) are ALREADY interleaved (a_0, b_0, a_1, b_1, ...), see `interleave_glu`.  a [M, K] / [G, M, K] bf16,
     w [N, K] / [G, N, K] bf16, out fp32 [M, N / 2] / [G, M, N / 2] (may be a strided view into the mask tensor)."""
-    _rows2d(a, "a", torch.bfloat16)
-    _rows2d(w, "w", torch.bfloat16)
+    _rows2d(a, "a", HALF_DTYPES)
+    _rows2d(w, "w", HALF_DTYPES)
     _rows2d(out, "out", torch.float32)
     g, m, k, lda, ags = _geom(a)
     gw, n, kw, ldw, wgs = _geom(w)
@@ -212,6 +228,7 @@ def gemm_bf16_glu(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: 
     args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
     args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
     args.epi = 2
+    args.operand_fp16 = _half_kind(a, w)
     if bias is not None:
         if bias.dtype != torch.float32 or bias.numel() != g * n or not bias.is_contiguous():
             raise ValueError("bias must be contiguous fp32 [groups, N] (interleaved like w's rows)")
@@ -237,22 +254,23 @@ def band_norm(x: torch.Tensor, gamma: torch.Tensor, band_off: torch.Tensor, out:
     gamma[off_j:off_{j+1}]).  x fp32 [rows, >= off_last] (row stride free), out bf16 likewise, band_off int32 device."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("x must be a CUDA fp32 [rows, cols] tensor with unit column stride")
-    if out.dtype != torch.bfloat16 or out.dim() != 2 or out.stride(1) != 1 or out.shape[0] != x.shape[0]:
-        raise ValueError("out must be bf16 [rows, cols] with unit column stride")
+    if out.dtype not in HALF_DTYPES or out.dim() != 2 or out.stride(1) != 1 or out.shape[0] != x.shape[0]:
+        raise ValueError("out must be bf16 / fp16 [rows, cols] with unit column stride")
     if band_off.dtype != torch.int32 or not band_off.is_contiguous() or gamma.dtype != torch.float32 or not gamma.is_contiguous():
         raise ValueError("band_off must be contiguous int32, gamma contiguous fp32")
     _lib.check(_lib.lib().al_band_norm(x.data_ptr(), x.stride(0), gamma.data_ptr(), band_off.data_ptr(), band_off.numel() - 1,
-                                       out.data_ptr(), out.stride(0), x.shape[0], float(eps), _stream()), "al_band_norm")
+                                       out.data_ptr(), out.stride(0), x.shape[0], float(eps), _half_kind(out), _stream()),
+               "al_band_norm")
 
 
 def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss_out: torch.Tensor, *,
                        bias: Optional[torch.Tensor] = None, max_ctas: int = 0, accumulate: bool = True) -> None:
     """x32 += a @ w^T + bias (fp32, in place); xb = bf16(x32); ss_out[m, j] = sum of x32[m, S j : S (j+1)]^2 with
     S = resid_slab(N)."""
-    _rows2d(a, "a", torch.bfloat16)
-    _rows2d(w, "w", torch.bfloat16)
+    _rows2d(a, "a", HALF_DTYPES)
+    _rows2d(w, "w", HALF_DTYPES)
     _rows2d(x32, "x32", torch.float32)
-    _rows2d(xb, "xb", torch.bfloat16)
+    _rows2d(xb, "xb", HALF_DTYPES)
     g, m, k, lda, ags = _geom(a)
     gw, n, kw, ldw, wgs = _geom(w)
     if gw != g or kw != k or n % 128 != 0:
@@ -276,6 +294,7 @@ def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: 
     args.A, args.W, args.M, args.N, args.K, args.groups = a.data_ptr(), w.data_ptr(), m, n, k, g
     args.lda, args.a_group_stride, args.ldw, args.w_group_stride = lda, ags, ldw, wgs
     args.epi = 1
+    args.operand_fp16 = _half_kind(a, w, xb)
     if bias is not None:
         if bias.dtype != torch.float32 or bias.numel() != g * n or not bias.is_contiguous():
             raise ValueError("bias must be contiguous fp32 [groups, N]")
@@ -296,7 +315,8 @@ def resid_prepare(x_in: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss: t
     for t, name in ((x_in, "x_in"), (x32, "x32")):
         if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (n, d):
             raise ValueError(f"{name} must be a contiguous CUDA fp32 [rows, dim] tensor")
-    _check_bf16_rows(xb, "xb")
+    if not xb.is_cuda or xb.dtype not in HALF_DTYPES or not xb.is_contiguous() or tuple(xb.shape) != (n, d):
+        raise ValueError("xb must be a contiguous CUDA bf16 / fp16 [rows, dim] tensor")
     if ss.dtype != torch.float32 or not ss.is_contiguous() or ss.numel() % n != 0:
         raise ValueError("ss must be contiguous fp32 [rows, parts]")
     for v, name in ((bias, "bias"), (gamma, "gamma")):
@@ -304,4 +324,5 @@ def resid_prepare(x_in: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss: t
             raise ValueError(f"{name} must be contiguous fp32 [dim]")
     _lib.check(_lib.lib().al_resid_prepare(x_in.data_ptr(), None if bias is None else bias.data_ptr(),
                                            None if gamma is None else gamma.data_ptr(), x32.data_ptr(), xb.data_ptr(),
-                                           ss.data_ptr(), n, d, ss.numel() // n, float(eps), _stream()), "al_resid_prepare")
+                                           ss.data_ptr(), n, d, ss.numel() // n, float(eps), _half_kind(xb), _stream()),
+               "al_resid_prepare")

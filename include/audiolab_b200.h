@@ -192,11 +192,15 @@ int al_rmsnorm_bf16(void* x, const float* gamma, const float* bias, void* out, i
 int al_rotary_bf16(void* q, void* k, const float* cos_sin, int64_t n_rows, int heads, int dim_head, int64_t pos_div,
                    int pos_mod, void* stream);
 int al_gate_sigmoid_bf16(void* o, const void* gates, int64_t n_rows, int heads, int dim_head, void* stream);
-/* as al_gate_sigmoid_bf16 with a row stride: gates[row * gate_ld + h] (the gate columns of the fused to_qkv + to_gates GEMM) */
-int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, void* stream);
+/* as al_gate_sigmoid_bf16 with a row stride: gates[row * gate_ld + h] (the gate columns of the fused to_qkv + to_gates GEMM);
+ * fp16 = 1: o and gates are IEEE half (the fp16-operand mode of the network, see al_gemm_args.operand_fp16); likewise the
+ * `fp16` argument of al_band_attention_bf16 (q, k, v, o, gates half; cos_sin must then be NULL). */
+int al_gate_sigmoid_ld_bf16(void* o, const void* gates, int64_t gate_ld, int64_t n_rows, int heads, int dim_head, int fp16,
+                            void* stream);
 int al_gelu_bf16(void* x, int64_t n, void* stream);
 int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
-                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, void* stream);
+                           const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, int fp16,
+                           void* stream);
 
 /*
  * al_gemm_bf16 -- K4: one nn.Linear (or a batch of `groups` of them) of the RoFormer mask network on the tcgen05
@@ -230,7 +234,8 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
  *
  * al_band_norm -- upstream BandSplit's per-band RMSNorm: for each band j, out[m, off_j : off_{j+1}] =
  *   bf16(F.normalize(x[m, off_j : off_{j+1}]) * sqrt(off_{j+1} - off_j) * gamma[off_j : off_{j+1}]); x fp32 (row stride ldx),
- *   out bf16 (row stride ldo), band_off DEVICE int32 [n_bands + 1].  The A operand of the grouped band-split GEMM.
+ *   out bf16 (IEEE half if out_fp16; row stride ldo), band_off DEVICE int32 [n_bands + 1].  The A operand of the grouped
+ *   band-split GEMM.
  */
 #define AL_GEMM_EPI_BF16 0
 #define AL_GEMM_EPI_RESIDUAL 1
@@ -264,20 +269,22 @@ typedef struct al_gemm_args {
     int32_t no_accumulate;        /* EPI_RESIDUAL: 1 = x32 = acc + bias (start of the stream, x32 is not read) */
     int64_t side_row_stride;      /* 0 = default (row_ss / ss_out indexed by group * M + row); else the row index of the per-row */
     int64_t side_group_stride;    /*   side arrays is group * side_group_stride + row * side_row_stride (band-grouped calls)  */
+    int32_t operand_fp16;         /* 1 = every 16-bit tensor of the call (A, W, out, xb) is IEEE half instead of bfloat16: same */
+                                  /*   tensor-core rate, 11 instead of 8 significand bits, outputs saturate at +-65504          */
 } al_gemm_args;
 
 int al_gemm_bf16(const al_gemm_args* args, void* stream);
 int al_band_norm(const float* x, int64_t ldx, const float* gamma, const int32_t* band_off, int n_bands, void* out, int64_t ldo,
-                 int64_t n_rows, float eps, void* stream);
+                 int64_t n_rows, float eps, int out_fp16, void* stream);
 
 /*
  * al_resid_prepare -- start (or re-normalise) the fp32 residual stream the residual epilogue of al_gemm_bf16 keeps:
  *   y = x_in (+ bias);  if gamma != NULL: y = F.normalize(y, dim=-1) * sqrt(dim) * gamma (upstream RMSNorm);
  *   x32 = y,  xb = bf16(y),  ss[m * ss_parts + p] = sum of y[m, p * dim / ss_parts ...)^2.
- * x_in fp32 [n_rows, dim] (may alias x32); dim a multiple of 8 * ss_parts, <= 2048.
+ * x_in fp32 [n_rows, dim] (may alias x32); dim a multiple of 8 * ss_parts, <= 2048; xb is IEEE half if xb_fp16.
  */
 int al_resid_prepare(const float* x_in, const float* bias, const float* gamma, float* x32, void* xb, float* ss,
-                     int64_t n_rows, int dim, int ss_parts, float eps, void* stream);
+                     int64_t n_rows, int dim, int ss_parts, float eps, int xb_fp16, void* stream);
 
 #ifdef __cplusplus
 }

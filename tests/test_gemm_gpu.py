@@ -258,3 +258,103 @@ def test_roformer_mask_all_tc_path_vs_fp32_modules():
     assert got.shape == ref.shape
     rel = float((torch.view_as_real(got) - torch.view_as_real(ref)).norm() / torch.view_as_real(ref).norm())
     assert rel < 1.5e-2, rel
+
+
+# ---- IEEE-half operand mode (al_gemm_args.operand_fp16): same kernels, 11 significand bits -------------------------------
+def _close_f16(got, ref, what):
+    got = got.float()
+    err = (got - ref).abs()
+    tol = 2.0 ** -11 * ref.abs() + 2e-5 * ref.abs().max().clamp(min=1e-6)      # half an ulp of binary16 = 2^-12 relative
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} outside fp16 rounding, max err {float(err.max()):.3e}"
+
+
+def test_fp16_gemm_epilogues():
+    netops = _cuda()
+    m, n, k = 1111, 2048, 512
+    x = _rand((m, k), 60, 3.0)
+    a = x.half()
+    w = _rand((n, k), 61, k ** -0.5).half()
+    bias = _rand((n,), 62, 0.5)
+    ss = x.view(m, 4, -1).square().sum(-1).contiguous()
+    out = torch.empty((m, n), device="cuda", dtype=torch.float16)
+    netops.gemm_bf16(a, w, out, bias=bias, row_ss=ss, ss_scale=math.sqrt(k), act="gelu")
+    torch.cuda.synchronize()
+    rs = math.sqrt(k) / x.square().sum(-1).sqrt()
+    _close_f16(out, torch.nn.functional.gelu((a.float() @ w.float().t()) * rs[:, None] + bias), "fp16 rowscale+bias+gelu")
+    with pytest.raises(ValueError):
+        netops.gemm_bf16(a, w.bfloat16(), out)                       # mixed 16-bit formats are refused
+    # residual epilogue: xb is the half rounding (saturating) of the stored fp32 row
+    w2 = _rand((512, n), 63, n ** -0.5).half()
+    x0 = _rand((m, 512), 64, 2.0)
+    x32, xb, ss2 = x0.clone(), torch.empty((m, 512), device="cuda", dtype=torch.float16), torch.empty((m, 4), device="cuda")
+    netops.gemm_bf16_residual(out, w2, x32, xb, ss2, bias=None)
+    torch.cuda.synchronize()
+    ref = x0 + out.float() @ w2.float().t()
+    assert torch.allclose(x32, ref, rtol=2e-5, atol=2e-5 * float(ref.abs().max()))
+    assert torch.equal(xb, x32.half())
+    # GLU epilogue
+    n_out = 48
+    w3 = netops.interleave_glu(_rand((2 * n_out, n), 65, n ** -0.5)).half()
+    o3 = torch.empty((m, n_out), device="cuda")
+    netops.gemm_bf16_glu(out, w3, o3)
+    torch.cuda.synchronize()
+    y = out.float() @ w3.float().t()
+    assert torch.allclose(o3, y[:, 0::2] * torch.sigmoid(y[:, 1::2]), rtol=2e-5, atol=2e-5)
+    # saturation instead of inf
+    big = torch.full((128, 64), 300.0, device="cuda").half()
+    o4 = torch.empty((128, 64), device="cuda", dtype=torch.float16)
+    netops.gemm_bf16(big, big[:64], o4)
+    torch.cuda.synchronize()
+    assert torch.isfinite(o4.float()).all() and float(o4.float().max()) == 65504.0
+
+
+def test_fp16_rowwise_kernels_and_band_attention():
+    netops = _cuda()
+    m, d = 999, 512
+    x = _rand((m, d), 70, 2.0)
+    x32, xb, ss = torch.empty_like(x), torch.empty((m, d), device="cuda", dtype=torch.float16), torch.empty((m, 4), device="cuda")
+    gamma = _rand((d,), 71).abs() + 0.5
+    netops.resid_prepare(x, x32, xb, ss, gamma=gamma)
+    offs = torch.tensor([0, 8, 24, 72, 512], dtype=torch.int32, device="cuda")
+    xn = torch.zeros((m, 520), device="cuda", dtype=torch.float16)
+    netops.band_norm(x, gamma, offs, xn)
+    torch.cuda.synchronize()
+    y = torch.nn.functional.normalize(x, dim=-1) * math.sqrt(d) * gamma
+    assert torch.allclose(x32, y, rtol=1e-5, atol=1e-5) and torch.equal(xb, x32.half())
+    for a, b in zip(offs.tolist()[:-1], offs.tolist()[1:]):
+        _close_f16(xn[:, a:b], torch.nn.functional.normalize(x[:, a:b], dim=-1) * math.sqrt(b - a) * gamma[a:b], "band_norm fp16")
+    # band attention + gate in half
+    n_seq, f, h, dh = 37, 62, 8, 64
+    q, k, v = (_rand((n_seq * f, h * dh), 72 + i).half() for i in range(3))
+    gates16 = _rand((n_seq * f, 16), 75).half()
+    got = netops.band_attention(q, k, v, n_seq, f, h, dh, gates=gates16[:, :h]).float()
+    shp = (n_seq, f, h, dh)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.view(shp).transpose(1, 2).float(), k.view(shp).transpose(1, 2).float(),
+                                                           v.view(shp).transpose(1, 2).float()).transpose(1, 2)
+    ref = (ref * torch.sigmoid(gates16[:, :h].float()).view(n_seq, f, h, 1)).reshape(n_seq * f, h * dh)
+    assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+    o = _rand((n_seq * f, h * dh), 76).half()
+    want = (o.float().view(-1, h, dh) * torch.sigmoid(gates16[:, :h].float())[:, :, None]).view(-1, h * dh)
+    netops.gate_sigmoid_(o, gates16[:, :h], h, dh)
+    torch.cuda.synchronize()
+    _close_f16(o, want, "gate fp16")
+
+
+def test_roformer_mask_fp16_operands_vs_fp32_modules():
+    """The all-tcgen05 mask() path with IEEE-half operands: ~8x closer to the fp32 module path than bfloat16 operands."""
+    _cuda()
+    from audiolab_b200.configs import RoformerConfig
+    from audiolab_b200.nets.roformer import RoformerMaskNet
+    torch.manual_seed(4321)
+    cfg = RoformerConfig(dim=128, depth=2, heads=4, dim_head=64, chunk_size=441 * 40)
+    net = RoformerMaskNet(cfg).cuda().eval()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    spec = torch.view_as_complex(torch.randn((3, 41, 1025, 2, 2), generator=g)).cuda()
+    ref = torch.view_as_real(net.set_compute_dtype(torch.float32).mask(spec))
+    rel = {}
+    for dt in (torch.bfloat16, torch.float16):
+        got = torch.view_as_real(net.set_compute_dtype(dt).mask(spec))
+        rel[dt] = float((got - ref).norm() / ref.norm())
+    print(f"relative L2 error of the mask: bf16 operands {rel[torch.bfloat16]:.2e}, fp16 operands {rel[torch.float16]:.2e}")
+    assert rel[torch.float16] < 2.5e-3 and rel[torch.float16] < 0.25 * rel[torch.bfloat16]

@@ -96,14 +96,14 @@ extern "C" void emul_gate(void* o, const void* gates, long long n_rows, int head
     const int vec_per_row = heads * dim_head / 8;
     const long long n_vec = n_rows * vec_per_row;
     emul_launch(dim3((unsigned)((n_vec + 255) / 256)), dim3(256), [&] {
-        gate_bf16_kernel(reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
+        gate_h16_kernel<false>(reinterpret_cast<uint4*>(o), reinterpret_cast<const __nv_bfloat16*>(gates), n_vec, vec_per_row, heads, dim_head);
     });
 }
 
 extern "C" void emul_band_attn(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
                                int n_seq, int F, int H, float scale) {
     emul_launch(dim3(n_seq * H), dim3(128), [&] {
-        band_attn_bf16_kernel(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+        band_attn_bf16_kernel<false>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
                               reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(o),
                               reinterpret_cast<const __nv_bfloat16*>(gates), reinterpret_cast<const float2*>(cos_sin), F, H, scale, 0);
     });

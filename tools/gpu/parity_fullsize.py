@@ -2,6 +2,7 @@
 weights seed 4321, mix seed 1236) against the fp32 CPU oracle -- the table VERDICT r1 asked for.  Writes JSON lines.
 
   tc       : tcgen05 GEMM path (bf16 MMA operands, fp32 residual stream + fp32 norm statistics)
+  tc_fp16  : the same path with IEEE-half operands (11 significand bits instead of 8, same tensor-core rate)
   fused    : round-1 path (cuBLAS, bf16 residual stream)                     AUDIOLAB_B200_TC_GEMM=0 semantics
   fp32     : the CUDA fp32 path (parity configuration)
   oracle16 : the ORACLE itself under bf16 autocast on the CPU (the reference's use_autocast=True arithmetic)
@@ -39,7 +40,9 @@ def main():
     print(json.dumps({"oracle_fp32_s": round(time.perf_counter() - t0, 2), "depth": depth}), flush=True)
     pc = RoformerConfig(**dataclasses.asdict(oc))
     out = {}
-    for name, dtype, tc in (("tc", torch.bfloat16, True), ("fused", torch.bfloat16, False), ("fp32", torch.float32, True)):
+    paths = (("tc", torch.bfloat16, True), ("tc_fp16", torch.float16, True), ("fused", torch.bfloat16, False),
+             ("fp32", torch.float32, True))
+    for name, dtype, tc in paths:
         pm = rof.RoformerMaskNet(pc)
         pm.load_state_dict(om.state_dict(), strict=True)
         pm = pm.cuda().eval().set_compute_dtype(dtype)
