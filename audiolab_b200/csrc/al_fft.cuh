@@ -117,6 +117,10 @@ template <> struct Cfg<2> { static constexpr int G = 8, UW = 8; };
 template <> struct Cfg<4> { static constexpr int G = 8, UW = 16; };   // 8 frames = one 32-byte sector of a T-innermost row
 template <> struct Cfg<6> { static constexpr int G = 4, UW = 12; };
 
+// float2 slots reserved in shared memory for the radix-D combine twiddles [(D-1)][513] (a multiple of 32 keeps the unit
+// slots that follow bank-aligned)
+template <int D> struct CtwPad { static constexpr int value = ((D - 1) * 513 + 31) / 32 * 32; };
+
 // ---- spectrogram addressing --------------------------------------------------------------------
 // row = group*channels + ch  (group = chunk, or chunk*stems + stem)
 // layout 0: c64 [rows, T, Fo]; 1: c64 [rows, Fo, T]; 2: f32 [rows*2 (re, im planes), Fo, T];

@@ -320,7 +320,7 @@ class RoformerMaskNet(nn.Module):
         to to_qkv as 16 extra output rows (8 real + zero padding) with its bias."""
         params = (attn.norm.gamma, attn.to_qkv.weight, attn.to_gates.weight, attn.to_gates.bias, attn.to_out[0].weight,
                   ff.net[0].gamma, ff.net[1].weight, ff.net[1].bias, ff.net[4].weight, ff.net[4].bias)
-        key = ("tc", id(attn))
+        key = ("tc", id(attn), self._fused_dtype)
         ver = tuple(p._version for p in params) + (str(params[0].device),)
         hit = self._bf16_cache.get(key)
         if hit is not None and hit[0] == ver:
@@ -411,7 +411,7 @@ class RoformerMaskNet(nn.Module):
         return True
 
     def _grouped_pack(self):
-        key = ("grouped",)
+        key = ("grouped", self._fused_dtype)
         params = list(self.band_split.parameters()) + list(self.mask_estimators.parameters())
         ver = tuple(p._version for p in params) + (str(params[0].device),)
         hit = self._bf16_cache.get(key)
@@ -464,7 +464,7 @@ class RoformerMaskNet(nn.Module):
         x32, xb, ss = st[0], st[1], st[2]
         bt = feats.shape[0]
         nb, d = len(self.band_split.dim_inputs), x32.shape[1]
-        key = ("xn", bt, str(feats.device))
+        key = ("xn", bt, str(feats.device), self._fused_dtype)
         xn = self._rot_cache.get(key)
         if xn is None:
             xn = torch.zeros((bt, pk["ld"]), device=feats.device, dtype=self._fused_dtype)   # padding columns stay zero
