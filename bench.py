@@ -43,6 +43,7 @@ if ROOT not in sys.path:
 
 SR = 44100
 TRACK_SECONDS = 60
+PARITY_DB = {"fp16": 63.61, "bf16": 44.69}     # SI-SDR vs the fp32 oracle at the real size (profiles/r02i_parity_fullsize_fp16.jsonl)
 METRIC = "realtime factor (audio-s/s) of chunked STFT->mask->iSTFT+OLA demix"
 UNIT = "audio-s/s"
 
@@ -57,7 +58,8 @@ def workload_config(n_gpus: int, mode: str) -> dict:
         sharding = "none"
     return {
         "workload": "BS-RoFormer vocals/instrumental (dim 512, depth 12, 62 bands), n_fft=2048 hop=441 stereo, "
-                    "8 s chunks overlap=4, bf16 random-init weights (seed 4321), "
+                    "8 s chunks overlap=4, 16-bit random-init weights (seed 4321; fp16 operands by default, bf16 selectable -- "
+                    "see precision_modes), "
                     f"{TRACK_SECONDS} s of 44.1 kHz synthetic audio per GPU (BASELINE.json configs[1])",
         "n_fft": 2048, "hop": 441, "chunk_samples": 352800, "overlap": 4, "track_seconds": TRACK_SECONDS,
         "sharding": sharding,
@@ -684,6 +686,22 @@ def run_ours(args) -> None:
         h2d = mix_host.numel() * 4 * world
         d2h = 2 * n * 4 * cfg.num_stems
 
+    # ---- the other 16-bit operand format, for context (same kernels) ----------------------------------------------
+    net_dtype = demixer.net.compute_dtype
+    net_dtype_name = "fp16" if net_dtype == torch.float16 else "bf16"
+    other_mode = None
+    if world == 1 and not args.profile_mode:
+        other = "bf16" if net_dtype_name == "fp16" else "fp16"
+        sep2 = Separator(log_level=40, allow_random_init=True, use_autocast=True, device=str(dev),
+                         mdxc_params={"batch_size": args.batch, "overlap": 4, "compute_dtype": other})
+        d2 = sep2.load_model("model_bs_roformer_ep_368_sdr_12.9628.ckpt").demixer
+        mix2 = torch.from_numpy(synth_mix(track_seconds * SR, seed=1236)).to(dev)
+        d2.demix(mix2)
+        ms2 = _timed_passes(torch, lambda: d2.demix(mix2), 2)
+        other_mode = {"name": other, "value": track_seconds * 1e3 / ms2}
+        del sep2, d2, mix2
+        torch.cuda.empty_cache()
+
     # ---- the other BASELINE configurations -----------------------------------------------------------------------
     want = [] if args.profile_mode else parse_configs(args.configs, world)
     for k in ("mix_host", "mix_dev", "span", "sharded"):
@@ -726,8 +744,9 @@ def run_ours(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 mask net (fp32 accumulate, fp32 residual stream), "
-                                                             "f32 STFT/iSTFT/OLA",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": f"{net_dtype_name} operands in the mask net (tcgen05 kind::f16, fp32 accumulate, fp32 residual stream), "
+                     "f32 STFT/iSTFT/OLA",
             "data": "synthetic", "config": workload_config(world, mode),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -752,6 +771,15 @@ def run_ours(args) -> None:
                                      "; band split / mask estimator under bf16 autocast")) if tc else
                                  "dense layers via cuBLAS / cuDNN SDPA (AUDIOLAB_B200_TC_GEMM=0 comparison path)"},
         }
+        if other_mode is not None:
+            line["precision_modes"] = {
+                net_dtype_name: {"value": value, "si_sdr_db_vs_fp32_oracle_full_size": PARITY_DB.get(net_dtype_name)},
+                other_mode["name"]: {"value": other_mode["value"],
+                                     "si_sdr_db_vs_fp32_oracle_full_size": PARITY_DB.get(other_mode["name"])},
+                "note": "same kernels, 16-bit operand format selected by Separator(mdxc_params={'compute_dtype': ...}); SI-SDR "
+                        "figures from profiles/r02i_parity_fullsize_fp16.jsonl (asserted by tests/test_demix_gpu.py::"
+                        "test_roformer_full_size_parity_of_the_16bit_paths); BASELINE.json asks for >= 60 dB",
+            }
         if shard_info is not None:
             line["sharding"] = shard_info
         if tracks_mode is not None:
