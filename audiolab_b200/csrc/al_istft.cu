@@ -23,8 +23,7 @@ istft_kernel(const IstftParams p) {
     constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, NT = UW * 32, N = D * 1024, HW = D / 2;
     AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);     // [1024]
-    float2* s_ctw = s_tw + 1024;                             // [(D-1)*513] combine twiddles (were L2 loads per item)
-    float2* s_slot = s_ctw + CtwPad<D>::value;               // [UW][kSlotF2]
+    float2* s_slot = s_tw + 1024;                            // [UW][kSlotF2]
     float* s_carry = reinterpret_cast<float*>(s_slot + UW * kSlotF2);   // [N - hop], updated in place
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,7 +61,6 @@ istft_kernel(const IstftParams p) {
                               (long long)chunk * p.dst_chunk_stride + place;
 
     for (int i = tid; i < 1024; i += NT) s_tw[i] = p.tw[i];
-    for (int i = tid; i < (D - 1) * 513; i += NT) s_ctw[i] = p.ctw[i];
     for (int i = tid; i < carry_len; i += NT) s_carry[i] = 0.f;
 
     // rounds run past the last frame until the carry has been flushed up to Pb
@@ -117,7 +115,7 @@ istft_kernel(const IstftParams p) {
                     xs[0] = y[0];
 #pragma unroll
                     for (int r = 1; r < D; ++r)
-                        xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], s_ctw[(r - 1) * 513 + kappa]);
+                        xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
                 }
             }
         } else {
@@ -149,7 +147,7 @@ istft_kernel(const IstftParams p) {
             xs[0] = y[0];
 #pragma unroll
             for (int r = 1; r < D; ++r)
-                xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], s_ctw[(r - 1) * 513 + kappa]);
+                xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf] = cmul_conj(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
         };
         int it = tid;
         for (; it + NT < G * 513; it += 2 * NT) {
@@ -359,7 +357,7 @@ static size_t istft_tiling(IstftParams& p, int rows) {
     hpc = hpc > 16 ? hpc : 16;
     p.hops_per_cta = hpc;
     p.segs = (total_hops + hpc - 1) / hpc;
-    return (1024 + CtwPad<D>::value) * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)(N - p.hop) * sizeof(float);
+    return 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)(N - p.hop) * sizeof(float);
 }
 // [emul-end]
 
@@ -371,11 +369,11 @@ static cudaError_t launch_istft_d(const IstftParams& p0, int n_chunks, cudaStrea
     const size_t smem = istft_tiling<D>(p, rows);
     static PerDeviceOnce attr_set;
     if (attr_set.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(istft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set.mark();
     }
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
     istft_kernel<D><<<(unsigned)(rows * p.segs), UW * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError();

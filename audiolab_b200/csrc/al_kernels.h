@@ -52,7 +52,6 @@ struct StftParams {
     int ps;
     int rounds_per_cta;
     int tiles;
-    int rows_total;        // channels * chunks: the kernel is persistent over rows_total * tiles work items
 };
 
 struct IstftParams {

@@ -18,25 +18,19 @@ stft_kernel(const StftParams p) {
     constexpr int G = Cfg<D>::G, UW = Cfg<D>::UW, NT = UW * 32, N = D * 1024, HW = D / 2;
     AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);             // [1024]
-    float2* s_ctw = s_tw + 1024;                                     // [(D-1)*513] combine twiddles (were L2 loads per item)
-    float2* s_slot = s_ctw + CtwPad<D>::value;                           // [UW][kSlotF2]
+    float2* s_slot = s_tw + 1024;                                    // [UW][kSlotF2]
     float* s_stage = reinterpret_cast<float*>(s_slot + UW * kSlotF2);  // [D][ps]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x / p.tiles, tile = blockIdx.x - row * p.tiles;
+    const int chunk = row / p.channels, ch = row - chunk * p.channels;
+    const long long coff = p.chunk_offsets ? p.chunk_offsets[chunk] : p.off0 + (long long)chunk * p.off_step;
+    const float* __restrict__ src = p.track + (long long)ch * p.ch_stride;
     const int ps = p.ps;
     const int span = (G - 1) * p.hop + N;
     const SpecView view{p.spec, p.layout, p.n_frames, p.n_bins_out, p.channels};
 
     for (int i = tid; i < 1024; i += NT) s_tw[i] = p.tw[i];
-    for (int i = tid; i < (D - 1) * 513; i += NT) s_ctw[i] = p.ctw[i];
-
-    // persistent over (row, tile) work items: the tables above are loaded once per CTA, and L1 keeps the window warm
-    const int n_items = p.rows_total * p.tiles;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int row = item / p.tiles, tile = item - row * p.tiles;
-    const int chunk = row / p.channels, ch = row - chunk * p.channels;
-    const long long coff = p.chunk_offsets ? p.chunk_offsets[chunk] : p.off0 + (long long)chunk * p.off_step;
-    const float* __restrict__ src = p.track + (long long)ch * p.ch_stride;
 
     for (int round = 0; round < p.rounds_per_cta; ++round) {
         const int t0 = (tile * p.rounds_per_cta + round) * G;
@@ -50,17 +44,9 @@ stft_kernel(const StftParams p) {
         static_assert(NT % D == 0, "the staging loop relies on NT % D == 0");
         float* __restrict__ sdst = s_stage + (tid % D) * ps + tid / D;
         if (s0 >= 0 && s0 + span <= p.chunk_len && coff + s0 >= 0 && coff + s0 + span <= p.n_valid) {
-            // batches of 8 independent loads per thread: the whole batch is in flight before the first shared-memory store
             const float* __restrict__ g = src + coff + s0;
             int q = 0;
-            for (int i = tid; i < span; i += 8 * NT, q += 8 * (NT / D)) {
-                float v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (i + u * NT < span) ? __ldg(g + i + u * NT) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (i + u * NT < span) sdst[q + u * (NT / D)] = v[u];
-            }
+            for (int i = tid; i < span; i += NT, q += NT / D) sdst[q] = __ldg(g + i);
         } else {
             int q = 0;
             for (int i = tid; i < span; i += NT, q += NT / D) {
@@ -131,7 +117,7 @@ stft_kernel(const StftParams p) {
 #pragma unroll
                     for (int r = 0; r < D; ++r) y[r] = xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf];
 #pragma unroll
-                    for (int r = 1; r < D; ++r) y[r] = cmul(y[r], s_ctw[(r - 1) * 513 + kappa]);
+                    for (int r = 1; r < D; ++r) y[r] = cmul(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
                     SmallDft<D, false>::run(y);
 #pragma unroll
                     for (int q = 0; q < D; ++q) {
@@ -173,7 +159,7 @@ stft_kernel(const StftParams p) {
 #pragma unroll
             for (int r = 0; r < D; ++r) y[r] = xs[(r >> 1) * kSlotF2 + (r & 1) * kXHalf];
 #pragma unroll
-            for (int r = 1; r < D; ++r) y[r] = cmul(y[r], s_ctw[(r - 1) * 513 + kappa]);
+            for (int r = 1; r < D; ++r) y[r] = cmul(y[r], __ldg(p.ctw + (r - 1) * 513 + kappa));
             SmallDft<D, false>::run(y);
 #pragma unroll
             for (int q = 0; q < D; ++q) {
@@ -193,8 +179,6 @@ stft_kernel(const StftParams p) {
             }
         }
     }
-    __syncthreads();   // the next item's staging overwrites the stage / slots this item's combine was reading
-    }  // work items
 }
 
 // launch shape of stft_kernel<D>: fills ps / rounds_per_cta / tiles, returns the dynamic shared memory size
@@ -206,7 +190,7 @@ static size_t stft_tiling(StftParams& p) {
     p.rounds_per_cta = (D == 2) ? 1 : 2;
     const int frames_per_cta = G * p.rounds_per_cta;
     p.tiles = (p.n_frames + frames_per_cta - 1) / frames_per_cta;
-    return (1024 + CtwPad<D>::value) * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)D * p.ps * sizeof(float);
+    return 1024 * sizeof(float2) + (size_t)UW * kSlotF2 * sizeof(float2) + (size_t)D * p.ps * sizeof(float);
 }
 // [emul-end]
 
@@ -217,16 +201,12 @@ static cudaError_t launch_stft_d(const StftParams& p0, int rows, cudaStream_t st
     const size_t smem = stft_tiling<D>(p);
     static PerDeviceOnce attr_set;
     if (attr_set.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(stft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(stft_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set.mark();
     }
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    p.rows_total = rows;
-    const long long items = (long long)rows * p.tiles;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;                     // CTAs that fit one SM's shared memory
-    const long long cap = (long long)sm_count() * per_sm;
-    stft_kernel<D><<<(unsigned)(items < cap ? items : cap), UW * 32, smem, stream>>>(p);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    stft_kernel<D><<<(unsigned)(rows * p.tiles), UW * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }

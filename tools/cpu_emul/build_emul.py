@@ -18,10 +18,7 @@ static int emul_stft_d(StftParams p, int rows) {
     const size_t smem = stft_tiling<D>(p);
     if (smem > sizeof(g_smem)) return -2;
     std::memset(g_smem, 0xFF, sizeof(g_smem));
-    p.rows_total = rows;
-    // fewer CTAs than work items: the persistent loop (several items per CTA) is what gets emulated
-    const int items = rows * p.tiles;
-    emul_launch(dim3(items > 3 ? (items + 2) / 3 : items), dim3(Cfg<D>::UW * 32), [&] { stft_kernel<D>(p); });
+    emul_launch(dim3(rows * p.tiles), dim3(Cfg<D>::UW * 32), [&] { stft_kernel<D>(p); });
     return 0;
 }
 
