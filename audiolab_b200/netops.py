@@ -133,6 +133,21 @@ class GemmArgs(_C.Structure):
 
 
 ACT = {None: 0, "none": 0, "gelu": 1, "tanh": 2}
+
+# bench.py's roofline leg: when set to a list, every al_gemm_bf16 launch is bracketed by CUDA events on its stream and
+# appended as (epilogue name, flops, algorithmic bytes, start event, end event).  None (default) = no events.
+gemm_timer = None
+
+
+def _timed_gemm(kind: str, flops: float, nbytes: float, args, what: str) -> None:
+    if gemm_timer is None:
+        _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), what)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), what)
+    e1.record()
+    gemm_timer.append((kind, flops, nbytes, e0, e1))
 HALF_DTYPES = (torch.bfloat16, torch.float16)     # 16-bit operand formats of the tcgen05 path (same tensor-core rate)
 
 
@@ -203,7 +218,7 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, outs, *, bias: Optional[torch.Te
         args.out[i], args.ldo[i], args.o_group_stride[i] = o.data_ptr(), ldo, ogs
     args.out_split = int(out_split)
     args.max_ctas = int(max_ctas)
-    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16")
+    _timed_gemm("bf16" if act is None else act, 2.0 * g * m * n * k, 2.0 * g * m * (k + n) + 2.0 * g * n * k, args, "al_gemm_bf16")
 
 
 def resid_slab(n: int) -> int:
@@ -236,7 +251,7 @@ def gemm_bf16_glu(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: 
     args.out[0], args.ldo[0], args.o_group_stride[0] = out.data_ptr(), ldo, ogs
     args.out_split = no                 # valid output columns (w may carry zero rows up to a multiple of 16)
     args.max_ctas = int(max_ctas)
-    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16(glu)")
+    _timed_gemm("glu", 2.0 * g * m * n * k, 2.0 * g * m * k + 4.0 * g * m * no + 2.0 * g * n * k, args, "al_gemm_bf16(glu)")
 
 
 def interleave_glu(t: torch.Tensor) -> torch.Tensor:
@@ -305,7 +320,9 @@ def gemm_bf16_residual(a: torch.Tensor, w: torch.Tensor, x32: torch.Tensor, xb: 
     args.max_ctas = int(max_ctas)
     args.no_accumulate = 0 if accumulate else 1
     args.side_row_stride, args.side_group_stride = side_rs, side_gs
-    _lib.check(_lib.lib().al_gemm_bf16(_C.byref(args), _stream()), "al_gemm_bf16(residual)")
+    # A read + x32 read (if accumulating) + x32 write + 16-bit shadow write + weights
+    nbytes = 2.0 * g * m * k + (8.0 if accumulate else 4.0) * g * m * n + 2.0 * g * m * n + 2.0 * g * n * k
+    _timed_gemm("residual", 2.0 * g * m * n * k, nbytes, args, "al_gemm_bf16(residual)")
 
 
 def resid_prepare(x_in: torch.Tensor, x32: torch.Tensor, xb: torch.Tensor, ss: torch.Tensor, *,
