@@ -30,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "al_gemm.h"
@@ -42,9 +44,11 @@ namespace tc {
 constexpr int BM = 128;          // rows of A per tile = tensor memory lanes
 constexpr int BK = 64;           // bf16 elements per 128-byte swizzled row
 constexpr int UK = 16;           // K of one tcgen05.mma kind::f16
-constexpr int kThreads = 320;    // 10 warps: TMA producer, MMA issuer, 8 epilogue
-constexpr int kEpiWarps = 8;
 constexpr int kResSlots = 2;     // EPI_RES: ring of 32-column fp32 chunks per epilogue warp
+// Epilogue warps EW: 8 = two per tensor-memory lane quadrant.  16 (four per quadrant, 3 ring stages to pay for their
+// staging buffers) was measured 12-19 % SLOWER on the K = 512 shapes (profiles/r02l_gemm_epilogue_width.log): these shapes
+// are paced by the depth of the operand ring, not by the epilogue arithmetic.
+constexpr int threads_of(int ew) { return 64 + 32 * ew; }     // + TMA producer warp + MMA issuer warp
 
 struct Tmaps {
     CUtensorMap a, b;
@@ -53,23 +57,24 @@ struct Tmaps {
                         //           swizzle), o[2] = x32 again with a 64 x 128 box for the L2 prefetch
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int EW>
 struct SmemLayout {
     static constexpr int kA = BM * BK * 2;                    // 16 KB
     static constexpr int kB = BN * BK * 2;
     static constexpr int kStage = kA + kB;
     static constexpr int kEpiPerWarp = EPI == EPI_RES ? (kResSlots * 4096 + 2048) : 4096;
     static constexpr int kEpiOff = STAGES * kStage;
-    static constexpr int kBarOff = kEpiOff + kEpiWarps * kEpiPerWarp;
-    static constexpr int kNumBars = 2 * STAGES + 4 + kEpiWarps * kResSlots;
+    static constexpr int kBarOff = kEpiOff + EW * kEpiPerWarp;
+    static constexpr int kNumBars = 2 * STAGES + 4 + EW * kResSlots;
     static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;            // slack for the manual 1024-byte alignment
 };
 
-template <int BN, int STAGES, int EPI, bool F16>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int STAGES, int EPI, bool F16, int EW>
+__global__ void __launch_bounds__(threads_of(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
-    using L = SmemLayout<BN, STAGES, EPI>;
+    using L = SmemLayout<BN, STAGES, EPI, EW>;
+    constexpr int kEpiWarps = EW;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = smem_addr(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;            // 128-byte swizzle atoms are 1024-byte aligned
@@ -127,7 +132,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
                 const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
-                if (EPI == EPI_RES && g.accumulate != 0) {
+                if (EPI == EPI_RES && g.accumulate != 0 && g.pf_x != 0) {
                     // the fp32 residual tile this accumulator will be added to: into L2 now, so that the epilogue's
                     // small ring of TMA loads sees L2 latency, not HBM latency
 #pragma unroll
@@ -183,16 +188,39 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
         // 8 warps: warp w may touch tensor memory lanes 32 (w % 4) .. + 31 only, so two warps share a lane quadrant
         // and split the accumulator's columns (half 0 / half 1).  Two warps per scheduler keep the issue slots busy
         // while one of them waits on tcgen05.ld / shared memory / the TMA store.
-        const int ew = warp - 2;                 // 0..7: private staging buffers / barriers
+        const int ew = warp - 2;                 // 0..EW-1: private staging buffers / barriers
         const int q = warp & 3;                  // tensor memory lane quadrant
-        const int half = ew >> 2;                // which half of the N tile
+        const int half = ew >> 2;                // which column block of the N tile (EW / 4 blocks)
         const uint32_t ebuf = base + L::kEpiOff + (uint32_t)ew * L::kEpiPerWarp;
         unsigned char* ebuf_ptr = base_ptr + L::kEpiOff + ew * L::kEpiPerWarp;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
 
         if constexpr (EPI != EPI_RES) {
-            constexpr int kWarpCols = BN / 2 >= 64 ? BN / 2 : 64;      // columns per warp, in 64-column steps
+            constexpr int kColBlocks = EW / 4;
+            constexpr int kWarpCols = BN / kColBlocks >= 64 ? BN / kColBlocks : 64;   // columns per warp, in 64-column steps
             const int wcol0 = half * kWarpCols;                         // first column of this warp inside the tile
+            // partial sums of squares of this lane's row in tile `t` (the previous residual epilogue left them): fetched one
+            // tile ahead, so that their latency is covered by the current tile's arithmetic
+            const bool ss_vec = (reinterpret_cast<uintptr_t>(g.row_ss) & 15) == 0;
+            auto load_ss = [&](int t) -> float {
+                if (g.row_ss == nullptr || t >= total_tiles) return 1.f;
+                const int grp_ = t / tiles_per_group;
+                const int row_ = ((t - grp_ * tiles_per_group) / g.n_tiles) * BM + q * 32 + lane;
+                if (row_ >= g.M) return 1.f;
+                const float* sp = g.row_ss + ((long long)grp_ * g.side_gs + (long long)row_ * g.side_rs) * g.ss_parts;
+                float ss = 0.f;
+                if (g.ss_parts == 2 && ss_vec) {
+                    const float2 t2 = __ldg(reinterpret_cast<const float2*>(sp));
+                    ss = t2.x + t2.y;
+                } else if (g.ss_parts == 4 && ss_vec) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sp));
+                    ss = (t4.x + t4.y) + (t4.z + t4.w);
+                } else {
+                    for (int p = 0; p < g.ss_parts; ++p) ss += __ldg(sp + p);
+                }
+                return ss;
+            };
+            float ss_cur = load_ss((int)blockIdx.x);
             int it = 0;
             for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
                 const int grp = tile / tiles_per_group;
@@ -201,17 +229,14 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 const int row0 = m_blk * BM + q * 32;
-                const long long row = (long long)row0 + lane;
-                const long long grow = (long long)grp * g.side_gs + row * g.side_rs;   // row of the per-row side inputs
+                const int row = row0 + lane;
+                const float ss_next = load_ss(tile + (int)gridDim.x);
                 float rs = 1.f;
-                if (g.row_ss != nullptr && row < g.M) {
-                    float ss = 0.f;
-                    for (int p = 0; p < g.ss_parts; ++p) ss += __ldg(g.row_ss + grow * g.ss_parts + p);
-                    rs = g.ss_scale / fmaxf(sqrtf(ss), g.ss_eps);
-                }
+                if (g.row_ss != nullptr && row < g.M) rs = g.ss_scale / fmaxf(sqrtf(ss_cur), g.ss_eps);
+                ss_cur = ss_next;
                 const float2 rs2 = make_float2(rs, rs);
                 int pos = 0;
-                if (g.cos_sin != nullptr) pos = (int)((row / g.pos_div) % g.pos_mod);
+                if (g.cos_sin != nullptr) pos = (int)(((uint32_t)row / (uint32_t)g.pos_div) % (uint32_t)g.pos_mod);
                 const int n0 = n_blk * BN;
                 const int n_cols = min(BN, g.N - n0);
                 mbar_wait(tfull_bar(acc), acc_phase);
@@ -319,6 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
             if (lane == 0) bulk_wait<0>();
         } else {
             // ---------------- EPI_RES: x32 += acc + bias ; xb = bf16(x32) ; ss partials ----------------
+            static_assert(EPI != EPI_RES || EW == 8, "the residual epilogue splits the tile over two warps per quadrant");
             // Each warp streams the 32-column chunks of its half of the tile: the fp32 residual chunk arrives by TMA
             // (prefetched into L2 by the producer warp when the tile's main loop started) into a 2-slot ring, is
             // updated in place and leaves by TMA together with its bf16 image.
@@ -463,7 +489,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, in
 
 struct DevInfo {
     int n_sm = 0;
-    bool attr[16] = {};
+    bool attr[24] = {};
 };
 static DevInfo& dev_info(int dev) {
     static DevInfo info[64];
@@ -477,30 +503,31 @@ static DevInfo& dev_info(int dev) {
     return d;
 }
 
-template <int BN, int STAGES, int EPI, bool F16>
+template <int BN, int STAGES, int EPI, bool F16, int EW>
 static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
-    using L = SmemLayout<BN, STAGES, EPI>;
+    using L = SmemLayout<BN, STAGES, EPI, EW>;
     static_assert(L::kDynamic <= 232448, "shared memory budget");
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevInfo& d = dev_info(dev);
     if (!d.attr[slot]) {
-        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, F16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return e;
         d.attr[slot] = true;
     }
     const int total = g.m_tiles * g.n_tiles * g.groups;
     int grid = total < d.n_sm ? total : d.n_sm;
     if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-    gemm_bf16_kernel<BN, STAGES, EPI, F16><<<grid, kThreads, L::kDynamic, stream>>>(tm, g);
+    gemm_bf16_kernel<BN, STAGES, EPI, F16, EW><<<grid, threads_of(EW), L::kDynamic, stream>>>(tm, g);
     count_launch();
     return cudaGetLastError();
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int EW = 8>
 static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
-    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true>(tm, g, slot + 8, stream) : launch_cfg1<BN, STAGES, EPI, false>(tm, g, slot, stream);
+    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true, EW>(tm, g, slot + 12, stream)
+                  : launch_cfg1<BN, STAGES, EPI, false, EW>(tm, g, slot, stream);
 }
 
 }  // namespace tc
@@ -526,6 +553,12 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     g.side_gs = c.side_row_stride > 0 ? c.side_group_stride : c.M;
     g.accumulate = c.no_accumulate ? 0 : 1;
     g.fp16 = c.operand_fp16 ? 1 : 0;
+    {
+        // AL_GEMM_PFX=1: L2 prefetch of the fp32 residual tile when its main loop starts.  Measured SLOWER
+        // (profiles/r02m_gemm_residual_prefetch_variants.log: to_out 1.86 ms with, 1.59 ms without), so off by default.
+        static const int pfx = [] { const char* e = getenv("AL_GEMM_PFX"); return e ? atoi(e) : 0; }();
+        g.pf_x = pfx;
+    }
     const CUtensorMapDataType dt16 = c.operand_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if ((long long)g.m_tiles * g.n_tiles * g.groups > 0x7fffffffll) return "too many tiles";
     Tmaps tm;

@@ -30,6 +30,7 @@ struct GemmArgs {
     long long side_rs, side_gs;   // per-row side arrays (row_ss, ss_out): row index = group * side_gs + row * side_rs
     int accumulate;               // EPI_RES: 0 = start the stream (no residual read)
     int fp16;                     // 16-bit operands / outputs are IEEE half instead of bfloat16
+    int pf_x;                     // EPI_RES: prefetch the fp32 residual tile into L2 when its main loop starts
 };
 
 // Returns NULL on success, else a static message (and the CUDA error, if that is what failed, in *cuda_err).
