@@ -46,6 +46,8 @@ SIGNATURES = {
     "al_gelu_bf16": (C.c_int, [C.c_void_p, c_i64, C.c_void_p]),
     "al_band_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_f32p, c_i64, C.c_int,
                                          C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "al_time_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
     "al_gemm_bf16": (C.c_int, [C.c_void_p, C.c_void_p]),
     "al_band_norm": (C.c_int, [c_f32p, c_i64, c_f32p, c_i32p, C.c_int, C.c_void_p, c_i64, c_i64, C.c_float, C.c_int, C.c_void_p]),
     "al_resid_prepare": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p, c_f32p, c_i64, C.c_int, C.c_int, C.c_float,

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaudiolab_b200.so")
-SOURCES = ["al_capi.cu", "al_stft.cu", "al_stft_pk.cu", "al_istft.cu", "al_istft_pk.cu", "al_ola.cu", "al_resample.cu", "al_netops.cu", "al_attn.cu", "al_gemm.cu"]
+SOURCES = ["al_capi.cu", "al_stft.cu", "al_stft_pk.cu", "al_istft.cu", "al_istft_pk.cu", "al_ola.cu", "al_resample.cu", "al_netops.cu", "al_attn.cu", "al_gemm.cu", "al_fattn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "8",
               "--shared", "-Xcompiler", "-fPIC"]
 

@@ -484,6 +484,23 @@ int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o,
     return AL_OK;
 }
 
+int al_time_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
+                           int64_t n_batch, int seq_len, int inner, int heads, int dim_head, float scale, int fp16,
+                           void* stream) {
+    if (!q || !k || !v || !o) return fail(AL_E_ARG, "al_time_attention_bf16: NULL argument");
+    if (n_batch == 0) return AL_OK;
+    if (n_batch < 0 || heads <= 0 || inner <= 0 || seq_len <= 0) return fail(AL_E_ARG, "al_time_attention_bf16: bad sizes");
+    if (dim_head != 64) return fail(AL_E_UNSUPPORTED, "al_time_attention_bf16: dim_head %d (needs 64)", dim_head);
+    if (gates && gate_ld != 0 && (gate_ld < heads || gate_ld > (1 << 20)))
+        return fail(AL_E_ARG, "al_time_attention_bf16: gate_ld %lld must be 0 (= heads) or >= heads", (long long)gate_ld);
+    cudaError_t ce = cudaSuccess;
+    const char* msg = al::launch_time_attention(q, k, v, o, gates, gate_ld, n_batch, seq_len, inner, heads, dim_head, scale, fp16,
+                                                (cudaStream_t)stream, &ce);
+    if (!msg) return AL_OK;
+    if (ce != cudaSuccess) return cuda_fail(ce, "al_time_attention_bf16");
+    return fail(AL_E_ARG, "al_time_attention_bf16: %s", msg);
+}
+
 int al_gemm_bf16(const al_gemm_args* a, void* stream) {
     if (!a || !a->A || !a->W) return fail(AL_E_ARG, "al_gemm_bf16: NULL argument");
     if (a->M == 0) return AL_OK;

@@ -1,0 +1,553 @@
+// Time-axis attention of the RoFormer mask network on the 5th-generation tensor cores (sm_100a):
+//   o[b, t, f, h, :] = sigmoid(gate[b, t, f, h]) * sum_t' softmax_t'(q[b, t, f, h, :] . k[b, t', f, h, :] * scale) v[b, t', f, h, :]
+// upstream Attention.forward inside the time transformer (driven by MDXCSeparator.demix behind
+// modules/separator/stem_separator.py:281).  Replaces F.scaled_dot_product_attention (cuDNN) + the separate gate pass.
+//
+// q, k, v, o: [B * T * F, H * 64] 16-bit, token (b, t, f) in row (b T + t) F + f -- the token-major layout of the residual
+// stream.  A sequence (b, f, h) is the T rows with row stride F: the TMA tensor map views the buffers as
+// [B][T][F * H][64], so a 128 x 64 tile of one sequence is ONE box and no transposition copy exists on either side.
+//
+// One persistent CTA per SM, three warpgroups, warp-specialised; a work unit is (sequence, pair of 128-row query tiles):
+//   warp 8      producer : TMA loads of the two Q tiles and of the K / V tiles (128 x 64, 128-byte swizzle) into a ring
+//   warp 9      MMA      : one thread, event driven: S_L = Q_L K_j^T (128 x 128 x 64) as soon as softmax group L has taken
+//                          S_L(j-1) out of tensor memory, O_L (+)= P_L V_j (128 x 64 x 128) as soon as P_L(j) is ready
+//                          (warps 8..11 hand their registers to the softmax groups: setmaxnreg 40 / 232)
+//   warps 0..3  softmax group A (query tile 2p), warps 4..7 group B (tile 2p + 1): thread = query row.  The row of S
+//                          comes out of tensor memory once (128 registers), p = 2^(s c - m) with a LAZY reference m: it
+//                          only moves when the row maximum grows by more than 2^8 (then O is rescaled in tensor memory),
+//                          P goes back as the 16-bit A operand of the second product, O accumulates in tensor memory.
+// While group A runs its exponentials the tensor core works for group B and vice versa; the kernel is paced by the
+// MUFU.EX2 rate (16 / clk / SM), not by the tensor pipe (d = 64).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "al_kernels.h"
+#include "al_tc.cuh"
+
+namespace al {
+namespace fa {
+
+using namespace al::tc;
+
+constexpr int kD = 64;            // head dimension
+constexpr int kBM = 128;          // query rows per tile = tensor memory lanes
+constexpr int kBN = 128;          // keys per tile
+constexpr int kStages = 4;        // K / V ring
+constexpr int kThreads = 384;    // softmax groups A, B + the producer / MMA warpgroup
+constexpr int kTile = kBM * kD * 2;           // 16 KB: one 128 x 64 16-bit tile
+constexpr float kLazy = 8.0f;                 // log2 of the growth of the row maximum that triggers a rescale
+
+struct Maps {
+    CUtensorMap q, k, v, o;
+};
+
+struct Args {
+    int T, F, H, B;
+    int n_qt, n_kv, n_pairs;       // query tiles, key tiles per sequence; query tile pairs per sequence
+    long long n_units;             // B * F * H * n_pairs
+    float scale_log2;              // scale * log2(e)
+    const void* gates;             // [rows, gate_ld] 16-bit or NULL
+    long long gate_ld;
+};
+
+struct Smem {
+    static constexpr int kQ = 0;                                   // 2 x 16 KB
+    static constexpr int kKV = 2 * kTile;                          // kStages x (K 16 KB + V 16 KB)
+    static constexpr int kP = kKV + kStages * 2 * kTile;           // 2 x 32 KB (P tile; its first 16 KB stage the O tile)
+    static constexpr int kBar = kP + 2 * 2 * kTile;
+    // barriers: q_full[2] q_empty[2] s_full[2] s_empty[2] p_full[2] o_full[2] k_full[ST] v_full[ST] kv_empty[ST]
+    static constexpr int kNumBars = 12 + 3 * kStages;
+    static constexpr int kTotal = kBar + kNumBars * 8 + 16;
+    static constexpr int kDynamic = kTotal + 1024;
+};
+static_assert(Smem::kDynamic <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// non-blocking probe of an mbarrier phase (the MMA warp polls several barriers)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// instruction descriptor: D fp32, A / B 16-bit (f16 = 0, bf16 = 1), A K-major, B K-major or MN-major (bit 16)
+__device__ __forceinline__ uint32_t idesc(int m, int n, bool f16, bool b_mn_major) {
+    const uint32_t fmt = f16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(kThreads, 1)
+time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw = smem_addr(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_dyn + (base - raw);
+    const uint32_t bars = base + Smem::kBar;
+    auto q_full = [&](int l) { return bars + 8u * l; };
+    auto q_empty = [&](int l) { return bars + 8u * (2 + l); };
+    auto s_full = [&](int l) { return bars + 8u * (4 + l); };
+    auto s_empty = [&](int l) { return bars + 8u * (6 + l); };
+    auto p_full = [&](int l) { return bars + 8u * (8 + l); };
+    auto o_full = [&](int l) { return bars + 8u * (10 + l); };
+    auto k_full = [&](int s) { return bars + 8u * (12 + s); };
+    auto v_full = [&](int s) { return bars + 8u * (12 + kStages + s); };
+    auto kv_empty = [&](int s) { return bars + 8u * (12 + 2 * kStages + s); };
+    const uint32_t tmem_slot = bars + 8u * Smem::kNumBars;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + Smem::kBar + 8 * Smem::kNumBars);
+
+    const int warp = (int)(threadIdx.x >> 5);
+    const int lane = lane_id();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm.q);
+            tma_prefetch_desc(&tm.k);
+            tma_prefetch_desc(&tm.v);
+            tma_prefetch_desc(&tm.o);
+        }
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    } else if (warp == 9 && lane == 0) {
+        for (int l = 0; l < 2; ++l) {
+            mbar_init(q_full(l), 1);
+            mbar_init(q_empty(l), 1);
+            mbar_init(s_full(l), 1);
+            mbar_init(s_empty(l), 4);
+            mbar_init(p_full(l), 4);
+            mbar_init(o_full(l), 1);
+        }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(k_full(s), 1);
+            mbar_init(v_full(s), 1);
+            mbar_init(kv_empty(s), 1);
+        }
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    // tensor memory columns: S_A 0..127, S_B 128..255, O_A 256..319, O_B 320..383
+    auto s_col = [&](int l) { return (uint32_t)(l * kBN); };
+    auto o_col = [&](int l) { return (uint32_t)(2 * kBN + l * kD); };
+
+    const int n_kv = g.n_kv;
+    const int last_cols = g.T - (n_kv - 1) * kBN;                 // valid keys of the last key tile
+    const int last_n16 = (last_cols + 15) & ~15;
+    const int FH = g.F * g.H;
+
+    if (warp >= 8) {
+        // the producer / MMA warpgroup hands its registers to the softmax groups (168 * 384 = 224 * 256 + 56 * 128)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
+    if (warp == 8) {
+        // ================================= TMA producer =================================
+        if (lane == 0) {
+            uint32_t kvc = 0;
+            uint32_t uc[2] = {0, 0};
+            for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+                const long long hs = u / g.n_pairs;
+                const int p = (int)(u - hs * g.n_pairs);
+                const int b = (int)(hs / FH), j = (int)(hs - (long long)b * FH);
+                for (int l = 0; l < 2; ++l) {
+                    const int qt = 2 * p + l;
+                    if (qt >= g.n_qt) continue;
+                    mbar_wait(q_empty(l), (uc[l] & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(q_full(l), (uint32_t)kTile);
+                    tma_load_4d(base + Smem::kQ + (uint32_t)l * kTile, &tm.q, q_full(l), 0, j, qt * kBM, b);
+                    ++uc[l];
+                }
+                for (int jt = 0; jt < n_kv; ++jt, ++kvc) {
+                    const int s = (int)(kvc % kStages);
+                    const uint32_t ph = (kvc / kStages) & 1u;
+                    mbar_wait(kv_empty(s), ph ^ 1u);
+                    const uint32_t kb = base + Smem::kKV + (uint32_t)s * 2 * kTile;
+                    mbar_arrive_expect_tx(k_full(s), (uint32_t)kTile);
+                    tma_load_4d(kb, &tm.k, k_full(s), 0, j, jt * kBN, b);
+                    mbar_arrive_expect_tx(v_full(s), (uint32_t)kTile);
+                    tma_load_4d(kb + kTile, &tm.v, v_full(s), 0, j, jt * kBN, b);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================= MMA issuer (event driven) =================================
+        if (lane == 0) {
+            uint32_t kv0 = 0;                  // ring position of key tile 0 of the current unit
+            uint32_t uc[2] = {0, 0};           // units seen per group
+            uint32_t s_tot[2] = {0, 0};        // S products issued per group (all units)
+            uint32_t pv_tot[2] = {0, 0};       // P V products issued per group
+            for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+                const long long hs = u / g.n_pairs;
+                const int p = (int)(u - hs * g.n_pairs);
+                bool active[2];
+                int s_iss[2] = {0, 0}, pv_iss[2] = {0, 0};
+                bool q_ok[2] = {false, false};
+                for (int l = 0; l < 2; ++l) {
+                    active[l] = 2 * p + l < g.n_qt;
+                    if (active[l]) ++uc[l];
+                    else s_iss[l] = pv_iss[l] = n_kv;
+                }
+                int rel = 0;
+                const long long t0 = clock64();
+                while (rel < n_kv) {
+#pragma unroll
+                    for (int l = 0; l < 2; ++l) {
+                        if (!active[l]) continue;
+                        if (s_iss[l] < n_kv) {
+                            const int jt = s_iss[l];
+                            const uint32_t kvc = kv0 + (uint32_t)jt;
+                            const int st = (int)(kvc % kStages);
+                            if (!q_ok[l]) q_ok[l] = mbar_test(q_full(l), (uc[l] - 1u) & 1u);
+                            // S_l is free when the softmax group has read product number s_tot (completion number s_tot)
+                            if (q_ok[l] && mbar_test(k_full(st), (kvc / kStages) & 1u) &&
+                                (s_tot[l] == 0 || mbar_test(s_empty(l), (s_tot[l] - 1u) & 1u))) {
+                                tc_fence_after();
+                                const int n16 = jt == n_kv - 1 ? last_n16 : kBN;
+                                const uint32_t id = idesc(kBM, n16, F16, false);
+                                const uint64_t a_desc = umma_desc_sw128(base + Smem::kQ + (uint32_t)l * kTile);
+                                const uint64_t b_desc = umma_desc_sw128(base + Smem::kKV + (uint32_t)st * 2 * kTile);
+#pragma unroll
+                                for (int k = 0; k < kD / 16; ++k)
+                                    umma_bf16_ss(tmem_base + s_col(l), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), id,
+                                                 (uint32_t)(k != 0));
+                                umma_commit(s_full(l));
+                                ++s_iss[l];
+                                ++s_tot[l];
+                                if (s_iss[l] == n_kv) umma_commit(q_empty(l));       // Q tile free once the last S has read it
+                            }
+                        }
+                        if (pv_iss[l] < s_iss[l]) {
+                            const int jt = pv_iss[l];
+                            const uint32_t kvc = kv0 + (uint32_t)jt;
+                            const int st = (int)(kvc % kStages);
+                            if (mbar_test(p_full(l), pv_tot[l] & 1u) && mbar_test(v_full(st), (kvc / kStages) & 1u)) {
+                                tc_fence_after();
+                                const int n16 = jt == n_kv - 1 ? last_n16 : kBN;
+                                const uint32_t id = idesc(kBM, kD, F16, true);
+                                const uint32_t pb = base + Smem::kP + (uint32_t)l * 2 * kTile;
+                                const uint32_t vb = base + Smem::kKV + (uint32_t)st * 2 * kTile + kTile;
+                                for (int kk = 0; kk < n16 / 16; ++kk) {
+                                    // A = P: K-major, two 64-column swizzle atoms of 16 KB; B = V: MN-major, 16 keys = 2 KB
+                                    const uint64_t a_desc = umma_desc_sw128(pb + (uint32_t)(kk >> 2) * kTile) + (uint64_t)(2 * (kk & 3));
+                                    const uint64_t b_desc = umma_desc_sw128(vb + (uint32_t)kk * 2048u);
+                                    umma_bf16_ss(tmem_base + o_col(l), a_desc, b_desc, id, (uint32_t)((jt | kk) != 0));
+                                }
+                                umma_commit(o_full(l));
+                                ++pv_iss[l];
+                                ++pv_tot[l];
+                            }
+                        }
+                    }
+                    while (rel < n_kv && s_iss[0] > rel && s_iss[1] > rel && pv_iss[0] > rel && pv_iss[1] > rel) {
+                        umma_commit(kv_empty((int)((kv0 + (uint32_t)rel) % kStages)));
+                        ++rel;
+                    }
+                    if (clock64() - t0 > 8000000000ll) __trap();
+                }
+                kv0 += (uint32_t)n_kv;
+            }
+        }
+    } else if (warp < 8) {
+        // ================================= softmax groups =================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int l = warp >> 2;                          // group A / B
+        const int qd = warp & 3;                          // tensor memory lane quadrant of this warp
+        const int row = qd * 32 + lane;                   // query row inside the tile
+        const int gtid = (int)threadIdx.x - l * 128;      // 0..127 inside the group
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const uint32_t pbuf = base + Smem::kP + (uint32_t)l * 2 * kTile;
+        unsigned char* pbuf_ptr = base_ptr + Smem::kP + l * 2 * kTile;
+        uint32_t n_s = 0, n_o = 0;                        // completions of s_full / o_full consumed so far
+        for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+            const long long hs = u / g.n_pairs;
+            const int p = (int)(u - hs * g.n_pairs);
+            const int qt = 2 * p + l;
+            if (qt >= g.n_qt) continue;
+            const int b = (int)(hs / FH), j = (int)(hs - (long long)b * FH);
+            const int t = qt * kBM + row;
+            const bool warp_valid = qt * kBM + qd * 32 < g.T;     // any valid query row in this warp
+            float gate = 1.f;
+            if (g.gates != nullptr && t < g.T) {
+                const int f = j / g.H, h = j - f * g.H;
+                const long long grow = ((long long)b * g.T + t) * g.F + f;
+                if (F16) gate = __half2float(reinterpret_cast<const __half*>(g.gates)[grow * g.gate_ld + h]);
+                else gate = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g.gates)[grow * g.gate_ld + h]);
+                gate = sigmoid_fast(gate);
+            }
+            float m_ref = 0.f, lsum = 0.f;
+            for (int jt = 0; jt < n_kv; ++jt) {
+                const int ncols = jt == n_kv - 1 ? last_cols : kBN;
+                const int n16 = (ncols + 15) & ~15;
+                uint32_t s[4][32];
+                mbar_wait(s_full(l), n_s & 1u);
+                ++n_s;
+                tc_fence_after();
+                if (warp_valid) {
+                    const uint32_t ta = lane_taddr + s_col(l);
+                    tmem_ld_32x32(ta, s[0]);
+                    if (n16 > 32) tmem_ld_32x32(ta + 32, s[1]);
+                    if (n16 > 64) tmem_ld_32x32(ta + 64, s[2]);
+                    if (n16 > 96) tmem_ld_32x32(ta + 96, s[3]);
+                    tmem_wait_ld();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty(l));          // S_l may be overwritten by the next product
+                bool o_waited = false;
+                if (warp_valid) {
+                    // ---- row maximum over the valid keys (columns >= ncols of the last tile are zero-filled keys)
+                    if (ncols < kBN) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i >= ncols) s[c][i] = 0xff800000u;          // -inf
+                    }
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < n16) {
+                            float m0 = __uint_as_float(s[c][0]), m1 = __uint_as_float(s[c][1]);
+#pragma unroll
+                            for (int i = 2; i < 32; i += 2) {
+                                m0 = fmaxf(m0, __uint_as_float(s[c][i]));
+                                m1 = fmaxf(m1, __uint_as_float(s[c][i + 1]));
+                            }
+                            mx = fmaxf(mx, fmaxf(m0, m1));
+                        }
+                    }
+                    mx *= g.scale_log2;
+                    if (jt == 0) {
+                        m_ref = mx;
+                    } else {
+                        const bool need = mx > m_ref + kLazy;
+                        if (__any_sync(0xffffffffu, need)) {
+                            // the reference moves: rescale the running sum and the accumulator in tensor memory
+                            const float alpha = need ? fast_ex2(m_ref - mx) : 1.f;
+                            if (need) m_ref = mx;
+                            lsum *= alpha;
+                            mbar_wait(o_full(l), n_o & 1u);      // P V (jt - 1) has finished writing O_l
+                            ++n_o;
+                            o_waited = true;
+                            tc_fence_after();
+                            for (int c = 0; c < kD / 8; ++c) {            // rare path: 8 columns at a time, few registers
+                                uint32_t o[8];
+                                tmem_ld_32x8(lane_taddr + o_col(l) + (uint32_t)(c * 8), o);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                                tmem_st_32x8(lane_taddr + o_col(l) + (uint32_t)(c * 8), o);
+                            }
+                            tmem_wait_st();
+                        }
+                    }
+                    // ---- p = 2^(s c - m), row sum in fp32, P as 16-bit pairs (in place: s[c][i] <- pair i of chunk c)
+                    const float2 sc2 = make_float2(g.scale_log2, g.scale_log2);
+                    const float2 nm2 = make_float2(-m_ref, -m_ref);
+                    float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < n16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])),
+                                                            sc2, nm2);
+                                const float2 e = make_float2(fast_ex2(x.x), fast_ex2(x.y));
+                                acc2 = __fadd2_rn(acc2, e);
+                                s[c][i] = pack16<F16>(e.x, e.y);
+                            }
+                        }
+                    }
+                    lsum += acc2.x + acc2.y;
+                }
+                if (jt > 0 && !o_waited) {
+                    mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: the buffer is free
+                    ++n_o;
+                } else if (jt == 0) {
+                    // the O tile of the previous unit was staged in this buffer: its TMA store must have read it
+                    if (gtid == 0) bulk_wait_read<0>();
+                    named_bar_sync(1 + l, 128);
+                }
+                if (warp_valid) {
+                    // P tile, K-major with the 128-byte swizzle (two 64-column atoms of 16 KB): row r, 16-byte chunk c16
+                    unsigned char* prow = pbuf_ptr + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < n16) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c16 = (c & 1) * 4 + i;                  // chunk inside the atom (8 columns each)
+                                const uint4 v4 = make_uint4(s[c][4 * i], s[c][4 * i + 1], s[c][4 * i + 2], s[c][4 * i + 3]);
+                                *reinterpret_cast<uint4*>(prow + (c >> 1) * kTile + ((c16 ^ (row & 7)) << 4)) = v4;
+                            }
+                        }
+                    }
+                    fence_proxy_async();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full(l));
+            }
+            // ---- epilogue of the unit: O / l * sigmoid(gate) -> 16-bit tile -> TMA store
+            mbar_wait(o_full(l), n_o & 1u);
+            ++n_o;
+            tc_fence_after();
+            if (warp_valid) {
+                const float inv = gate / lsum;
+                unsigned char* orow = pbuf_ptr + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(lane_taddr + o_col(l) + (uint32_t)(c * 32), o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v4;
+                        v4.x = pack16<F16>(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                        v4.y = pack16<F16>(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                        v4.z = pack16<F16>(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                        v4.w = pack16<F16>(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                        const int c16 = c * 4 + i;
+                        *reinterpret_cast<uint4*>(orow + ((c16 ^ (row & 7)) << 4)) = v4;
+                    }
+                }
+                fence_proxy_async();
+            }
+            tc_fence_before();
+            named_bar_sync(1 + l, 128);
+            if (gtid == 0) {
+                tma_store_4d(&tm.o, pbuf, 0, j, qt * kBM, b);
+                bulk_commit();
+            }
+        }
+        if (gtid == 0) bulk_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// [B][T][F * H][64] view of a token-major [B * T * F, H * 64] buffer; box = one 128 x 64 tile of one (b, f, h) sequence
+static bool make_map(CUtensorMap* m, const void* ptr, bool fp16, long long B, long long T, long long FH) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)FH, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)(kD * 2), (cuuint64_t)(FH * kD * 2), (cuuint64_t)(T * FH * kD * 2)};
+    cuuint32_t box[4] = {(cuuint32_t)kD, 1u, (cuuint32_t)kBM, 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return fn(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace fa
+
+const char* launch_time_attention(const void* q, const void* k, const void* v, void* o, const void* gates, long long gate_ld,
+                                  long long n_batch, int seq_len, int inner, int heads, int dim_head, float scale, int fp16,
+                                  cudaStream_t stream, cudaError_t* cuda_err) {
+    using namespace fa;
+    *cuda_err = cudaSuccess;
+    if (dim_head != kD) return "dim_head must be 64";
+    if (n_batch <= 0 || seq_len <= 0 || inner <= 0 || heads <= 0) return "bad sizes";
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(o)) & 15)
+        return "q, k, v, o must be 16-byte aligned";
+    const long long FH = (long long)inner * heads;
+    if (FH > 0x7fffffffll || n_batch > 0x7fffffffll) return "too many sequences";
+    Maps tm;
+    if (!make_map(&tm.q, q, fp16 != 0, n_batch, seq_len, FH) || !make_map(&tm.k, k, fp16 != 0, n_batch, seq_len, FH) ||
+        !make_map(&tm.v, v, fp16 != 0, n_batch, seq_len, FH) || !make_map(&tm.o, o, fp16 != 0, n_batch, seq_len, FH))
+        return "cuTensorMapEncodeTiled failed";
+    Args g{};
+    g.T = seq_len; g.F = inner; g.H = heads; g.B = (int)n_batch;
+    g.n_qt = (seq_len + kBM - 1) / kBM;
+    g.n_kv = (seq_len + kBN - 1) / kBN;
+    g.n_pairs = (g.n_qt + 1) / 2;
+    g.n_units = n_batch * FH * g.n_pairs;
+    g.scale_log2 = scale * 1.4426950408889634f;
+    g.gates = gates;
+    g.gate_ld = gates != nullptr ? (gate_ld > 0 ? gate_ld : heads) : 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { *cuda_err = e; return "cudaGetDevice failed"; }
+    static std::mutex mu;
+    static bool attr[64][2] = {};
+    static int n_sm[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (n_sm[dev & 63] == 0) {
+            cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+            if (n_sm[dev & 63] <= 0) n_sm[dev & 63] = 148;
+        }
+        if (!attr[dev & 63][fp16 ? 1 : 0]) {
+            e = fp16 ? cudaFuncSetAttribute(time_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kDynamic)
+                     : cudaFuncSetAttribute(time_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kDynamic);
+            if (e != cudaSuccess) { *cuda_err = e; return "cudaFuncSetAttribute failed"; }
+            attr[dev & 63][fp16 ? 1 : 0] = true;
+        }
+    }
+    const long long grid = g.n_units < n_sm[dev & 63] ? g.n_units : n_sm[dev & 63];
+    if (fp16) time_attn_kernel<true><<<(unsigned)grid, kThreads, Smem::kDynamic, stream>>>(tm, g);
+    else time_attn_kernel<false><<<(unsigned)grid, kThreads, Smem::kDynamic, stream>>>(tm, g);
+    count_launch();
+    *cuda_err = cudaGetLastError();
+    return *cuda_err == cudaSuccess ? nullptr : "launch failed";
+}
+
+}  // namespace al

@@ -167,6 +167,11 @@ cudaError_t launch_gelu_bf16(void* x, long long n, cudaStream_t stream);
 cudaError_t launch_band_attn_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, const float* cos_sin,
                                   long long n_seq, int F, int heads, float scale, int gate_ld, int fp16, cudaStream_t stream);
 
+// csrc/al_fattn.cu: returns NULL on success, else a static message (and the CUDA error, if that is what failed, in *cuda_err)
+const char* launch_time_attention(const void* q, const void* k, const void* v, void* o, const void* gates, long long gate_ld,
+                                  long long n_batch, int seq_len, int inner, int heads, int dim_head, float scale, int fp16,
+                                  cudaStream_t stream, cudaError_t* cuda_err);
+
 cudaError_t launch_env(const float* window_raw, int n_fft, int hop, int n_frames_total, float* inv_env,
                        cudaStream_t stream);
 

@@ -109,6 +109,35 @@ def band_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int
     return o
 
 
+def time_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_batch: int, seq_len: int, inner: int, heads: int,
+                   dim_head: int, gates: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(dim_head)) v per (batch, inner index, head) along the seq_len axis of token-major
+    [n_batch * seq_len * inner, heads * dim_head] buffers -- token (b, t, i) in row (b * seq_len + t) * inner + i -- on the
+    tcgen05 tensor cores (al_fattn.cu; dim_head == 64, any seq_len).  With `gates` [rows, heads] the output is also multiplied
+    by sigmoid(gates) per (token, head).  Returns a new tensor of q's shape."""
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda:
+            raise RuntimeError("audiolab_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if t.dtype not in HALF_DTYPES or t.dim() != 2 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous bf16 / fp16 [rows, cols] tensor")
+    fp16 = _half_kind(q, k, v)
+    if q.shape != k.shape or q.shape != v.shape or tuple(q.shape) != (n_batch * seq_len * inner, heads * dim_head):
+        raise ValueError("q, k, v must be [n_batch * seq_len * inner, heads * dim_head]")
+    gate_ld = 0
+    if gates is not None:
+        if (not gates.is_cuda or gates.dtype != q.dtype or tuple(gates.shape) != (q.shape[0], heads)
+                or gates.stride(1) != 1):
+            raise ValueError("gates must be a CUDA [rows, heads] tensor of q's dtype with unit column stride")
+        gate_ld = gates.stride(0)
+    o = torch.empty_like(q)
+    _lib.check(_lib.lib().al_time_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                                 None if gates is None else gates.data_ptr(), int(gate_ld), int(n_batch),
+                                                 int(seq_len), int(inner), int(heads), int(dim_head), float(dim_head) ** -0.5,
+                                                 fp16, _stream()),
+               "al_time_attention_bf16")
+    return o
+
+
 # ---- K4: tcgen05 GEMM with fused epilogues (csrc/al_gemm.cu) ---------------------------------------------------
 import ctypes as _C
 

@@ -201,6 +201,18 @@ int al_gelu_bf16(void* x, int64_t n, void* stream);
 int al_band_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
                            const float* cos_sin, int64_t n_seq, int seq_len, int heads, int dim_head, float scale, int fp16,
                            void* stream);
+/*
+ * al_time_attention_bf16 -- upstream Attention.forward of the time-axis transformer (csrc/al_fattn.cu, tcgen05 flash
+ * attention): softmax(q k^T * scale) v per (batch, inner index, head) over the seq_len positions of the sequence, then
+ * o *= sigmoid(gate).  q, k, v, o [n_batch * seq_len * inner, heads * 64] 16-bit (bfloat16, or IEEE half with fp16 = 1),
+ * token (b, t, i) in row (b * seq_len + t) * inner + i: for the RoFormer inner = number of bands, so consecutive positions
+ * of one sequence are `inner` rows apart and no transposition copy is needed on either side (the reference path runs
+ * rearrange 'b t f d -> (b f) t d' + F.scaled_dot_product_attention + gate multiply + rearrange back).
+ * gates (nullable) [rows, heads] with row stride gate_ld (0 = heads).  dim_head = 64; any seq_len.
+ */
+int al_time_attention_bf16(const void* q, const void* k, const void* v, void* o, const void* gates, int64_t gate_ld,
+                           int64_t n_batch, int seq_len, int inner, int heads, int dim_head, float scale, int fp16,
+                           void* stream);
 
 /*
  * al_gemm_bf16 -- K4: one nn.Linear (or a batch of `groups` of them) of the RoFormer mask network on the tcgen05

@@ -255,6 +255,62 @@ def test_band_attention_kernel(cuda, F_, H, n_seq):
     assert float((got - ref).abs().max()) <= 2 ** -6 * float(ref.abs().max())
 
 
+def ref_time_attention(q, k, v, n_batch, seq_len, inner, heads, dh, gates=None):
+    """fp32 definition of al_time_attention_bf16: attention along t of token-major rows (b, t, i), per (b, i, head)."""
+    shp = (n_batch, seq_len, inner * heads, dh)
+    o = F.scaled_dot_product_attention(q.view(shp).transpose(1, 2).float(), k.view(shp).transpose(1, 2).float(),
+                                       v.view(shp).transpose(1, 2).float())
+    o = o.transpose(1, 2).reshape(q.shape)
+    if gates is not None:
+        o = (o.view(-1, heads, dh) * torch.sigmoid(gates.float())[:, :, None]).reshape(q.shape)
+    return o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,T,I,H", [(2, 801, 3, 2), (1, 128, 1, 1), (1, 129, 2, 1), (3, 33, 5, 2), (1, 1, 1, 1), (2, 300, 2, 3),
+                                     (1, 1000, 1, 2), (1, 256, 7, 1)])
+def test_time_attention_kernel(cuda, B, T, I, H, dtype):
+    """csrc/al_fattn.cu (tcgen05 flash attention along the time axis, gate folded in) against fp32 torch SDPA of the same
+    16-bit inputs.  Tolerance: the output is rounded to 16 bits (2^-11 / 2^-8 relative) and P is a 16-bit operand."""
+    import audiolab_b200.netops as netops
+    g = torch.Generator().manual_seed(B * 1000 + T + I + H)
+    q, k, v = (torch.randn(B * T * I, H * 64, generator=g).to(dtype).to(cuda) for _ in range(3))
+    gates = (2 * torch.randn(B * T * I, 16, generator=g)).to(dtype).to(cuda)[:, :H]      # strided rows, as in the network
+    got = netops.time_attention(q, k, v, B, T, I, H, 64, gates=gates).float()
+    ref = ref_time_attention(q, k, v, B, T, I, H, 64, gates)
+    tol = (2 ** -9 if dtype == torch.float16 else 2 ** -6) * float(ref.abs().max())
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= tol
+    got2 = netops.time_attention(q, k, v, B, T, I, H, 64).float()                         # no gate
+    ref2 = ref_time_attention(q, k, v, B, T, I, H, 64)
+    assert float((got2 - ref2).abs().max()) <= tol
+
+
+@pytest.mark.gpu
+def test_time_attention_kernel_rescales_when_the_row_maximum_grows(cuda):
+    """Scores that grow along the key axis by far more than 2^8 per key tile: the lazy reference of the online softmax must
+    move and the accumulator in tensor memory must be rescaled (the rare path of al_fattn.cu)."""
+    import audiolab_b200.netops as netops
+    B, T, I, H = 1, 700, 2, 2
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(B * T * I, H * 64, generator=g)
+    k = torch.randn(B * T * I, H * 64, generator=g)
+    v = torch.randn(B * T * I, H * 64, generator=g)
+    # key t = q-direction-independent noise + a component along a fixed direction that grows with t; queries have a
+    # positive component on that direction, so the maximum of row i sits near the last keys and rises tile after tile
+    d = torch.zeros(H * 64)
+    d[::2] = 1.0
+    t_idx = (torch.arange(B * T * I) // I) % T
+    k = 0.3 * k + d[None, :] * (t_idx[:, None].float() / 40.0)
+    q = 0.3 * q + d[None, :] * 0.5
+    q, k, v = (x.to(torch.float16).to(cuda) for x in (q, k, v))
+    got = netops.time_attention(q, k, v, B, T, I, H, 64).float()
+    ref = ref_time_attention(q, k, v, B, T, I, H, 64)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+
+
 # ---- host logic of the tcgen05 path (nets/roformer.py::_axial_tc) with the GEMM replaced by its torch definition ----
 def ref_gemm_bf16(a, w, outs, *, bias=None, row_ss=None, ss_scale=1.0, ss_eps=1e-12, cos_sin=None, pos_div=1, pos_mod=1,
                   rot_cols=0, act=None, out_split=0, max_ctas=0):
