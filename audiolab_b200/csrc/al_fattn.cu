@@ -8,14 +8,15 @@
 // [B][T][F * H][64], so a 128 x 64 tile of one sequence is ONE box and no transposition copy exists on either side.
 //
 // One persistent CTA per SM, three warpgroups, warp-specialised; a work unit is (sequence, pair of 128-row query tiles):
-//   warp 8      producer : TMA loads of the two Q tiles and of the K / V tiles (128 x 64, 128-byte swizzle) into a ring
-//   warp 9      MMA      : one thread, event driven: S_L = Q_L K_j^T (128 x 128 x 64) as soon as softmax group L has taken
-//                          S_L(j-1) out of tensor memory, O_L (+)= P_L V_j (128 x 64 x 128) as soon as P_L(j) is ready
-//                          (warps 8..11 hand their registers to the softmax groups: setmaxnreg 40 / 232)
-//   warps 0..3  softmax group A (query tile 2p), warps 4..7 group B (tile 2p + 1): thread = query row.  The row of S
-//                          comes out of tensor memory once (128 registers), p = 2^(s c - m) with a LAZY reference m: it
-//                          only moves when the row maximum grows by more than 2^8 (then O is rescaled in tensor memory),
-//                          P goes back as the 16-bit A operand of the second product, O accumulates in tensor memory.
+//   warp 8       producer : TMA loads of the two Q tiles and of the K / V tiles (128 x 64, 128-byte swizzle) into a ring
+//   warps 9, 10  MMA issuers of softmax group A / B (one thread each, blocking waits in a fixed order):
+//                           S_L(j+1) = Q_L K_{j+1}^T (128 x 128 x 64) as soon as group L has taken S_L(j) out of tensor
+//                           memory, O_L (+)= P_L(j) V_j (128 x 64 x 128, P read from TENSOR MEMORY) when P_L(j) is ready
+//                           (warps 8..11 hand their registers to the softmax groups: setmaxnreg 56 / 224)
+//   warps 0..3   softmax group A (query tile 2p), warps 4..7 group B (tile 2p + 1): thread = query row.  The row of S
+//                           comes out of tensor memory once (128 registers), p = 2^(s c - m) with a LAZY reference m: it
+//                           only moves when the row maximum grows by more than 2^8 (then O is rescaled in tensor memory),
+//                           P goes back to tensor memory as packed 16-bit pairs (tcgen05.st), O accumulates in tensor memory.
 // While group A runs its exponentials the tensor core works for group B and vice versa; the kernel is paced by the
 // MUFU.EX2 rate (16 / clk / SM), not by the tensor pipe (d = 64).
 #include <cuda.h>
@@ -38,7 +39,7 @@ using namespace al::tc;
 constexpr int kD = 64;            // head dimension
 constexpr int kBM = 128;          // query rows per tile = tensor memory lanes
 constexpr int kBN = 128;          // keys per tile
-constexpr int kStages = 4;        // K / V ring
+constexpr int kStages = 5;        // K / V ring
 constexpr int kThreads = 384;    // softmax groups A, B + the producer / MMA warpgroup
 constexpr int kTile = kBM * kD * 2;           // 16 KB: one 128 x 64 16-bit tile
 constexpr float kLazy = 8.0f;                 // log2 of the growth of the row maximum that triggers a rescale
@@ -59,8 +60,8 @@ struct Args {
 struct Smem {
     static constexpr int kQ = 0;                                   // 2 x 16 KB
     static constexpr int kKV = 2 * kTile;                          // kStages x (K 16 KB + V 16 KB)
-    static constexpr int kP = kKV + kStages * 2 * kTile;           // 2 x 32 KB (P tile; its first 16 KB stage the O tile)
-    static constexpr int kBar = kP + 2 * 2 * kTile;
+    static constexpr int kO = kKV + kStages * 2 * kTile;           // 2 x 16 KB: O tiles on their way out (TMA store)
+    static constexpr int kBar = kO + 2 * kTile;
     // barriers: q_full[2] q_empty[2] s_full[2] s_empty[2] p_full[2] o_full[2] k_full[ST] v_full[ST] kv_empty[ST]
     static constexpr int kNumBars = 12 + 3 * kStages;
     static constexpr int kTotal = kBar + kNumBars * 8 + 16;
@@ -102,6 +103,27 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 x 16, 16-bit) sits in tensor memory, lane = row, one 32-bit column
+// = two consecutive K elements (low half first)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -157,7 +179,7 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(k_full(s), 1);
             mbar_init(v_full(s), 1);
-            mbar_init(kv_empty(s), 1);
+            mbar_init(kv_empty(s), 2);            // one arrival per MMA issuer
         }
         fence_mbar_init();
     }
@@ -165,9 +187,10 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    // tensor memory columns: S_A 0..127, S_B 128..255, O_A 256..319, O_B 320..383
+    // tensor memory columns: S_A 0..127, S_B 128..255, O_A 256..319, O_B 320..383, P_A 384..447, P_B 448..511 (16-bit pairs)
     auto s_col = [&](int l) { return (uint32_t)(l * kBN); };
     auto o_col = [&](int l) { return (uint32_t)(2 * kBN + l * kD); };
+    auto p_col = [&](int l) { return (uint32_t)(2 * kBN + 2 * kD + l * (kBN / 2)); };
 
     const int n_kv = g.n_kv;
     const int last_cols = g.T - (n_kv - 1) * kBN;                 // valid keys of the last key tile
@@ -207,82 +230,69 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                 }
             }
         }
-    } else if (warp == 9) {
-        // ================================= MMA issuer (event driven) =================================
+    } else if (warp == 9 || warp == 10) {
+        // ================================= MMA issuer of group l =================================
         if (lane == 0) {
-            uint32_t kv0 = 0;                  // ring position of key tile 0 of the current unit
-            uint32_t uc[2] = {0, 0};           // units seen per group
-            uint32_t s_tot[2] = {0, 0};        // S products issued per group (all units)
-            uint32_t pv_tot[2] = {0, 0};       // P V products issued per group
+            const int l = warp - 9;
+            uint32_t kvc = 0;                  // ring position of key tile 0 of the current unit
+            uint32_t n_q = 0, n_se = 0, n_pf = 0, n_s = 0;     // completions consumed: q_full, s_empty, p_full; S products issued
+            const uint64_t q_desc = umma_desc_sw128(base + Smem::kQ + (uint32_t)l * kTile);
+            const uint32_t id_pv = idesc(kBM, kD, F16, true);
+            const uint32_t s_tmem = tmem_base + s_col(l), o_tmem = tmem_base + o_col(l), p_tmem = tmem_base + p_col(l);
+            auto issue_s = [&](uint32_t kv, int jt) {
+                const int st = (int)(kv % kStages);
+                mbar_wait(k_full(st), (kv / kStages) & 1u);
+                if (n_s != 0) {                                   // S_l is free once the group has read the previous product
+                    mbar_wait(s_empty(l), n_se & 1u);
+                    ++n_se;
+                }
+                tc_fence_after();
+                const uint32_t id = idesc(kBM, jt == n_kv - 1 ? last_n16 : kBN, F16, false);
+                const uint64_t b_desc = umma_desc_sw128(base + Smem::kKV + (uint32_t)st * 2 * kTile);
+#pragma unroll
+                for (int k = 0; k < kD / 16; ++k)
+                    umma_bf16_ss(s_tmem, q_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), id, (uint32_t)(k != 0));
+                umma_commit(s_full(l));
+                ++n_s;
+            };
             for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
                 const long long hs = u / g.n_pairs;
                 const int p = (int)(u - hs * g.n_pairs);
-                bool active[2];
-                int s_iss[2] = {0, 0}, pv_iss[2] = {0, 0};
-                bool q_ok[2] = {false, false};
-                for (int l = 0; l < 2; ++l) {
-                    active[l] = 2 * p + l < g.n_qt;
-                    if (active[l]) ++uc[l];
-                    else s_iss[l] = pv_iss[l] = n_kv;
-                }
-                int rel = 0;
-                const long long t0 = clock64();
-                while (rel < n_kv) {
-#pragma unroll
-                    for (int l = 0; l < 2; ++l) {
-                        if (!active[l]) continue;
-                        if (s_iss[l] < n_kv) {
-                            const int jt = s_iss[l];
-                            const uint32_t kvc = kv0 + (uint32_t)jt;
-                            const int st = (int)(kvc % kStages);
-                            if (!q_ok[l]) q_ok[l] = mbar_test(q_full(l), (uc[l] - 1u) & 1u);
-                            // S_l is free when the softmax group has read product number s_tot (completion number s_tot)
-                            if (q_ok[l] && mbar_test(k_full(st), (kvc / kStages) & 1u) &&
-                                (s_tot[l] == 0 || mbar_test(s_empty(l), (s_tot[l] - 1u) & 1u))) {
-                                tc_fence_after();
-                                const int n16 = jt == n_kv - 1 ? last_n16 : kBN;
-                                const uint32_t id = idesc(kBM, n16, F16, false);
-                                const uint64_t a_desc = umma_desc_sw128(base + Smem::kQ + (uint32_t)l * kTile);
-                                const uint64_t b_desc = umma_desc_sw128(base + Smem::kKV + (uint32_t)st * 2 * kTile);
-#pragma unroll
-                                for (int k = 0; k < kD / 16; ++k)
-                                    umma_bf16_ss(tmem_base + s_col(l), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), id,
-                                                 (uint32_t)(k != 0));
-                                umma_commit(s_full(l));
-                                ++s_iss[l];
-                                ++s_tot[l];
-                                if (s_iss[l] == n_kv) umma_commit(q_empty(l));       // Q tile free once the last S has read it
-                            }
-                        }
-                        if (pv_iss[l] < s_iss[l]) {
-                            const int jt = pv_iss[l];
-                            const uint32_t kvc = kv0 + (uint32_t)jt;
-                            const int st = (int)(kvc % kStages);
-                            if (mbar_test(p_full(l), pv_tot[l] & 1u) && mbar_test(v_full(st), (kvc / kStages) & 1u)) {
-                                tc_fence_after();
-                                const int n16 = jt == n_kv - 1 ? last_n16 : kBN;
-                                const uint32_t id = idesc(kBM, kD, F16, true);
-                                const uint32_t pb = base + Smem::kP + (uint32_t)l * 2 * kTile;
-                                const uint32_t vb = base + Smem::kKV + (uint32_t)st * 2 * kTile + kTile;
-                                for (int kk = 0; kk < n16 / 16; ++kk) {
-                                    // A = P: K-major, two 64-column swizzle atoms of 16 KB; B = V: MN-major, 16 keys = 2 KB
-                                    const uint64_t a_desc = umma_desc_sw128(pb + (uint32_t)(kk >> 2) * kTile) + (uint64_t)(2 * (kk & 3));
-                                    const uint64_t b_desc = umma_desc_sw128(vb + (uint32_t)kk * 2048u);
-                                    umma_bf16_ss(tmem_base + o_col(l), a_desc, b_desc, id, (uint32_t)((jt | kk) != 0));
-                                }
-                                umma_commit(o_full(l));
-                                ++pv_iss[l];
-                                ++pv_tot[l];
-                            }
-                        }
+                if (2 * p + l >= g.n_qt) {
+                    // nothing for this group in the unit: hand the ring slots back as the other issuer finishes with them
+                    for (int jt = 0; jt < n_kv; ++jt, ++kvc) {
+                        const int st = (int)(kvc % kStages);
+                        mbar_wait(k_full(st), (kvc / kStages) & 1u);
+                        mbar_wait(v_full(st), (kvc / kStages) & 1u);
+                        mbar_arrive(kv_empty(st));
                     }
-                    while (rel < n_kv && s_iss[0] > rel && s_iss[1] > rel && pv_iss[0] > rel && pv_iss[1] > rel) {
-                        umma_commit(kv_empty((int)((kv0 + (uint32_t)rel) % kStages)));
-                        ++rel;
-                    }
-                    if (clock64() - t0 > 8000000000ll) __trap();
+                    continue;
                 }
-                kv0 += (uint32_t)n_kv;
+                mbar_wait(q_full(l), n_q & 1u);
+                ++n_q;
+                issue_s(kvc, 0);
+                for (int jt = 0; jt < n_kv; ++jt) {
+                    if (jt + 1 < n_kv) issue_s(kvc + (uint32_t)(jt + 1), jt + 1);
+                    else umma_commit(q_empty(l));                 // Q tile free once the last S has read it
+                    const uint32_t kv = kvc + (uint32_t)jt;
+                    const int st = (int)(kv % kStages);
+                    mbar_wait(v_full(st), (kv / kStages) & 1u);
+                    mbar_wait(p_full(l), n_pf & 1u);              // P_l(jt) is in tensor memory, O_l is ours
+                    ++n_pf;
+                    tc_fence_after();
+                    const int nk16 = (jt == n_kv - 1 ? last_n16 : kBN) / 16;
+                    const uint64_t v_desc = umma_desc_sw128(base + Smem::kKV + (uint32_t)st * 2 * kTile + kTile);
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk) {
+                        // A = P: 16 keys = 8 columns of packed pairs; B = V: MN-major, 16 keys = 2 KB of the swizzled tile
+                        if (kk < nk16)
+                            umma_f16_ts(o_tmem, p_tmem + (uint32_t)(kk * 8), v_desc + (uint64_t)(kk * 128), id_pv,
+                                        (uint32_t)((jt | kk) != 0));
+                    }
+                    umma_commit(o_full(l));
+                    umma_commit(kv_empty(st));
+                }
+                kvc += (uint32_t)n_kv;
             }
         }
     } else if (warp < 8) {
@@ -293,8 +303,8 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         const int row = qd * 32 + lane;                   // query row inside the tile
         const int gtid = (int)threadIdx.x - l * 128;      // 0..127 inside the group
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        const uint32_t pbuf = base + Smem::kP + (uint32_t)l * 2 * kTile;
-        unsigned char* pbuf_ptr = base_ptr + Smem::kP + l * 2 * kTile;
+        const uint32_t obuf = base + Smem::kO + (uint32_t)l * kTile;
+        const uint32_t orow = obuf + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         uint32_t n_s = 0, n_o = 0;                        // completions of s_full / o_full consumed so far
         for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
             const long long hs = u / g.n_pairs;
@@ -345,13 +355,15 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 < n16) {
-                            float m0 = __uint_as_float(s[c][0]), m1 = __uint_as_float(s[c][1]);
+                            float m4[4];
 #pragma unroll
-                            for (int i = 2; i < 32; i += 2) {
-                                m0 = fmaxf(m0, __uint_as_float(s[c][i]));
-                                m1 = fmaxf(m1, __uint_as_float(s[c][i + 1]));
-                            }
-                            mx = fmaxf(mx, fmaxf(m0, m1));
+                            for (int i = 0; i < 4; ++i) m4[i] = fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][4 + i]));
+#pragma unroll
+                            for (int i = 8; i < 32; i += 8)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    m4[k] = fmaxf(m4[k], fmaxf(__uint_as_float(s[c][i + k]), __uint_as_float(s[c][i + 4 + k])));
+                            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
                         }
                     }
                     mx *= g.scale_log2;
@@ -382,7 +394,7 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                     // ---- p = 2^(s c - m), row sum in fp32, P as 16-bit pairs (in place: s[c][i] <- pair i of chunk c)
                     const float2 sc2 = make_float2(g.scale_log2, g.scale_log2);
                     const float2 nm2 = make_float2(-m_ref, -m_ref);
-                    float2 acc2 = make_float2(0.f, 0.f);
+                    float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 < n16) {
@@ -391,48 +403,39 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                                 const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])),
                                                             sc2, nm2);
                                 const float2 e = make_float2(fast_ex2(x.x), fast_ex2(x.y));
-                                acc2 = __fadd2_rn(acc2, e);
+                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], e);
                                 s[c][i] = pack16<F16>(e.x, e.y);
                             }
                         }
                     }
-                    lsum += acc2.x + acc2.y;
+                    lsum += (acc2[0].x + acc2[1].x) + (acc2[0].y + acc2[1].y);
                 }
                 if (jt > 0 && !o_waited) {
-                    mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: the buffer is free
+                    mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: its columns are free
                     ++n_o;
-                } else if (jt == 0) {
-                    // the O tile of the previous unit was staged in this buffer: its TMA store must have read it
-                    if (gtid == 0) bulk_wait_read<0>();
-                    named_bar_sync(1 + l, 128);
+                    tc_fence_after();
                 }
                 if (warp_valid) {
-                    // P tile, K-major with the 128-byte swizzle (two 64-column atoms of 16 KB): row r, 16-byte chunk c16
-                    unsigned char* prow = pbuf_ptr + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c * 32 < n16) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int c16 = (c & 1) * 4 + i;                  // chunk inside the atom (8 columns each)
-                                const uint4 v4 = make_uint4(s[c][4 * i], s[c][4 * i + 1], s[c][4 * i + 2], s[c][4 * i + 3]);
-                                *reinterpret_cast<uint4*>(prow + (c >> 1) * kTile + ((c16 ^ (row & 7)) << 4)) = v4;
-                            }
-                        }
-                    }
-                    fence_proxy_async();
+                    // P_l: key pair i of chunk c -> column 16 c + i (what the A operand of the second product expects)
+                    const uint32_t tp = lane_taddr + p_col(l);
+                    tmem_st_32x16(tp, s[0]);
+                    if (n16 > 32) tmem_st_32x16(tp + 16, s[1]);
+                    if (n16 > 64) tmem_st_32x16(tp + 32, s[2]);
+                    if (n16 > 96) tmem_st_32x16(tp + 48, s[3]);
+                    tmem_wait_st();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full(l));
             }
             // ---- epilogue of the unit: O / l * sigmoid(gate) -> 16-bit tile -> TMA store
+            if (gtid == 0) bulk_wait_read<0>();                  // the previous unit's store has read the staging tile
+            named_bar_sync(1 + l, 128);
             mbar_wait(o_full(l), n_o & 1u);
             ++n_o;
             tc_fence_after();
             if (warp_valid) {
                 const float inv = gate / lsum;
-                unsigned char* orow = pbuf_ptr + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t o[32];
@@ -440,13 +443,12 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        uint4 v4;
-                        v4.x = pack16<F16>(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-                        v4.y = pack16<F16>(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-                        v4.z = pack16<F16>(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-                        v4.w = pack16<F16>(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-                        const int c16 = c * 4 + i;
-                        *reinterpret_cast<uint4*>(orow + ((c16 ^ (row & 7)) << 4)) = v4;
+                        const int c16 = c * 4 + i;               // 16-byte chunk of the 128-byte row, 128-byte swizzle
+                        st_shared_v4(orow + (uint32_t)((c16 ^ (row & 7)) << 4),
+                                     pack16<F16>(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                                     pack16<F16>(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                                     pack16<F16>(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                                     pack16<F16>(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
                     }
                 }
                 fence_proxy_async();
@@ -454,7 +456,7 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
             tc_fence_before();
             named_bar_sync(1 + l, 128);
             if (gtid == 0) {
-                tma_store_4d(&tm.o, pbuf, 0, j, qt * kBM, b);
+                tma_store_4d(&tm.o, obuf, 0, j, qt * kBM, b);
                 bulk_commit();
             }
         }
