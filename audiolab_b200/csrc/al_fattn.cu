@@ -42,6 +42,7 @@ constexpr int kBN = 128;          // keys per tile
 constexpr int kStages = 5;        // K / V ring
 constexpr int kThreads = 384;    // softmax groups A, B + the producer / MMA warpgroup
 constexpr int kTile = kBM * kD * 2;           // 16 KB: one 128 x 64 16-bit tile
+constexpr int kTurn = 3;                      // named barriers 3, 4: whose turn it is to run exponentials
 constexpr float kLazy = 8.0f;                 // log2 of the growth of the row maximum that triggers a rescale
 
 struct Maps {
@@ -126,6 +127,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // instruction descriptor: D fp32, A / B 16-bit (f16 = 0, bf16 = 1), A K-major, B K-major or MN-major (bit 16)
@@ -306,21 +308,27 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         const uint32_t obuf = base + Smem::kO + (uint32_t)l * kTile;
         const uint32_t orow = obuf + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         uint32_t n_s = 0, n_o = 0;                        // completions of s_full / o_full consumed so far
+        if (l == 1) named_bar_arrive(kTurn, 256);         // group A takes the first turn
         for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
             const long long hs = u / g.n_pairs;
             const int p = (int)(u - hs * g.n_pairs);
             const int qt = 2 * p + l;
-            if (qt >= g.n_qt) continue;
+            if (qt >= g.n_qt) {
+                // no query tile for this group in the unit: keep the turn-taking of the exponential phases going
+                for (int jt = 0; jt < n_kv; ++jt) {
+                    named_bar_sync(kTurn + l, 256);
+                    named_bar_arrive(kTurn + (l ^ 1), 256);
+                }
+                continue;
+            }
             const int b = (int)(hs / FH), j = (int)(hs - (long long)b * FH);
             const int t = qt * kBM + row;
             const bool warp_valid = qt * kBM + qd * 32 < g.T;     // any valid query row in this warp
-            float gate = 1.f;
+            uint16_t gate_raw = 0;                                // read now, used in the unit's epilogue
             if (g.gates != nullptr && t < g.T) {
                 const int f = j / g.H, h = j - f * g.H;
                 const long long grow = ((long long)b * g.T + t) * g.F + f;
-                if (F16) gate = __half2float(reinterpret_cast<const __half*>(g.gates)[grow * g.gate_ld + h]);
-                else gate = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g.gates)[grow * g.gate_ld + h]);
-                gate = sigmoid_fast(gate);
+                gate_raw = __ldg(reinterpret_cast<const uint16_t*>(g.gates) + grow * g.gate_ld + h);
             }
             float m_ref = 0.f, lsum = 0.f;
             for (int jt = 0; jt < n_kv; ++jt) {
@@ -351,21 +359,23 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                             for (int i = 0; i < 32; ++i)
                                 if (c * 32 + i >= ncols) s[c][i] = 0xff800000u;          // -inf
                     }
-                    float mx = -INFINITY;
+                    // eight independent chains (3-input maxima), chunks beyond the valid keys never loaded: skipped
+                    float m8[8];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int k = 0; k < 8; ++k) m8[k] = fmaxf(__uint_as_float(s[0][k]), __uint_as_float(s[0][8 + k]));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) m8[k] = fmaxf(m8[k], fmaxf(__uint_as_float(s[0][16 + k]), __uint_as_float(s[0][24 + k])));
+#pragma unroll
+                    for (int c = 1; c < 4; ++c) {
                         if (c * 32 < n16) {
-                            float m4[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) m4[i] = fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][4 + i]));
-#pragma unroll
-                            for (int i = 8; i < 32; i += 8)
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    m4[k] = fmaxf(m4[k], fmaxf(__uint_as_float(s[c][i + k]), __uint_as_float(s[c][i + 4 + k])));
-                            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+                            for (int k = 0; k < 8; ++k) {
+                                m8[k] = fmaxf(m8[k], fmaxf(__uint_as_float(s[c][k]), __uint_as_float(s[c][8 + k])));
+                                m8[k] = fmaxf(m8[k], fmaxf(__uint_as_float(s[c][16 + k]), __uint_as_float(s[c][24 + k])));
+                            }
                         }
                     }
+                    float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                     mx *= g.scale_log2;
                     if (jt == 0) {
                         m_ref = mx;
@@ -391,25 +401,33 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                             tmem_wait_st();
                         }
                     }
-                    // ---- p = 2^(s c - m), row sum in fp32, P as 16-bit pairs (in place: s[c][i] <- pair i of chunk c)
+                }
+                // ---- p = 2^(s c - m): the MUFU phase.  The two groups take turns (named barriers kTurn, kTurn + 1), so that
+                // one group's exponentials run at the full MUFU rate while the other group loads / reduces / stores
+                named_bar_sync(kTurn + l, 256);
+                if (warp_valid) {
                     const float2 sc2 = make_float2(g.scale_log2, g.scale_log2);
                     const float2 nm2 = make_float2(-m_ref, -m_ref);
                     float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 < n16) {
+                            float2 x[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                x[i] = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) x[i] = make_float2(fast_ex2(x[i].x), fast_ex2(x[i].y));
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])),
-                                                            sc2, nm2);
-                                const float2 e = make_float2(fast_ex2(x.x), fast_ex2(x.y));
-                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], e);
-                                s[c][i] = pack16<F16>(e.x, e.y);
+                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], x[i]);
+                                s[c][i] = pack16<F16>(x[i].x, x[i].y);
                             }
                         }
                     }
                     lsum += (acc2[0].x + acc2[1].x) + (acc2[0].y + acc2[1].y);
                 }
+                named_bar_arrive(kTurn + (l ^ 1), 256);
                 if (jt > 0 && !o_waited) {
                     mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: its columns are free
                     ++n_o;
@@ -435,6 +453,11 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
             ++n_o;
             tc_fence_after();
             if (warp_valid) {
+                float gate = 1.f;
+                if (g.gates != nullptr) {
+                    gate = F16 ? __half2float(__ushort_as_half(gate_raw)) : __bfloat162float(__ushort_as_bfloat16(gate_raw));
+                    gate = sigmoid_fast(gate);
+                }
                 const float inv = gate / lsum;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
