@@ -402,32 +402,52 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                         }
                     }
                 }
-                // ---- p = 2^(s c - m): the MUFU phase.  The two groups take turns (named barriers kTurn, kTurn + 1), so that
-                // one group's exponentials run at the full MUFU rate while the other group loads / reduces / stores
-                named_bar_sync(kTurn + l, 256);
+                // ---- p = 2^(s c - m).  The exponentials are the scarce resource (MUFU: 16 / clk / SM), so the two groups take
+                // turns on them (named barriers kTurn, kTurn + 1) and a turn holds NOTHING but the 128 MUFU.EX2 of the row:
+                // the arguments are formed before it, sums and 16-bit pairs after it -- while this group does those, loads S,
+                // reduces the maximum or stores P, the other group's exponentials run at the full rate.
                 if (warp_valid) {
                     const float2 sc2 = make_float2(g.scale_log2, g.scale_log2);
                     const float2 nm2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < n16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])),
+                                                            sc2, nm2);
+                                s[c][2 * i] = __float_as_uint(x.x);
+                                s[c][2 * i + 1] = __float_as_uint(x.y);
+                            }
+                        }
+                    }
+                }
+                named_bar_sync(kTurn + l, 256);
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c * 32 < n16) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(fast_ex2(__uint_as_float(s[c][i])));
+                        }
+                    }
+                }
+                named_bar_arrive(kTurn + (l ^ 1), 256);
+                if (warp_valid) {
                     float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 < n16) {
-                            float2 x[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                x[i] = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) x[i] = make_float2(fast_ex2(x[i].x), fast_ex2(x[i].y));
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], x[i]);
-                                s[c][i] = pack16<F16>(x[i].x, x[i].y);
+                                const float2 e = make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
+                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], e);
+                                s[c][i] = pack16<F16>(e.x, e.y);
                             }
                         }
                     }
                     lsum += (acc2[0].x + acc2[1].x) + (acc2[0].y + acc2[1].y);
                 }
-                named_bar_arrive(kTurn + (l ^ 1), 256);
                 if (jt > 0 && !o_waited) {
                     mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: its columns are free
                     ++n_o;
