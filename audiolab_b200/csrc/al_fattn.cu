@@ -137,6 +137,25 @@ __device__ __forceinline__ uint32_t idesc(int m, int n, bool f16, bool b_mn_majo
            ((uint32_t)(m >> 4) << 24);
 }
 
+// 2^x for x <= 8 on the FMA pipe (every 4th pair of a row: the MUFU is the scarce unit): x = n + r with n = round(x) taken
+// from the low mantissa bits of x + 1.5 * 2^23, 2^r by a degree-4 polynomial on [-0.5, 0.5] (relative error 3.6e-6, far
+// below the 16-bit rounding of P), n added to the exponent field.
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    const float2 t = __fadd2_rn(x, magic);
+    const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 r = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 p = __ffma2_rn(make_float2(0.00966636836528778f, 0.00966636836528778f), r,
+                          make_float2(0.055921975523233414f, 0.055921975523233414f));
+    p = __ffma2_rn(p, r, make_float2(0.2402234971523285f, 0.2402234971523285f));
+    p = __ffma2_rn(p, r, make_float2(0.6931210160255432f, 0.6931210160255432f));
+    p = __ffma2_rn(p, r, make_float2(1.0f, 1.0f));
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
@@ -208,10 +227,10 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         if (lane == 0) {
             uint32_t kvc = 0;
             uint32_t uc[2] = {0, 0};
-            for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
-                const long long hs = u / g.n_pairs;
-                const int p = (int)(u - hs * g.n_pairs);
-                const int b = (int)(hs / FH), j = (int)(hs - (long long)b * FH);
+            for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
+                const uint32_t hs = u / (uint32_t)g.n_pairs;
+                const int p = (int)(u - hs * (uint32_t)g.n_pairs);
+                const int b = (int)(hs / (uint32_t)FH), j = (int)(hs - (uint32_t)b * (uint32_t)FH);
                 for (int l = 0; l < 2; ++l) {
                     const int qt = 2 * p + l;
                     if (qt >= g.n_qt) continue;
@@ -257,9 +276,9 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                 umma_commit(s_full(l));
                 ++n_s;
             };
-            for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
-                const long long hs = u / g.n_pairs;
-                const int p = (int)(u - hs * g.n_pairs);
+            for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
+                const uint32_t hs = u / (uint32_t)g.n_pairs;
+                const int p = (int)(u - hs * (uint32_t)g.n_pairs);
                 if (2 * p + l >= g.n_qt) {
                     // nothing for this group in the unit: hand the ring slots back as the other issuer finishes with them
                     for (int jt = 0; jt < n_kv; ++jt, ++kvc) {
@@ -309,9 +328,9 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         const uint32_t orow = obuf + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         uint32_t n_s = 0, n_o = 0;                        // completions of s_full / o_full consumed so far
         if (l == 1) named_bar_arrive(kTurn, 256);         // group A takes the first turn
-        for (long long u = blockIdx.x; u < g.n_units; u += gridDim.x) {
-            const long long hs = u / g.n_pairs;
-            const int p = (int)(u - hs * g.n_pairs);
+        for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
+            const uint32_t hs = u / (uint32_t)g.n_pairs;
+            const int p = (int)(u - hs * (uint32_t)g.n_pairs);
             const int qt = 2 * p + l;
             if (qt >= g.n_qt) {
                 // no query tile for this group in the unit: keep the turn-taking of the exponential phases going
@@ -321,7 +340,7 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                 }
                 continue;
             }
-            const int b = (int)(hs / FH), j = (int)(hs - (long long)b * FH);
+            const int b = (int)(hs / (uint32_t)FH), j = (int)(hs - (uint32_t)b * (uint32_t)FH);
             const int t = qt * kBM + row;
             const bool warp_valid = qt * kBM + qd * 32 < g.T;     // any valid query row in this warp
             uint16_t gate_raw = 0;                                // read now, used in the unit's epilogue
@@ -402,52 +421,33 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                         }
                     }
                 }
-                // ---- p = 2^(s c - m).  The exponentials are the scarce resource (MUFU: 16 / clk / SM), so the two groups take
-                // turns on them (named barriers kTurn, kTurn + 1) and a turn holds NOTHING but the 128 MUFU.EX2 of the row:
-                // the arguments are formed before it, sums and 16-bit pairs after it -- while this group does those, loads S,
-                // reduces the maximum or stores P, the other group's exponentials run at the full rate.
+                // ---- p = 2^(s c - m): the MUFU phase.  The two groups take turns (named barriers kTurn, kTurn + 1), so that
+                // one group's exponentials run at the full MUFU rate while the other group loads / reduces / stores
+                named_bar_sync(kTurn + l, 256);
                 if (warp_valid) {
                     const float2 sc2 = make_float2(g.scale_log2, g.scale_log2);
                     const float2 nm2 = make_float2(-m_ref, -m_ref);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c * 32 < n16) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])),
-                                                            sc2, nm2);
-                                s[c][2 * i] = __float_as_uint(x.x);
-                                s[c][2 * i + 1] = __float_as_uint(x.y);
-                            }
-                        }
-                    }
-                }
-                named_bar_sync(kTurn + l, 256);
-                if (warp_valid) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c * 32 < n16) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) s[c][i] = __float_as_uint(fast_ex2(__uint_as_float(s[c][i])));
-                        }
-                    }
-                }
-                named_bar_arrive(kTurn + (l ^ 1), 256);
-                if (warp_valid) {
                     float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c * 32 < n16) {
+                            float2 x[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                x[i] = __ffma2_rn(make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), sc2, nm2);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                x[i] = (i & 3) == 3 ? exp2_fma2(x[i]) : make_float2(fast_ex2(x[i].x), fast_ex2(x[i].y));
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const float2 e = make_float2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1]));
-                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], e);
-                                s[c][i] = pack16<F16>(e.x, e.y);
+                                acc2[i & 1] = __fadd2_rn(acc2[i & 1], x[i]);
+                                s[c][i] = pack16<F16>(x[i].x, x[i].y);
                             }
                         }
                     }
                     lsum += (acc2[0].x + acc2[1].x) + (acc2[0].y + acc2[1].y);
                 }
+                named_bar_arrive(kTurn + (l ^ 1), 256);
                 if (jt > 0 && !o_waited) {
                     mbar_wait(o_full(l), n_o & 1u);              // P V (jt - 1) has read P_l: its columns are free
                     ++n_o;
@@ -554,7 +554,8 @@ const char* launch_time_attention(const void* q, const void* k, const void* v, v
          reinterpret_cast<uintptr_t>(o)) & 15)
         return "q, k, v, o must be 16-byte aligned";
     const long long FH = (long long)inner * heads;
-    if (FH > 0x7fffffffll || n_batch > 0x7fffffffll) return "too many sequences";
+    if (FH > 0x7fffffffll || n_batch > 0x7fffffffll || n_batch * FH * ((seq_len + 2 * kBM - 1) / (2 * kBM)) > 0x7fffffffll)
+        return "too many sequences";
     Maps tm;
     if (!make_map(&tm.q, q, fp16 != 0, n_batch, seq_len, FH) || !make_map(&tm.k, k, fp16 != 0, n_batch, seq_len, FH) ||
         !make_map(&tm.v, v, fp16 != 0, n_batch, seq_len, FH) || !make_map(&tm.o, o, fp16 != 0, n_batch, seq_len, FH))

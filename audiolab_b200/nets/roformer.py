@@ -27,6 +27,8 @@ from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
 _BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "1") != "0"   # band-axis attention kernel inside the tc path (default)
+# time-axis attention kernel (csrc/al_fattn.cu, tcgen05 flash attention + gate) inside the tc path; 0 = cuDNN SDPA + gate pass
+_TIME_ATTN_TC = os.environ.get("AUDIOLAB_B200_TIME_ATTN", "0") != "0"
 _GROUPED = os.environ.get("AUDIOLAB_B200_GROUPED", "1") != "0"   # band split / mask estimator as grouped tcgen05 GEMMs
 _TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 
@@ -370,6 +372,9 @@ class RoformerMaskNet(nn.Module):
             if not time_axis and _BAND_ATTN_TC and f <= 64:
                 # band axis (<= 64 tokens per sequence): our kernel (csrc/al_attn.cu), sigmoid gate folded into its epilogue
                 o2 = netops.band_attention(q, k, v, b * t, f, h, dh, gates=gates[:, :h])
+            elif time_axis and _TIME_ATTN_TC:
+                # time axis: tcgen05 flash attention straight on the token-major layout, sigmoid gate in its epilogue
+                o2 = netops.time_attention(q, k, v, b, t, f, h, dh, gates=gates[:, :h])
             else:
                 shape = (b, t, f * h, dh) if time_axis else (b * t, f, h, dh)
                 o = F.scaled_dot_product_attention(q.view(shape).transpose(1, 2), k.view(shape).transpose(1, 2),
