@@ -51,8 +51,9 @@ struct Maps {
 
 struct Args {
     int T, F, H, B;
-    int n_qt, n_kv, n_pairs;       // query tiles, key tiles per sequence; query tile pairs per sequence
-    long long n_units;             // B * F * H * n_pairs
+    int n_qt, n_kv;                // query tiles, key tiles per sequence
+    long long n_seq;               // B * F * H sequences
+    long long n_units;             // ceil(n_seq / 2) * n_qt: the 2 n_qt query tiles of two sequences, taken two at a time
     float scale_log2;              // scale * log2(e)
     const void* gates;             // [rows, gate_ld] 16-bit or NULL
     long long gate_ld;
@@ -213,6 +214,26 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
     auto o_col = [&](int l) { return (uint32_t)(2 * kBN + l * kD); };
     auto p_col = [&](int l) { return (uint32_t)(2 * kBN + 2 * kD + l * (kBN / 2)); };
 
+    // Work units.  Two consecutive sequences (b, f, h) form a group; the 2 n_qt query tiles of the group are taken two at a
+    // time, tile 2 r + l of the list going to softmax group l of unit r.  With an odd number of tiles per sequence (801
+    // frames = 6 full tiles + 33 rows) one unit of the group is MIXED: its two query tiles belong to different sequences and
+    // the K / V ring carries the tiles of both, alternating -- instead of one unit per sequence that keeps a whole softmax
+    // group idle.  The unit index inside the group is rotated by the CTA's iteration count so that every CTA sees the same mix.
+    const uint32_t U = (uint32_t)g.n_qt;
+    const bool rotate = gridDim.x % U == 0;
+    struct Lane { uint32_t hs; int qt; bool active; };
+    auto decode = [&](uint32_t u, int l) {
+        const uint32_t grp = u / U;
+        uint32_t r = u - grp * U;
+        if (rotate) r = (r + u / gridDim.x) % U;
+        const uint32_t k = 2 * r + (uint32_t)l;
+        const uint32_t second = k >= U ? 1u : 0u;
+        Lane x;
+        x.hs = 2 * grp + second;
+        x.qt = (int)(k - second * U);
+        x.active = (long long)x.hs < g.n_seq;
+        return x;
+    };
     const int n_kv = g.n_kv;
     const int last_cols = g.T - (n_kv - 1) * kBN;                 // valid keys of the last key tile
     const int last_n16 = (last_cols + 15) & ~15;
@@ -228,26 +249,30 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
             uint32_t kvc = 0;
             uint32_t uc[2] = {0, 0};
             for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
-                const uint32_t hs = u / (uint32_t)g.n_pairs;
-                const int p = (int)(u - hs * (uint32_t)g.n_pairs);
-                const int b = (int)(hs / (uint32_t)FH), j = (int)(hs - (uint32_t)b * (uint32_t)FH);
+                Lane ln[2] = {decode(u, 0), decode(u, 1)};
+                int bb[2], jj[2];
                 for (int l = 0; l < 2; ++l) {
-                    const int qt = 2 * p + l;
-                    if (qt >= g.n_qt) continue;
+                    bb[l] = (int)(ln[l].hs / (uint32_t)FH);
+                    jj[l] = (int)(ln[l].hs - (uint32_t)bb[l] * (uint32_t)FH);
+                    if (!ln[l].active) continue;
                     mbar_wait(q_empty(l), (uc[l] & 1u) ^ 1u);
                     mbar_arrive_expect_tx(q_full(l), (uint32_t)kTile);
-                    tma_load_4d(base + Smem::kQ + (uint32_t)l * kTile, &tm.q, q_full(l), 0, j, qt * kBM, b);
+                    tma_load_4d(base + Smem::kQ + (uint32_t)l * kTile, &tm.q, q_full(l), 0, jj[l], ln[l].qt * kBM, bb[l]);
                     ++uc[l];
                 }
-                for (int jt = 0; jt < n_kv; ++jt, ++kvc) {
-                    const int s = (int)(kvc % kStages);
-                    const uint32_t ph = (kvc / kStages) & 1u;
-                    mbar_wait(kv_empty(s), ph ^ 1u);
-                    const uint32_t kb = base + Smem::kKV + (uint32_t)s * 2 * kTile;
-                    mbar_arrive_expect_tx(k_full(s), (uint32_t)kTile);
-                    tma_load_4d(kb, &tm.k, k_full(s), 0, j, jt * kBN, b);
-                    mbar_arrive_expect_tx(v_full(s), (uint32_t)kTile);
-                    tma_load_4d(kb + kTile, &tm.v, v_full(s), 0, j, jt * kBN, b);
+                const bool mixed = ln[0].active && ln[1].active && ln[0].hs != ln[1].hs;
+                const int first = ln[0].active ? 0 : 1;
+                for (int jt = 0; jt < n_kv; ++jt) {
+                    for (int l = first; l < (mixed ? 2 : first + 1); ++l, ++kvc) {       // mixed: K / V of both sequences, alternating
+                        const int s = (int)(kvc % kStages);
+                        const uint32_t ph = (kvc / kStages) & 1u;
+                        mbar_wait(kv_empty(s), ph ^ 1u);
+                        const uint32_t kb = base + Smem::kKV + (uint32_t)s * 2 * kTile;
+                        mbar_arrive_expect_tx(k_full(s), (uint32_t)kTile);
+                        tma_load_4d(kb, &tm.k, k_full(s), 0, jj[l], jt * kBN, bb[l]);
+                        mbar_arrive_expect_tx(v_full(s), (uint32_t)kTile);
+                        tma_load_4d(kb + kTile, &tm.v, v_full(s), 0, jj[l], jt * kBN, bb[l]);
+                    }
                 }
             }
         }
@@ -276,26 +301,41 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                 umma_commit(s_full(l));
                 ++n_s;
             };
+            // a ring slot this issuer has no use for (the other group's sequence, or no query tile at all): hand it back
+            auto pass = [&](uint32_t kv) {
+                const int st = (int)(kv % kStages);
+                mbar_wait(k_full(st), (kv / kStages) & 1u);
+                mbar_wait(v_full(st), (kv / kStages) & 1u);
+                mbar_arrive(kv_empty(st));
+            };
             for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
-                const uint32_t hs = u / (uint32_t)g.n_pairs;
-                const int p = (int)(u - hs * (uint32_t)g.n_pairs);
-                if (2 * p + l >= g.n_qt) {
-                    // nothing for this group in the unit: hand the ring slots back as the other issuer finishes with them
-                    for (int jt = 0; jt < n_kv; ++jt, ++kvc) {
-                        const int st = (int)(kvc % kStages);
-                        mbar_wait(k_full(st), (kvc / kStages) & 1u);
-                        mbar_wait(v_full(st), (kvc / kStages) & 1u);
-                        mbar_arrive(kv_empty(st));
-                    }
+                const Lane me = decode(u, l), other = decode(u, l ^ 1);
+                const bool mixed = me.active && other.active && me.hs != other.hs;
+                const uint32_t n_pos = (uint32_t)(mixed ? 2 * n_kv : n_kv);          // ring slots of the unit
+                if (!me.active) {
+                    for (uint32_t q = 0; q < n_pos; ++q) pass(kvc + q);
+                    kvc += n_pos;
                     continue;
                 }
+                // own slots: jt (shared K / V) or 2 jt + l (mixed unit); the slots in between belong to the other sequence
+                auto own = [&](int jt) { return kvc + (uint32_t)(mixed ? 2 * jt + l : jt); };
+                uint32_t next_pass = kvc + (uint32_t)(1 - l);
+                auto pass_below = [&](uint32_t kv) {               // slots below a slot that is already full: no waiting
+                    if (!mixed) return;
+                    for (; next_pass < kv; next_pass += 2) pass(next_pass);
+                };
                 mbar_wait(q_full(l), n_q & 1u);
                 ++n_q;
-                issue_s(kvc, 0);
+                issue_s(own(0), 0);
+                pass_below(own(0));
                 for (int jt = 0; jt < n_kv; ++jt) {
-                    if (jt + 1 < n_kv) issue_s(kvc + (uint32_t)(jt + 1), jt + 1);
-                    else umma_commit(q_empty(l));                 // Q tile free once the last S has read it
-                    const uint32_t kv = kvc + (uint32_t)jt;
+                    if (jt + 1 < n_kv) {
+                        issue_s(own(jt + 1), jt + 1);
+                        pass_below(own(jt + 1));
+                    } else {
+                        umma_commit(q_empty(l));                  // Q tile free once the last S has read it
+                    }
+                    const uint32_t kv = own(jt);
                     const int st = (int)(kv % kStages);
                     mbar_wait(v_full(st), (kv / kStages) & 1u);
                     mbar_wait(p_full(l), n_pf & 1u);              // P_l(jt) is in tensor memory, O_l is ours
@@ -313,7 +353,8 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                     umma_commit(o_full(l));
                     umma_commit(kv_empty(st));
                 }
-                kvc += (uint32_t)n_kv;
+                pass_below(kvc + n_pos);
+                kvc += n_pos;
             }
         }
     } else if (warp < 8) {
@@ -329,10 +370,8 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
         uint32_t n_s = 0, n_o = 0;                        // completions of s_full / o_full consumed so far
         if (l == 1) named_bar_arrive(kTurn, 256);         // group A takes the first turn
         for (uint32_t u = blockIdx.x; u < (uint32_t)g.n_units; u += gridDim.x) {
-            const uint32_t hs = u / (uint32_t)g.n_pairs;
-            const int p = (int)(u - hs * (uint32_t)g.n_pairs);
-            const int qt = 2 * p + l;
-            if (qt >= g.n_qt) {
+            const Lane me = decode(u, l);
+            if (!me.active) {
                 // no query tile for this group in the unit: keep the turn-taking of the exponential phases going
                 for (int jt = 0; jt < n_kv; ++jt) {
                     named_bar_sync(kTurn + l, 256);
@@ -340,7 +379,8 @@ time_attn_kernel(const __grid_constant__ Maps tm, const Args g) {
                 }
                 continue;
             }
-            const int b = (int)(hs / (uint32_t)FH), j = (int)(hs - (uint32_t)b * (uint32_t)FH);
+            const int qt = me.qt;
+            const int b = (int)(me.hs / (uint32_t)FH), j = (int)(me.hs - (uint32_t)b * (uint32_t)FH);
             const int t = qt * kBM + row;
             const bool warp_valid = qt * kBM + qd * 32 < g.T;     // any valid query row in this warp
             uint16_t gate_raw = 0;                                // read now, used in the unit's epilogue
@@ -554,7 +594,7 @@ const char* launch_time_attention(const void* q, const void* k, const void* v, v
          reinterpret_cast<uintptr_t>(o)) & 15)
         return "q, k, v, o must be 16-byte aligned";
     const long long FH = (long long)inner * heads;
-    if (FH > 0x7fffffffll || n_batch > 0x7fffffffll || n_batch * FH * ((seq_len + 2 * kBM - 1) / (2 * kBM)) > 0x7fffffffll)
+    if (FH > 0x7fffffffll || n_batch > 0x7fffffffll || n_batch * FH * ((seq_len + kBM - 1) / kBM) > 0x7fffffffll)
         return "too many sequences";
     Maps tm;
     if (!make_map(&tm.q, q, fp16 != 0, n_batch, seq_len, FH) || !make_map(&tm.k, k, fp16 != 0, n_batch, seq_len, FH) ||
@@ -564,8 +604,8 @@ const char* launch_time_attention(const void* q, const void* k, const void* v, v
     g.T = seq_len; g.F = inner; g.H = heads; g.B = (int)n_batch;
     g.n_qt = (seq_len + kBM - 1) / kBM;
     g.n_kv = (seq_len + kBN - 1) / kBN;
-    g.n_pairs = (g.n_qt + 1) / 2;
-    g.n_units = n_batch * FH * g.n_pairs;
+    g.n_seq = n_batch * FH;
+    g.n_units = ((g.n_seq + 1) / 2) * g.n_qt;
     g.scale_log2 = scale * 1.4426950408889634f;
     g.gates = gates;
     g.gate_ld = gates != nullptr ? (gate_ld > 0 ? gate_ld : heads) : 0;

@@ -269,7 +269,7 @@ def ref_time_attention(q, k, v, n_batch, seq_len, inner, heads, dh, gates=None):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,T,I,H", [(2, 801, 3, 2), (1, 128, 1, 1), (1, 129, 2, 1), (3, 33, 5, 2), (1, 1, 1, 1), (2, 300, 2, 3),
-                                     (1, 1000, 1, 2), (1, 256, 7, 1)])
+                                     (1, 1000, 1, 2), (1, 256, 7, 1), (1, 801, 1, 3)])
 def test_time_attention_kernel(cuda, B, T, I, H, dtype):
     """csrc/al_fattn.cu (tcgen05 flash attention along the time axis, gate folded in) against fp32 torch SDPA of the same
     16-bit inputs.  Tolerance: the output is rounded to 16 bits (2^-11 / 2^-8 relative) and P is a 16-bit operand."""
