@@ -27,8 +27,9 @@ from ..configs import RoformerConfig
 
 _BAND_ATTN = os.environ.get("AUDIOLAB_B200_BAND_ATTN") == "1"   # opt-in until measured on a B200 (NOTES.md)
 _BAND_ATTN_TC = os.environ.get("AUDIOLAB_B200_BAND_ATTN", "1") != "0"   # band-axis attention kernel inside the tc path (default)
-# time-axis attention kernel (csrc/al_fattn.cu, tcgen05 flash attention + gate) inside the tc path; 0 = cuDNN SDPA + gate pass
-_TIME_ATTN_TC = os.environ.get("AUDIOLAB_B200_TIME_ATTN", "0") != "0"
+# time-axis attention kernel (csrc/al_fattn.cu, tcgen05 flash attention + gate) inside the tc path (default); 0 = cuDNN SDPA +
+# gate pass (the comparison path: 4.39 ms per call against 4.27 ms, profiles/r02u_*)
+_TIME_ATTN_TC = os.environ.get("AUDIOLAB_B200_TIME_ATTN", "1") != "0"
 _GROUPED = os.environ.get("AUDIOLAB_B200_GROUPED", "1") != "0"   # band split / mask estimator as grouped tcgen05 GEMMs
 _TC_GEMM = os.environ.get("AUDIOLAB_B200_TC_GEMM", "1") != "0"  # tcgen05 GEMM path (default); 0 = cuBLAS comparison path
 

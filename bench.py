@@ -782,7 +782,9 @@ def run_ours(args) -> None:
                          "frac_of_bf16_peak": flops_step / (net_ms / 1e3) / 1e12 / world / pk["bf16_tflops"],
                          "note": ("linear layers: al_gemm_bf16 (hand-written tcgen05 / TMA / TMEM GEMM, RMSNorm + rotary + GELU "
                                   "+ bias + fp32 residual fused into the epilogues); attention: "
-                                  + ("al_band_attention (band axis) + cuDNN SDPA (time axis)" if rof._BAND_ATTN_TC else "cuDNN SDPA")
+                                  + ("al_band_attention (band axis, mma.sync) + " if rof._BAND_ATTN_TC else "cuDNN SDPA (band axis) + ")
+                                  + ("al_time_attention (time axis, tcgen05 flash attention with the gate in its epilogue; no "
+                                     "library call left in the step)" if rof._TIME_ATTN_TC else "cuDNN SDPA (time axis)")
                                   + ("; band split / mask estimator: grouped al_gemm_bf16 (GLU epilogue, fp32 mask)"
                                      if rof._GROUPED and inst.demixer.net._grouped_supported() else
                                      "; band split / mask estimator under bf16 autocast")) if tc else
