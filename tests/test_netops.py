@@ -380,6 +380,9 @@ def test_tc_axial_host_logic_matches_module_path(kind, monkeypatch):
     monkeypatch.setattr(netops, "band_attention",
                         lambda q, k, v, n_seq, seq_len, heads, dh, gates=None, cos_sin=None:
                         ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates))
+    monkeypatch.setattr(netops, "time_attention",
+                        lambda q, k, v, n_batch, seq_len, inner, heads, dh, gates=None:
+                        ref_time_attention(q, k, v, n_batch, seq_len, inner, heads, dh, gates).to(q.dtype))
     net._fused_dtype = torch.float32
     b, t, f = 2, 13, len(net.band_split.dim_inputs)
     x = torch.randn(b, t, f, cfg.dim)
@@ -456,6 +459,9 @@ def test_tc_grouped_band_split_and_mask_estimator_host_logic(monkeypatch):
     monkeypatch.setattr(netops, "band_attention",
                         lambda q, k, v, n_seq, seq_len, heads, dh, gates=None, cos_sin=None:
                         ref_band_attention(q, k, v, n_seq, seq_len, heads, dh, gates))
+    monkeypatch.setattr(netops, "time_attention",
+                        lambda q, k, v, n_batch, seq_len, inner, heads, dh, gates=None:
+                        ref_time_attention(q, k, v, n_batch, seq_len, inner, heads, dh, gates).to(q.dtype))
     b, t, f, s = 2, 7, 19, 2
     spec = torch.randn(b, t, f, s, dtype=torch.complex64)
     ref = net.mask(spec.clone())                                    # module path (compute dtype fp32)
