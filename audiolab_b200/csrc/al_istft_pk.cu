@@ -129,7 +129,7 @@ istft_pk2_kernel(const IstftPkParams p) {
         const float4* __restrict__ mr = MASK ? M + (long long)(ta + warp) * kIpBins : nullptr;
 #pragma unroll
         for (int r = 0; r < kIpPre; ++r) IP_ISSUE(xr, mr, r, r);
-        if (lane == 0) {
+        if (lane == 0 && p.l2_prefetch) {
             if (kIpPre == 0) {
                 prefetch_l2_bulk(xr, kIpBins * 16);
                 if (MASK) prefetch_l2_bulk(mr, kIpBins * 16);
@@ -155,7 +155,7 @@ istft_pk2_kernel(const IstftPkParams p) {
         float2 re[32], im[32];
         if (live) {
             constexpr int kAhead = kIpPre ? 2 : 1;   // rounds ahead of the L2 prefetch
-            if (lane == 0 && t + kAhead * kIpWarps <= tb) {
+            if (lane == 0 && p.l2_prefetch && t + kAhead * kIpWarps <= tb) {
                 prefetch_l2_bulk(X + (long long)(t + kAhead * kIpWarps) * kIpBins, kIpBins * 16);
                 if (MASK) prefetch_l2_bulk(M + (long long)(t + kAhead * kIpWarps) * kIpBins, kIpBins * 16);
             }
@@ -417,6 +417,8 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
     static const int ola_fast = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
     p.ola_fast = ola_fast;
+    static const int l2pf = (getenv("AL_IP_L2PF") && atoi(getenv("AL_IP_L2PF")) == 0) ? 0 : 1;
+    p.l2_prefetch = l2pf;
     const size_t smem = ip_launch_shape(p, n_chunks, n_sm, W);
     const size_t cap = 227 * 1024;
     if (smem > cap) return cudaErrorInvalidValue;

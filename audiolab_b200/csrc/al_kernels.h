@@ -132,6 +132,7 @@ struct IstftPkParams {
     long long dst_off0, dst_off_step;
     long long dst_limit;
     int ola_fast;             // interior rounds take the predicate-free overlap-add (AL_IP_OLAFAST=0 disables)
+    int l2_prefetch;          // bulk L2 prefetch of the next round's rows (AL_IP_L2PF=0 disables)
     // filled by the launcher
     int hops_per_cta;
     int segs;

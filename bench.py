@@ -900,10 +900,18 @@ def main():
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: honour --warmup exactly and skip the e2e leg (never a bench value)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries below us write to file descriptor 1 on their own (NCCL prints its
+    # version banner there when NCCL_DEBUG is set in the box's environment): point fd 1 at stderr for the whole run and keep
+    # the real stdout for the final line only.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
