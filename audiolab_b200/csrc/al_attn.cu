@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "al_async.cuh"
 #include "al_kernels.h"
 
 namespace al {
@@ -107,23 +108,45 @@ band_attn_bf16_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     const long long base = (long long)s * F * ld + (long long)h * kBaD;
 
     // ---- stage Q, K, V: 64 rows x 8 vectors of 16 B each; rows >= F are zero ----------------------------------
-    for (int i = tid; i < kBaF * 8; i += 128) {
-        const int row = i >> 3, c8 = (i & 7) * 8;
-        uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq;
-        if (row < F) {
-            const long long g = base + (long long)row * ld + c8;
-            vq = __ldg(reinterpret_cast<const uint4*>(q + g));
-            vk = __ldg(reinterpret_cast<const uint4*>(k + g));
-            vv = __ldg(reinterpret_cast<const uint4*>(v + g));
-            if (cos_sin) {   // upstream rotary_embed.rotate_queries_or_keys on q and k, position = band index (= row)
+    if (cos_sin == nullptr) {
+        // the production path (rotary already applied by the GEMM epilogue): asynchronous 16-byte copies, all 12 per thread in
+        // flight at once -- a register-staged loop serialises its four iterations on the load latency (35 % of the stall
+        // samples sat on the first shared-memory store, profiles/r02x_ncu_full_band_attention.txt)
+#pragma unroll
+        for (int i = tid; i < kBaF * 8; i += 128) {
+            const int row = i >> 3, c8 = (i & 7) * 8;
+            if (row < F) {
+                const long long g = base + (long long)row * ld + c8;
+                al_cp_async16(Qs + row * kBaLd + c8, q + g);
+                al_cp_async16(Ks + row * kBaLd + c8, k + g);
+                al_cp_async16(Vs + row * kBaLd + c8, v + g);
+            } else {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(Qs + row * kBaLd + c8) = z;
+                *reinterpret_cast<uint4*>(Ks + row * kBaLd + c8) = z;
+                *reinterpret_cast<uint4*>(Vs + row * kBaLd + c8) = z;
+            }
+        }
+        al_cp_async_commit();
+        al_cp_async_wait<0>();
+    } else {
+        for (int i = tid; i < kBaF * 8; i += 128) {
+            const int row = i >> 3, c8 = (i & 7) * 8;
+            uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq;
+            if (row < F) {
+                const long long g = base + (long long)row * ld + c8;
+                vq = __ldg(reinterpret_cast<const uint4*>(q + g));
+                vk = __ldg(reinterpret_cast<const uint4*>(k + g));
+                vv = __ldg(reinterpret_cast<const uint4*>(v + g));
+                // upstream rotary_embed.rotate_queries_or_keys on q and k, position = band index (= row)
                 const float2* cs = cos_sin + row * (kBaD / 2) + (c8 >> 1);
                 vq = rotate_bf16x8(vq, cs);
                 vk = rotate_bf16x8(vk, cs);
             }
+            *reinterpret_cast<uint4*>(Qs + row * kBaLd + c8) = vq;
+            *reinterpret_cast<uint4*>(Ks + row * kBaLd + c8) = vk;
+            *reinterpret_cast<uint4*>(Vs + row * kBaLd + c8) = vv;
         }
-        *reinterpret_cast<uint4*>(Qs + row * kBaLd + c8) = vq;
-        *reinterpret_cast<uint4*>(Ks + row * kBaLd + c8) = vk;
-        *reinterpret_cast<uint4*>(Vs + row * kBaLd + c8) = vv;
     }
     __syncthreads();
 
