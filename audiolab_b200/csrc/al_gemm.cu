@@ -57,10 +57,10 @@ struct Tmaps {
                         //           swizzle), o[2] = x32 again with a 64 x 128 box for the L2 prefetch
 };
 
-template <int BN, int STAGES, int EPI, int EW>
+template <int BN, int STAGES, int EPI, int EW, int CG = 1>
 struct SmemLayout {
     static constexpr int kA = BM * BK * 2;                    // 16 KB
-    static constexpr int kB = BN * BK * 2;
+    static constexpr int kB = BN / CG * BK * 2;               // a CTA of a pair holds half of the W tile
     static constexpr int kStage = kA + kB;
     static constexpr int kEpiPerWarp = EPI == EPI_RES ? (kResSlots * 4096 + 2048) : 4096;
     static constexpr int kEpiOff = STAGES * kStage;
@@ -70,11 +70,19 @@ struct SmemLayout {
     static constexpr int kDynamic = kTotal + 1024;            // slack for the manual 1024-byte alignment
 };
 
-template <int BN, int STAGES, int EPI, bool F16, int EW>
+// CG = 2: CTA pairs (cluster of two, tcgen05 cta_group::2).  The pair computes a 256 x BN tile -- CTA r owns rows 128 r ..
+// 128 r + 127 of it in its own tensor memory and loads its own A tile and rows (BN / 2) r .. of the W tile; the MMA is issued
+// by CTA 0 alone, TMA bytes of both CTAs are counted on CTA 0's full barrier, ring slots and finished accumulators are
+// published to both CTAs by multicast commits, and the epilogue warps of both CTAs release an accumulator on CTA 0's barrier.
+// A CTA then moves 32 KB instead of 48 KB of operands per 128 x 256 x 64 block and the ring is 6 deep instead of 4: the
+// K = 512 shapes of the network are paced by operand traffic from L2 (28 GB per to_qkv launch = the LTS throughput cap).
+template <int BN, int STAGES, int EPI, bool F16, int EW, int CG>
 __global__ void __launch_bounds__(threads_of(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
-    using L = SmemLayout<BN, STAGES, EPI, EW>;
+    using L = SmemLayout<BN, STAGES, EPI, EW, CG>;
+    static_assert(CG == 1 || (CG == 2 && EPI != EPI_RES), "CTA pairs: EPI_BF16 / EPI_GLU");
     constexpr int kEpiWarps = EW;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t raw = smem_addr(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;            // 128-byte swizzle atoms are 1024-byte aligned
@@ -99,8 +107,13 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
             tma_prefetch_desc(&tm.o[0]);
             if (EPI == EPI_RES) tma_prefetch_desc(&tm.o[1]);
         }
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
+        if constexpr (CG == 2) {
+            tmem_alloc2(tmem_slot, kTmemCols);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(tmem_slot, kTmemCols);
+            tmem_relinquish();
+        }
     } else if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
@@ -108,7 +121,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpiWarps);
+            mbar_init(tempty_bar(a), kEpiWarps * CG);            // pairs: the epilogue warps of both CTAs arrive on CTA 0's
         }
         for (int w = 0; w < kEpiWarps; ++w)
             for (int s = 0; s < kResSlots; ++s) mbar_init(res_bar(w, s), 1);
@@ -116,22 +129,31 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();                   // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int tiles_per_group = g.m_tiles * g.n_tiles;
+    // tiles: (group, row block, column block); a CTA pair walks PAIRS of row blocks, CTA r taking row block 2 pair + r
+    const int m_units = CG == 2 ? (g.m_tiles + 1) / 2 : g.m_tiles;
+    const int tiles_per_group = m_units * g.n_tiles;
     const int total_tiles = tiles_per_group * g.groups;
     const int k_blocks = (g.K + BK - 1) / BK;
+    const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_block = [&](int m_unit) { return CG == 2 ? 2 * m_unit + (int)rank : m_unit; };
 
     if (warp == 0) {
         // ================================= TMA producer =================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
-                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+                const int m_unit = rem / g.n_tiles, n_blk = rem - m_unit * g.n_tiles;
+                const int m_blk = row_block(m_unit);
+                int n_cur = g.N - n_blk * BN;
+                n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
                 if (EPI == EPI_RES && g.accumulate != 0 && g.pf_x != 0) {
                     // the fp32 residual tile this accumulator will be added to: into L2 now, so that the epilogue's
                     // small ring of TMA loads sees L2 latency, not HBM latency
@@ -140,29 +162,39 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 }
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)L::kStage);
                     const uint32_t sa = base + (uint32_t)stage * L::kStage;
-                    tma_load_3d(sa, &tm.a, full_bar(stage), kb * BK, m_blk * BM, grp);
-                    tma_load_3d(sa + L::kA, &tm.b, full_bar(stage), kb * BK, n_blk * BN, grp);
+                    if constexpr (CG == 2) {
+                        // both CTAs' bytes land on CTA 0's barrier, which expects them all
+                        if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * L::kStage));
+                        tma_load_3d_pair(sa, &tm.a, full_bar(stage), kb * BK, m_blk * BM, grp);
+                        // CTA r supplies rows [r n / 2, (r + 1) n / 2) of the n-row B operand (n < BN in a ragged last tile)
+                        tma_load_3d_pair(sa + L::kA, &tm.b, full_bar(stage), kb * BK, n_blk * BN + (int)rank * (n_cur / 2), grp);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), (uint32_t)L::kStage);
+                        tma_load_3d(sa, &tm.a, full_bar(stage), kb * BK, m_blk * BM, grp);
+                        tma_load_3d(sa + L::kA, &tm.b, full_bar(stage), kb * BK, n_blk * BN, grp);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================= MMA issuer =================================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {                             // pairs: CTA 0 issues for both CTAs
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const int rem = tile % tiles_per_group;
                 const int n_blk = rem % g.n_tiles;
                 int n_cur = g.N - n_blk * BN;
                 n_cur = n_cur >= BN ? BN : ((n_cur + 15) & ~15);
-                const uint32_t idesc = umma_idesc_16bit(BM, n_cur, F16);
+                const uint32_t idesc = umma_idesc_16bit(BM * CG, n_cur, F16);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
+                // epilogue has drained this accumulator (pairs: in both CTAs, the peer's warps arrive remotely)
+                if constexpr (CG == 2) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+                else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -174,13 +206,20 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                     for (int k = 0; k < BK / UK; ++k) {
                         // advancing K inside the 128-byte swizzle atom = advancing the start address by 32 bytes
-                        umma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * ((UK * 2) >> 4)), b_desc + (uint64_t)(k * ((UK * 2) >> 4)),
-                                     idesc, (uint32_t)((kb | k) != 0));
+                        if constexpr (CG == 2)
+                            umma_bf16_ss_pair(d_tmem, a_desc + (uint64_t)(k * ((UK * 2) >> 4)), b_desc + (uint64_t)(k * ((UK * 2) >> 4)),
+                                              idesc, (uint32_t)((kb | k) != 0));
+                        else
+                            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(k * ((UK * 2) >> 4)), b_desc + (uint64_t)(k * ((UK * 2) >> 4)),
+                                         idesc, (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(empty_bar(stage));               // ring slot free once these MMAs have read it
+                    // ring slot free once these MMAs have read it (pairs: in both CTAs)
+                    if constexpr (CG == 2) umma_commit_pair(empty_bar(stage));
+                    else umma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));                     // accumulator complete
+                if constexpr (CG == 2) umma_commit_pair(tfull_bar(acc));         // accumulator complete
+                else umma_commit(tfull_bar(acc));
             }
         }
     } else {
@@ -199,46 +238,69 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
             constexpr int kColBlocks = EW / 4;
             constexpr int kWarpCols = BN / kColBlocks >= 64 ? BN / kColBlocks : 64;   // columns per warp, in 64-column steps
             const int wcol0 = half * kWarpCols;                         // first column of this warp inside the tile
-            // partial sums of squares of this lane's row in tile `t` (the previous residual epilogue left them): fetched one
-            // tile ahead, so that their latency is covered by the current tile's arithmetic
+            // The tile sequence of this CTA (tile0, tile0 + tile_step, ...) is decoded incrementally (group, row unit, column
+            // block): the per-tile prologue of the eight epilogue warps was a fifth of their time (integer divisions with long
+            // dependent chains, profiles/r02z_*).
+            const int dn = tile_step % g.n_tiles, dm = tile_step / g.n_tiles;
+            int grp = tile0 / tiles_per_group;
+            int m_unit = (tile0 - grp * tiles_per_group) / g.n_tiles;
+            int n_blk = tile0 - grp * tiles_per_group - m_unit * g.n_tiles;
+            auto advance = [&](int& gr, int& mu, int& nb) {
+                nb += dn;
+                mu += dm;
+                if (nb >= g.n_tiles) { nb -= g.n_tiles; ++mu; }
+                while (mu >= m_units) { mu -= m_units; ++gr; }
+            };
+            // partial sums of squares of this lane's row (the previous residual epilogue left them): the RAW values are fetched
+            // one tile ahead and only summed when the tile comes up, so that their latency hides behind a tile of arithmetic
             const bool ss_vec = (reinterpret_cast<uintptr_t>(g.row_ss) & 15) == 0;
-            auto load_ss = [&](int t) -> float {
-                if (g.row_ss == nullptr || t >= total_tiles) return 1.f;
-                const int grp_ = t / tiles_per_group;
-                const int row_ = ((t - grp_ * tiles_per_group) / g.n_tiles) * BM + q * 32 + lane;
-                if (row_ >= g.M) return 1.f;
-                const float* sp = g.row_ss + ((long long)grp_ * g.side_gs + (long long)row_ * g.side_rs) * g.ss_parts;
-                float ss = 0.f;
+            auto load_ss = [&](bool valid, int gr, int mu) -> float4 {
+                float4 r4 = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (g.row_ss == nullptr || !valid) return r4;
+                const int row_ = row_block(mu) * BM + q * 32 + lane;
+                if (row_ >= g.M) return r4;
+                const float* sp = g.row_ss + ((long long)gr * g.side_gs + (long long)row_ * g.side_rs) * g.ss_parts;
                 if (g.ss_parts == 2 && ss_vec) {
                     const float2 t2 = __ldg(reinterpret_cast<const float2*>(sp));
-                    ss = t2.x + t2.y;
+                    r4 = make_float4(t2.x, t2.y, 0.f, 0.f);
                 } else if (g.ss_parts == 4 && ss_vec) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sp));
-                    ss = (t4.x + t4.y) + (t4.z + t4.w);
+                    r4 = __ldg(reinterpret_cast<const float4*>(sp));
                 } else {
+                    float ss = 0.f;
                     for (int p = 0; p < g.ss_parts; ++p) ss += __ldg(sp + p);
+                    r4 = make_float4(ss, 0.f, 0.f, 0.f);
                 }
-                return ss;
+                return r4;
             };
-            float ss_cur = load_ss((int)blockIdx.x);
+            float4 ss_cur = load_ss(tile0 < total_tiles, grp, m_unit);
             int it = 0;
-            for (int tile = (int)blockIdx.x; tile < total_tiles; tile += (int)gridDim.x, ++it) {
-                const int grp = tile / tiles_per_group;
-                const int rem = tile - grp * tiles_per_group;
-                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+                const int m_blk = row_block(m_unit);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 const int row0 = m_blk * BM + q * 32;
                 const int row = row0 + lane;
-                const float ss_next = load_ss(tile + (int)gridDim.x);
+                const int cur_grp = grp, cur_n = n_blk;
+                advance(grp, m_unit, n_blk);                                  // (grp, m_unit, n_blk) now name the NEXT tile
+                const float4 ss_next = load_ss(tile + tile_step < total_tiles, grp, m_unit);
                 float rs = 1.f;
-                if (g.row_ss != nullptr && row < g.M) rs = g.ss_scale / fmaxf(sqrtf(ss_cur), g.ss_eps);
+                if (g.row_ss != nullptr && row < g.M)
+                    rs = g.ss_scale / fmaxf(sqrtf((ss_cur.x + ss_cur.y) + (ss_cur.z + ss_cur.w)), g.ss_eps);
                 ss_cur = ss_next;
                 const float2 rs2 = make_float2(rs, rs);
-                int pos = 0;
-                if (g.cos_sin != nullptr) pos = (int)(((uint32_t)row / (uint32_t)g.pos_div) % (uint32_t)g.pos_mod);
-                const int n0 = n_blk * BN;
+                const int n0 = cur_n * BN;
                 const int n_cols = min(BN, g.N - n0);
+                int pos = 0;
+                const bool rot_tile = g.cos_sin != nullptr && n0 + wcol0 < g.rot_cols;
+                if (rot_tile) {
+                    pos = (int)(((uint32_t)row / (uint32_t)g.pos_div) % (uint32_t)g.pos_mod);
+                    // this lane's (cos, sin) row (256 bytes) into L1 while the main loop of the tile still runs
+                    const char* cr = reinterpret_cast<const char*>(g.cos_sin) + (long long)pos * 256;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(cr));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(cr + 128));
+                }
+                if (g.bias != nullptr && lane < kWarpCols / 32 && n0 + wcol0 + lane * 32 < g.N)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.bias + (long long)cur_grp * g.N + n0 + wcol0 + lane * 32));
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 int steps = 0;
@@ -246,7 +308,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 if (steps == 0) {                                   // nothing of this tile is ours (ragged / narrow tile)
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                 }
                 for (int st = 0; st < steps; ++st) {
                     uint32_t r[2][32];
@@ -258,7 +320,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     if (st == steps - 1) {                      // our part of the accumulator is in registers
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                     }
                     const int col0 = n0 + tcol;
                     const bool rot = g.cos_sin != nullptr && col0 < g.rot_cols;
@@ -270,11 +332,16 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     for (int h = 0; h < 2; ++h) {
                         float2 v[16];
                         if (g.bias != nullptr) {
-                            const float4* bp = reinterpret_cast<const float4*>(g.bias + (long long)grp * g.N + col0 + h * 32);
+                            // all eight loads go out together: the index is clamped instead of predicated (a predicated load is
+                            // a branch per load, each waiting for the one before); columns >= N are clipped by the TMA store
+                            const float* bg = g.bias + (long long)cur_grp * g.N;
+                            float4 bq[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                bq[j] = __ldg(reinterpret_cast<const float4*>(bg + min(col0 + h * 32 + j * 4, g.N - 4)));
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (col0 + h * 32 + j * 4 < g.N) b = __ldg(bp + j);
+                                const float4 b = bq[j];
                                 v[2 * j] = __ffma2_rn(make_float2(__uint_as_float(r[h][4 * j]), __uint_as_float(r[h][4 * j + 1])), rs2,
                                                       make_float2(b.x, b.y));
                                 v[2 * j + 1] = __ffma2_rn(make_float2(__uint_as_float(r[h][4 * j + 2]), __uint_as_float(r[h][4 * j + 3])),
@@ -332,10 +399,10 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                     __syncwarp();
                     if (lane == 0) {
                         if constexpr (EPI == EPI_GLU) {
-                            tma_store_3d(&tm.o[0], ebuf, col0 >> 1, row0, grp);
+                            tma_store_3d(&tm.o[0], ebuf, col0 >> 1, row0, cur_grp);
                         } else {
                             const int oi = col0 / g.out_split;
-                            tma_store_3d(&tm.o[oi], ebuf, col0 - oi * g.out_split, row0, grp);
+                            tma_store_3d(&tm.o[oi], ebuf, col0 - oi * g.out_split, row0, cur_grp);
                         }
                         bulk_commit();
                     }
@@ -450,7 +517,12 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG == 2) {
+        cluster_sync_all();          // neither CTA leaves (or frees tensor memory) while the pair still works on its behalf
+        if (warp == 0) tmem_dealloc2(tmem_base, kTmemCols);
+    } else {
+        if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -503,31 +575,62 @@ static DevInfo& dev_info(int dev) {
     return d;
 }
 
-template <int BN, int STAGES, int EPI, bool F16, int EW>
+template <int BN, int STAGES, int EPI, bool F16, int EW, int CG>
 static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
-    using L = SmemLayout<BN, STAGES, EPI, EW>;
+    using L = SmemLayout<BN, STAGES, EPI, EW, CG>;
     static_assert(L::kDynamic <= 232448, "shared memory budget");
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevInfo& d = dev_info(dev);
+    auto kernel = gemm_bf16_kernel<BN, STAGES, EPI, F16, EW, CG>;
     if (!d.attr[slot]) {
-        e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, F16, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return e;
         d.attr[slot] = true;
     }
-    const int total = g.m_tiles * g.n_tiles * g.groups;
-    int grid = total < d.n_sm ? total : d.n_sm;
-    if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-    gemm_bf16_kernel<BN, STAGES, EPI, F16, EW><<<grid, threads_of(EW), L::kDynamic, stream>>>(tm, g);
-    count_launch();
-    return cudaGetLastError();
+    const int units = (CG == 2 ? (g.m_tiles + 1) / 2 : g.m_tiles) * g.n_tiles * g.groups;
+    int grid = units * CG < d.n_sm ? units * CG : (d.n_sm / CG) * CG;
+    if (g.max_ctas > 0 && grid > g.max_ctas) grid = (g.max_ctas / CG) * CG > 0 ? (g.max_ctas / CG) * CG : CG;
+    if constexpr (CG == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)threads_of(EW));
+        cfg.dynamicSmemBytes = L::kDynamic;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, tm, g);
+        count_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    } else {
+        kernel<<<grid, threads_of(EW), L::kDynamic, stream>>>(tm, g);
+        count_launch();
+        return cudaGetLastError();
+    }
 }
 
-template <int BN, int STAGES, int EPI, int EW = 8>
+template <int BN, int STAGES, int EPI, int EW = 8, int CG = 1>
 static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
-    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true, EW>(tm, g, slot + 12, stream)
-                  : launch_cfg1<BN, STAGES, EPI, false, EW>(tm, g, slot, stream);
+    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true, EW, CG>(tm, g, slot + 12, stream)
+                  : launch_cfg1<BN, STAGES, EPI, false, EW, CG>(tm, g, slot, stream);
+}
+
+// AL_GEMM_PAIRS=1 selects CTA pairs (cta_group::2) for the 256-wide EPI_BF16 / EPI_GLU tiles.  Measured
+// (profiles/r02y_gemm_cta_pairs.log): the plain GEMM gains 8-12 % (FF1 shape 2.71 -> 2.53 ms: less operand traffic from L2,
+// 6-deep ring), but with the fused epilogues the kernel is paced by the epilogue warps and the pair adds cross-CTA hand-offs:
+// to_qkv 2.12 -> 2.25 ms, contract line 161.2 -> 158.7 audio-s/s.  Off by default.
+static bool cta_pairs() {
+    static const bool on = [] {
+        const char* e = getenv("AL_GEMM_PAIRS");
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
 }
 
 }  // namespace tc
@@ -565,7 +668,9 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     if (!make_map(&tm.a, c.A, dt16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(A) failed";
-    if (!make_map(&tm.b, c.W, dt16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, BN,
+    // CTA pairs (256-wide EPI_BF16 / EPI_GLU tiles): each CTA loads half of the W tile
+    const bool pairs = c.epi != EPI_RES && BN == 256 && cta_pairs();
+    if (!make_map(&tm.b, c.W, dt16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, pairs ? BN / 2 : BN,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(W) failed";
     if (c.epi == EPI_RES) {
@@ -598,7 +703,8 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
             return "cuTensorMapEncodeTiled(glu out) failed";
         tm.o[1] = tm.o[2] = tm.o[3] = tm.o[0];
         g.out_split = c.N;
-        if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_GLU>(tm, g, 5, stream);
+        if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 6, EPI_GLU, 8, 2>(tm, g, 8, stream);
+        else if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_GLU>(tm, g, 5, stream);
         else if (BN == 128) *cuda_err = launch_cfg<128, 6, EPI_GLU>(tm, g, 6, stream);
         else *cuda_err = launch_cfg<64, 8, EPI_GLU>(tm, g, 7, stream);
         return *cuda_err == cudaSuccess ? nullptr : "launch failed";
@@ -622,7 +728,8 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
                       c.o_group_stride[src], 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
             return "cuTensorMapEncodeTiled(out) failed";
     }
-    if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_BF16>(tm, g, 1, stream);
+    if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2>(tm, g, 9, stream);
+    else if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_BF16>(tm, g, 1, stream);
     else if (BN == 128) *cuda_err = launch_cfg<128, 6, EPI_BF16>(tm, g, 2, stream);
     else *cuda_err = launch_cfg<64, 8, EPI_BF16>(tm, g, 3, stream);
     return *cuda_err == cudaSuccess ? nullptr : "launch failed";
