@@ -76,9 +76,15 @@ struct SmemLayout {
 // published to both CTAs by multicast commits, and the epilogue warps of both CTAs release an accumulator on CTA 0's barrier.
 // A CTA then moves 32 KB instead of 48 KB of operands per 128 x 256 x 64 block and the ring is 6 deep instead of 4: the
 // K = 512 shapes of the network are paced by operand traffic from L2 (28 GB per to_qkv launch = the LTS throughput cap).
-template <int BN, int STAGES, int EPI, bool F16, int EW, int CG>
+// VAR = what the EPI_BF16 epilogue computes, fixed at compile time for the shapes of the network (one kernel with every
+// ingredient behind run-time flags is 44 KB of SASS and 159 registers): VAR_ANY = run-time flags (any combination),
+// VAR_ROT = row scale + bias + rotary (to_qkv + to_gates), VAR_GELU = row scale + bias + GELU (FeedForward Linear 1).
+enum { VAR_ANY = 0, VAR_ROT = 1, VAR_GELU = 2 };
+template <int BN, int STAGES, int EPI, bool F16, int EW, int CG, int VAR = VAR_ANY>
 __global__ void __launch_bounds__(threads_of(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
+    constexpr bool kMayRot = VAR == VAR_ANY || VAR == VAR_ROT;
+    constexpr bool kFixed = VAR != VAR_ANY;
     using L = SmemLayout<BN, STAGES, EPI, EW, CG>;
     static_assert(CG == 1 || (CG == 2 && EPI != EPI_RES), "CTA pairs: EPI_BF16 / EPI_GLU");
     constexpr int kEpiWarps = EW;
@@ -291,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 const int n0 = cur_n * BN;
                 const int n_cols = min(BN, g.N - n0);
                 int pos = 0;
-                const bool rot_tile = g.cos_sin != nullptr && n0 + wcol0 < g.rot_cols;
+                const bool rot_tile = kMayRot && g.cos_sin != nullptr && n0 + wcol0 < g.rot_cols;
                 if (rot_tile) {
                     pos = (int)(((uint32_t)row / (uint32_t)g.pos_div) % (uint32_t)g.pos_mod);
                     // this lane's (cos, sin) row (256 bytes) into L1 while the main loop of the tile still runs
@@ -323,7 +329,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                         if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                     }
                     const int col0 = n0 + tcol;
-                    const bool rot = g.cos_sin != nullptr && col0 < g.rot_cols;
+                    const bool rot = kMayRot && g.cos_sin != nullptr && col0 < g.rot_cols;
                     // the staging buffer is still being read by the TMA store of the previous step
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
@@ -331,7 +337,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         float2 v[16];
-                        if (g.bias != nullptr) {
+                        if (kFixed || g.bias != nullptr) {
                             // all eight loads go out together: the index is clamped instead of predicated (a predicated load is
                             // a branch per load, each waiting for the one before); columns >= N are clipped by the TMA store
                             const float* bg = g.bias + (long long)cur_grp * g.N;
@@ -363,10 +369,10 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                                 v[2 * j + 1] = make_float2(b.x * c.z - b.y * c.w, b.y * c.z + b.x * c.w);
                             }
                         }
-                        if (g.act == ACT_GELU) {
+                        if (VAR == VAR_GELU || (!kFixed && g.act == ACT_GELU)) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = gelu_erf2(v[j]);
-                        } else if (g.act == ACT_TANH) {
+                        } else if (!kFixed && g.act == ACT_TANH) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = make_float2(tanh_fast(v[j].x), tanh_fast(v[j].y));
                         }
@@ -561,7 +567,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, in
 
 struct DevInfo {
     int n_sm = 0;
-    bool attr[24] = {};
+    bool attr[32] = {};
 };
 static DevInfo& dev_info(int dev) {
     static DevInfo info[64];
@@ -575,7 +581,7 @@ static DevInfo& dev_info(int dev) {
     return d;
 }
 
-template <int BN, int STAGES, int EPI, bool F16, int EW, int CG>
+template <int BN, int STAGES, int EPI, bool F16, int EW, int CG, int VAR = VAR_ANY>
 static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
     using L = SmemLayout<BN, STAGES, EPI, EW, CG>;
     static_assert(L::kDynamic <= 232448, "shared memory budget");
@@ -583,7 +589,7 @@ static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cud
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     DevInfo& d = dev_info(dev);
-    auto kernel = gemm_bf16_kernel<BN, STAGES, EPI, F16, EW, CG>;
+    auto kernel = gemm_bf16_kernel<BN, STAGES, EPI, F16, EW, CG, VAR>;
     if (!d.attr[slot]) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return e;
@@ -615,10 +621,10 @@ static cudaError_t launch_cfg1(const Tmaps& tm, const GemmArgs& g, int slot, cud
     }
 }
 
-template <int BN, int STAGES, int EPI, int EW = 8, int CG = 1>
+template <int BN, int STAGES, int EPI, int EW = 8, int CG = 1, int VAR = VAR_ANY>
 static cudaError_t launch_cfg(const Tmaps& tm, const GemmArgs& g, int slot, cudaStream_t stream) {
-    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true, EW, CG>(tm, g, slot + 12, stream)
-                  : launch_cfg1<BN, STAGES, EPI, false, EW, CG>(tm, g, slot, stream);
+    return g.fp16 ? launch_cfg1<BN, STAGES, EPI, true, EW, CG, VAR>(tm, g, slot + 16, stream)
+                  : launch_cfg1<BN, STAGES, EPI, false, EW, CG, VAR>(tm, g, slot, stream);
 }
 
 // AL_GEMM_PAIRS=1 selects CTA pairs (cta_group::2) for the 256-wide EPI_BF16 / EPI_GLU tiles.  Measured
@@ -728,7 +734,13 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
                       c.o_group_stride[src], 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
             return "cuTensorMapEncodeTiled(out) failed";
     }
+    // the two shapes that carry the step get their own instantiation (AL_GEMM_VARIANTS=0: the general kernel for everything)
+    static const bool variants = [] { const char* e = getenv("AL_GEMM_VARIANTS"); return !(e != nullptr && e[0] == '0'); }();
+    const bool v_rot = variants && c.bias && c.row_ss && c.cos_sin && c.act == ACT_NONE;
+    const bool v_gelu = variants && c.bias && c.row_ss && !c.cos_sin && c.act == ACT_GELU;
     if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2>(tm, g, 9, stream);
+    else if (BN == 256 && v_rot) *cuda_err = launch_cfg<256, 4, EPI_BF16, 8, 1, VAR_ROT>(tm, g, 10, stream);
+    else if (BN == 256 && v_gelu) *cuda_err = launch_cfg<256, 4, EPI_BF16, 8, 1, VAR_GELU>(tm, g, 11, stream);
     else if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_BF16>(tm, g, 1, stream);
     else if (BN == 128) *cuda_err = launch_cfg<128, 6, EPI_BF16>(tm, g, 2, stream);
     else *cuda_err = launch_cfg<64, 8, EPI_BF16>(tm, g, 3, stream);
