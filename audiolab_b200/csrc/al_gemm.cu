@@ -86,7 +86,6 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
     constexpr bool kMayRot = VAR == VAR_ANY || VAR == VAR_ROT;
     constexpr bool kFixed = VAR != VAR_ANY;
     using L = SmemLayout<BN, STAGES, EPI, EW, CG>;
-    static_assert(CG == 1 || (CG == 2 && EPI != EPI_RES), "CTA pairs: EPI_BF16 / EPI_GLU");
     constexpr int kEpiWarps = EW;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     extern __shared__ unsigned char smem_dyn[];
@@ -422,15 +421,15 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
             // (prefetched into L2 by the producer warp when the tile's main loop started) into a 2-slot ring, is
             // updated in place and leaves by TMA together with its bf16 image.
             constexpr int CH = BN / 64;                                 // chunks per tile per warp
-            const int n_my = (int)blockIdx.x < total_tiles ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+            const int n_my = tile0 < total_tiles ? (total_tiles - tile0 + tile_step - 1) / tile_step : 0;
             const long long n_chunks = (long long)n_my * CH;
             auto coords = [&](long long gc, int& grp, int& row0, int& col0, int& tcol) {
                 const int it = (int)(gc / CH), c = (int)(gc - (long long)it * CH);
-                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int tile = tile0 + it * tile_step;
                 grp = tile / tiles_per_group;
                 const int rem = tile - grp * tiles_per_group;
-                const int m_blk = rem / g.n_tiles, n_blk = rem - m_blk * g.n_tiles;
-                row0 = m_blk * BM + q * 32;
+                const int m_unit = rem / g.n_tiles, n_blk = rem - m_unit * g.n_tiles;
+                row0 = row_block(m_unit) * BM + q * 32;
                 tcol = half * (BN / 2) + c * 32;
                 col0 = n_blk * BN + tcol;
             };
@@ -468,7 +467,7 @@ gemm_bf16_kernel(const __grid_constant__ Tmaps tm, const GemmArgs g) {
                 if (c == CH - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) { if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                 }
                 unsigned char* rb = ebuf_ptr + slot * 4096 + lane * 128;
                 unsigned char* xb = ebuf_ptr + kResSlots * 4096 + lane * 64;
@@ -674,8 +673,12 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     if (!make_map(&tm.a, c.A, dt16, 2, c.K, c.M, c.groups, c.lda, c.a_group_stride, BK, BM,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(A) failed";
-    // CTA pairs (256-wide EPI_BF16 / EPI_GLU tiles): each CTA loads half of the W tile
-    const bool pairs = c.epi != EPI_RES && BN == 256 && cta_pairs();
+    // CTA pairs (each CTA loads half of the W tile).  Residual epilogue: on for long reductions -- FF Linear 2 (K = 2048) is
+    // paced by operand traffic from L2 (32 GB per launch) and gains 6 % (3.00 -> 2.81 ms), to_out (K = 512) is paced by the
+    // residual stream in HBM and loses 12 % to the pair's hand-offs (profiles/r02y_gemm_cta_pairs.log); AL_GEMM_RES_PAIRS=0
+    // switches them off.  EPI_BF16 / EPI_GLU: opt-in, see cta_pairs().
+    static const bool res_pairs = [] { const char* e = getenv("AL_GEMM_RES_PAIRS"); return !(e != nullptr && e[0] == '0'); }();
+    const bool pairs = BN == 256 && (c.epi == EPI_RES ? (res_pairs && c.K >= 1024) : cta_pairs());
     if (!make_map(&tm.b, c.W, dt16, 2, c.K, c.N, c.groups, c.ldw, c.w_group_stride, BK, pairs ? BN / 2 : BN,
                   CU_TENSOR_MAP_SWIZZLE_128B))
         return "cuTensorMapEncodeTiled(W) failed";
@@ -694,7 +697,8 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
             return "cuTensorMapEncodeTiled(x32 prefetch) failed";
         tm.o[3] = tm.o[1];
         g.out_split = c.N;
-        if (BN == 256) *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
+        if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 4, EPI_RES, 8, 2>(tm, g, 12, stream);
+        else if (BN == 256) *cuda_err = launch_cfg<256, 3, EPI_RES>(tm, g, 0, stream);
         else *cuda_err = launch_cfg<128, 4, EPI_RES>(tm, g, 4, stream);
         return *cuda_err == cudaSuccess ? nullptr : "launch failed";
     }
