@@ -742,7 +742,9 @@ const char* launch_gemm_bf16(const GemmCall& c, cudaStream_t stream, cudaError_t
     static const bool variants = [] { const char* e = getenv("AL_GEMM_VARIANTS"); return !(e != nullptr && e[0] == '0'); }();
     const bool v_rot = variants && c.bias && c.row_ss && c.cos_sin && c.act == ACT_NONE;
     const bool v_gelu = variants && c.bias && c.row_ss && !c.cos_sin && c.act == ACT_GELU;
-    if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2>(tm, g, 9, stream);
+    if (BN == 256 && pairs && v_rot) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2, VAR_ROT>(tm, g, 13, stream);
+    else if (BN == 256 && pairs && v_gelu) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2, VAR_GELU>(tm, g, 14, stream);
+    else if (BN == 256 && pairs) *cuda_err = launch_cfg<256, 6, EPI_BF16, 8, 2>(tm, g, 9, stream);
     else if (BN == 256 && v_rot) *cuda_err = launch_cfg<256, 4, EPI_BF16, 8, 1, VAR_ROT>(tm, g, 10, stream);
     else if (BN == 256 && v_gelu) *cuda_err = launch_cfg<256, 4, EPI_BF16, 8, 1, VAR_GELU>(tm, g, 11, stream);
     else if (BN == 256) *cuda_err = launch_cfg<256, 4, EPI_BF16>(tm, g, 1, stream);
