@@ -92,6 +92,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
                  "r"(bytes)
                  : "memory");
 }
+// bulk asynchronous global -> shared copy whose bytes are counted on an mbarrier (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -103,6 +109,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival that also announces `bytes` of bulk copies (issued BEFORE this call: the emulation copies at issue time)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -119,6 +129,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 #else   // host emulation (tools/cpu_emul): the same protocol on std::atomic_ref, bulk copies done at issue time
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) { std::memcpy(gdst, ssrc, bytes); }
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t*) { std::memcpy(sdst, gsrc, bytes); }
 __device__ __forceinline__ void bulk_commit() {}
 __device__ __forceinline__ void bulk_wait_read_all() {}
 __device__ __forceinline__ void bulk_wait_all() {}
@@ -137,6 +148,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
         if (a.compare_exchange_weak(v, nv)) return;
     }
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t) { mbar_arrive(bar); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     std::atomic_ref<uint64_t> a(*bar);
     while ((a.load() & 1) == parity) std::this_thread::yield();

@@ -378,6 +378,212 @@ istft_pk2_kernel(const IstftPkParams p) {
 
 #undef IP_ISSUE
 
+// ---- ring-buffered form (default) ---------------------------------------------------------------------------------------
+// The kernel above keeps HBM latency away with a four-deep REGISTER pipeline of row loads: 128 of its 255 registers, 8 warps
+// per SM, and its three phases (rows -> Z, iFFT, overlap-add) alternate on CTA barriers -- 0.39 of the HBM roofline, latency
+// bound at 11 % of the warp slots (profiles/r01j_ncu_full_istft_in_bench.txt).  Here ONE producer warp streams the spectrum
+// and mask rows of the CTA's frames, in frame order, into a ring of kRgSlots shared-memory slots with bulk asynchronous
+// copies (cp.async.bulk, bytes counted on an mbarrier), and kRgWarps consumer warps take a frame each: Z from the slot
+// (LDS.128, no global-load registers), slot handed back, iFFT, window, park; then the consumers alone meet on a named barrier
+// for the overlap-add of the round.  Rows for the next rounds keep arriving during the iFFT and the overlap-add.
+constexpr int kRgWarps = 6;               // consumer warps = frames per round
+constexpr int kRgSlots = 3;               // frames in flight / being read
+constexpr int kRgThreads = (kRgWarps + 1) * 32;
+constexpr int kRgSlotF4 = 2 * kIpBins;    // float4 per slot: spectrum row, mask row
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+#ifndef AL_CPU_EMUL
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+#else
+    (void)id; (void)n;
+    __syncthreads();
+#endif
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(kRgThreads, 1)
+istft_pk3_kernel(const IstftPkParams p) {
+    constexpr int W = kRgWarps;
+    AL_DYN_SMEM(unsigned char, smem_raw);
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
+    float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
+    float4* s_scr = reinterpret_cast<float4*>(s_ctw + 1024);                   // [W][kScrF4]
+    float4* s_ring = s_scr + W * kScrF4;                                       // [kRgSlots][kRgSlotF4]
+    float2* s_carry = reinterpret_cast<float2*>(s_ring + kRgSlots * kRgSlotF4);   // [2048 - hop] (L, R)
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_carry + (kIpN - p.hop));  // [kRgSlots]
+    uint64_t* s_empty = s_full + kRgSlots;                                      // [kRgSlots]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
+    const int chunk = g / p.stems, stem = g - chunk * p.stems;
+    const int hop = p.hop, T = p.n_frames;
+    const int carry_len = kIpN - hop;
+    const int kOla_K = (kIpN + hop - 1) / hop;          // frames that can cover one position (<= kIpKMax: the launcher checks)
+
+    const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
+    const long long Pend = (long long)p.out_start + p.out_len;
+    const long long Pb = min(Pa + (long long)p.hops_per_cta * hop, Pend);
+    if (Pa >= Pb) return;
+    int ta = (int)((Pa - kIpN) / hop) + 1;              // first frame touching Pa
+    if (Pa < kIpN) ta = 0;
+    ta = max(ta, 0);
+    const int tb = min((int)((Pb - 1) / hop), T - 1);   // last frame touching Pb - 1
+    const int t_last = (int)((Pb - 1) / hop);           // rounds run until the carry is flushed up to Pb
+
+    const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
+    float* __restrict__ dst0 = p.dst + ((long long)stem * 2) * p.dst_ch_stride + (long long)chunk * p.dst_chunk_stride + place;
+    float* __restrict__ dst1 = dst0 + p.dst_ch_stride;
+    const float4* __restrict__ X = p.spec + (long long)(p.spec_has_stems ? g : chunk) * T * kIpBins;
+    const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
+
+    if (tid == 0) {
+        for (int s = 0; s < kRgSlots; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], 1);
+        }
+#ifndef AL_CPU_EMUL
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        fence_async_smem();
+    }
+    for (int i = tid; i < 1024; i += kRgThreads) {
+        s_tw[i] = p.tw[i];
+        s_ctw[i] = p.ctw[i];
+    }
+    for (int i = tid; i < carry_len; i += kRgThreads) s_carry[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    if (warp == W) {
+        // ================================= producer =================================
+        if (lane == 0) {
+            for (int t = ta; t <= tb; ++t) {
+                const int it = t - ta, s = it % kRgSlots;
+                mbar_wait(&s_empty[s], ((it / kRgSlots) & 1) ^ 1);
+                float4* slot = s_ring + s * kRgSlotF4;
+                bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, &s_full[s]);
+                if (MASK) bulk_load_g2s(slot + kIpBins, M + (long long)t * kIpBins, kIpBins * 16, &s_full[s]);
+                mbar_arrive_expect_tx(&s_full[s], (MASK ? 2u : 1u) * kIpBins * 16u);
+            }
+        }
+        return;
+    }
+
+    // ================================= consumers =================================
+    const float2* __restrict__ g_win = reinterpret_cast<const float2*>(p.window);   // (w[2k], w[2k+1]), through L1
+    float4* scr = s_scr + warp * kScrF4;
+    constexpr int kCons = W * 32;
+    for (int tr = ta; tr <= t_last; tr += W) {
+        const int nf = max(0, min(W, tb - tr + 1));   // live frames of this round (CTA-uniform)
+        const int t = tr + warp;
+        const bool live = warp < nf;                    // warp-uniform
+        if (live) {
+            float2 re[32], im[32];
+            const int it = t - ta, s = it % kRgSlots;
+            // Warps w and w + kRgSlots of a round share a slot (consecutive uses).  A parity wait may only look ONE phase ahead,
+            // so the later warp first waits for the earlier warp's use to land, then for its own.
+            for (int e = warp / kRgSlots; e >= 0; --e) mbar_wait(&s_full[s], ((it / kRgSlots) - e) & 1);
+            const float4* __restrict__ xs = s_ring + s * kRgSlotF4;
+            const float4* __restrict__ ms = xs + kIpBins;
+            // ---- Z from the rows in the slot: register pairs (r, 31 - r), k1 = 32 r + lane, k2 = 32 (31 - r) + lane
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int k1 = 32 * r + lane, k2 = 32 * (31 - r) + lane;
+                float2 p1r, p1i, q2r, q2i, p2r, p2i, q1r, q1i;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                ip_product<MASK>(xs[k1], MASK ? ms[k1] : z, p1r, p1i);
+                ip_product<MASK>(xs[1024 - k2], MASK ? ms[1024 - k2] : z, q2r, q2i);
+                ip_product<MASK>(xs[k2], MASK ? ms[k2] : z, p2r, p2i);
+                ip_product<MASK>(xs[1024 - k1], MASK ? ms[1024 - k1] : z, q1r, q1i);
+                if (r == 0 && lane == 0) {   // k1 = 0: C2R ignores Im of the DC and Nyquist bins
+                    p1i = make_float2(0.f, 0.f);
+                    q1i = make_float2(0.f, 0.f);
+                }
+                const float2 w1 = s_ctw[k1], w2 = s_ctw[k2];
+                ip_combine(p1r, p1i, q1r, q1i, w1, re[r], im[r]);
+                ip_combine(p2r, p2i, q2r, q2i, w2, re[31 - r], im[31 - r]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);   // the slot goes back to the producer
+            warp_fft1024p_wide<true>(re, im, scr, s_tw, lane);
+            // z[k] = (x[2k], x[2k+1]) * n_fft; window (carries 1 / n_fft) and park the frame: scr[k] = samples 2k, 2k+1
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 w = __ldg(g_win + 32 * r + lane);
+                const float2 ev = pscale(re[r], w.x), od = pscale(im[r], w.y);
+                scr[32 * r + lane] = make_float4(ev.x, ev.y, od.x, od.y);
+            }
+        }
+        named_bar_sync(1, kCons);   // all frames of the round are parked
+
+        // ---- overlap-add of the round (the register form of istft_pk2_kernel), consumers only ------------------
+        const long long S = (long long)tr * hop;
+        const float2* cin = s_carry;
+        float2* cout = s_carry;
+        const int emit = W * hop;
+        const int span = emit + carry_len;
+        constexpr int NH = W + kIpKMax - 1;
+        const long long rel = S - p.out_start;
+        const bool interior = p.ola_fast && nf == W && S >= Pa && S + emit <= Pb && place + rel >= 0 &&
+                              place + rel + emit <= p.dst_limit;
+        for (int j = tid; j < hop; j += kCons) {
+            const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
+            const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
+            float ev[W], wg[W];
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+                const long long P = S + h * hop + j;
+                const bool mine = interior || (P >= Pa && P < Pb);
+                ev[h] = mine ? __ldg(p.inv_env + P) : 0.f;
+                wg[h] = (mine && p.weight) ? __ldg(p.weight + (P - p.out_start)) : 1.f;
+            }
+            float2 out[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const int i = h * hop + j;
+                out[h] = (i < carry_len) ? cin[i] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int f = 0; f < W; ++f) {
+                if (f < nf) {
+                    const float2* __restrict__ sf = sj + f * (2 * kScrF4);
+#pragma unroll
+                    for (int k = 0; k < kIpKMax; ++k) {
+                        if (k <= kj) {
+                            const float2 v = sf[k * hop];
+                            out[f + k].x += v.x;
+                            out[f + k].y += v.y;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+                const long long P = S + h * hop + j;
+                if (interior || (P >= Pa && P < Pb)) {
+                    const long long pp = P - p.out_start;
+                    float v0 = out[h].x * ev[h], v1 = out[h].y * ev[h];
+                    if (p.weight) {
+                        v0 *= wg[h];
+                        v1 *= wg[h];
+                    }
+                    const long long qd = place + pp;
+                    if (interior || (qd >= 0 && qd < p.dst_limit)) {
+                        dst0[pp] = v0;
+                        dst1[pp] = v1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = W; h < NH; ++h) {
+                const int i = h * hop + j;
+                if (i < span) cout[i - emit] = out[h];
+            }
+        }
+        named_bar_sync(1, kCons);   // the scratches may be overwritten by the next round's frames
+    }
+}
+
+
 // segments per row: minimise waves * rounds per segment (a round = kIpWarps frames; each segment re-computes the
 // ceil((2048 - hop) / hop) frames that precede its first owned sample)
 static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int kIpWarps, int* hpc_out, int* segs_out) {
@@ -408,12 +614,42 @@ static size_t ip_launch_shape(IstftPkParams& p, int n_chunks, int n_sm, int W) {
     ip_tiling(rows, total_hops, p.hop, n_sm * (kIpSmWarps / W), W, &p.hops_per_cta, &p.segs);
     return (size_t)3 * 1024 * sizeof(float2) + (size_t)W * kScrF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2);
 }
+// launch shape of istft_pk3_kernel: one CTA per SM
+static size_t rg_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
+    const int rows = n_chunks * p.stems;
+    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
+    ip_tiling(rows, total_hops, p.hop, n_sm, kRgWarps, &p.hops_per_cta, &p.segs);
+    return (size_t)2 * 1024 * sizeof(float2) + (size_t)kRgWarps * kScrF4 * sizeof(float4) +
+           (size_t)kRgSlots * kRgSlotF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2) + 2 * kRgSlots * sizeof(uint64_t);
+}
 // [emul-end]
 
 cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
     IstftPkParams p = p0;
     const int n_sm = sm_count();
     const int rows = n_chunks * p.stems;
+    // the ring-buffered kernel (default; AL_IP_RING=0 selects the register-pipelined one): hop >= 410 (register-form overlap-add)
+    static const int ring = (getenv("AL_IP_RING") && atoi(getenv("AL_IP_RING")) == 0) ? 0 : 1;
+    if (ring && (kIpN + p.hop - 1) / p.hop <= kIpKMax) {
+        static const int ola_fast3 = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
+        p.ola_fast = ola_fast3;
+        p.l2_prefetch = 0;
+        const size_t smem3 = rg_launch_shape(p, n_chunks, n_sm);
+        if (smem3 <= (size_t)227 * 1024) {
+            static PerDeviceOnce attr3[2];
+            PerDeviceOnce& a3 = attr3[p.mask ? 1 : 0];
+            if (a3.needed()) {
+                cudaError_t e = p.mask ? cudaFuncSetAttribute(istft_pk3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                       : cudaFuncSetAttribute(istft_pk3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                if (e != cudaSuccess) return e;
+                a3.mark();
+            }
+            if (p.mask) istft_pk3_kernel<true><<<(unsigned)(rows * p.segs), kRgThreads, smem3, stream>>>(p);
+            else istft_pk3_kernel<false><<<(unsigned)(rows * p.segs), kRgThreads, smem3, stream>>>(p);
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     static const int W = (getenv("AL_IP_WARPS") && atoi(getenv("AL_IP_WARPS")) == 8) ? 8 : 4;
     static const int ola_fast = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
     p.ola_fast = ola_fast;
