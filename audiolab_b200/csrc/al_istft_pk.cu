@@ -382,12 +382,15 @@ istft_pk2_kernel(const IstftPkParams p) {
 // The kernel above keeps HBM latency away with a four-deep REGISTER pipeline of row loads: 128 of its 255 registers, 8 warps
 // per SM, and its three phases (rows -> Z, iFFT, overlap-add) alternate on CTA barriers -- 0.39 of the HBM roofline, latency
 // bound at 11 % of the warp slots (profiles/r01j_ncu_full_istft_in_bench.txt).  Here ONE producer warp streams the spectrum
-// and mask rows of the CTA's frames, in frame order, into a ring of kRgSlots shared-memory slots with bulk asynchronous
-// copies (cp.async.bulk, bytes counted on an mbarrier), and kRgWarps consumer warps take a frame each: Z from the slot
-// (LDS.128, no global-load registers), slot handed back, iFFT, window, park; then the consumers alone meet on a named barrier
-// for the overlap-add of the round.  Rows for the next rounds keep arriving during the iFFT and the overlap-add.
-constexpr int kRgWarps = 6;               // consumer warps = frames per round
-constexpr int kRgSlots = 3;               // frames in flight / being read
+// and mask rows of the CTA's frames, in frame order, into a ring of kRgTeam shared-memory slots with bulk asynchronous
+// copies (cp.async.bulk, bytes counted on an mbarrier), and TWO teams of kRgTeam consumer warps take alternate rounds of
+// kRgTeam frames: a warp builds Z from its slot (LDS.128, no global-load registers), hands the slot back, runs the iFFT,
+// windows and parks its frame; then its team alone does the overlap-add of the round.  While team A transforms and
+// overlap-adds round i, the rows of round i + 1 arrive and team B consumes them: the load latency of a round hides behind
+// the arithmetic of the round before.  The overlap-adds stay in round order (a token passed between the teams on named
+// barriers), so the carry between rounds and the summation order are those of istft_pk2_kernel.
+constexpr int kRgTeam = 3;                // consumer warps per team = frames per round = ring slots
+constexpr int kRgWarps = 2 * kRgTeam;     // consumer warps
 constexpr int kRgThreads = (kRgWarps + 1) * 32;
 constexpr int kRgSlotF4 = 2 * kIpBins;    // float4 per slot: spectrum row, mask row
 
@@ -399,19 +402,28 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
     __syncthreads();
 #endif
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+#ifndef AL_CPU_EMUL
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+#else
+    (void)id; (void)n;
+#endif
+}
 
 template <bool MASK>
 __global__ void __launch_bounds__(kRgThreads, 1)
 istft_pk3_kernel(const IstftPkParams p) {
-    constexpr int W = kRgWarps;
+    constexpr int W = kRgTeam;
     AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
     float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
-    float4* s_scr = reinterpret_cast<float4*>(s_ctw + 1024);                   // [W][kScrF4]
-    float4* s_ring = s_scr + W * kScrF4;                                       // [kRgSlots][kRgSlotF4]
-    float2* s_carry = reinterpret_cast<float2*>(s_ring + kRgSlots * kRgSlotF4);   // [2048 - hop] (L, R)
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_carry + (kIpN - p.hop));  // [kRgSlots]
-    uint64_t* s_empty = s_full + kRgSlots;                                      // [kRgSlots]
+    float4* s_scr = reinterpret_cast<float4*>(s_ctw + 1024);                   // [kRgWarps][kScrF4]
+    float4* s_ring = s_scr + kRgWarps * kScrF4;                                // [kRgTeam][kRgSlotF4]
+    float2* s_carry = reinterpret_cast<float2*>(s_ring + kRgTeam * kRgSlotF4);   // [2048 - hop] (L, R)
+    // a parity wait can only tell the current phase from the one before, so every waiter must see EVERY phase of its barrier:
+    // one "full" barrier per (team, slot) -- it advances once per round of that team -- and one "empty" per slot for the producer
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_carry + (kIpN - p.hop));  // [2][kRgTeam]
+    uint64_t* s_empty = s_full + 2 * kRgTeam;                                   // [kRgTeam]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
@@ -437,8 +449,9 @@ istft_pk3_kernel(const IstftPkParams p) {
     const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
 
     if (tid == 0) {
-        for (int s = 0; s < kRgSlots; ++s) {
+        for (int s = 0; s < kRgTeam; ++s) {
             mbar_init(&s_full[s], 1);
+            mbar_init(&s_full[kRgTeam + s], 1);
             mbar_init(&s_empty[s], 1);
         }
 #ifndef AL_CPU_EMUL
@@ -453,35 +466,42 @@ istft_pk3_kernel(const IstftPkParams p) {
     for (int i = tid; i < carry_len; i += kRgThreads) s_carry[i] = make_float2(0.f, 0.f);
     __syncthreads();
 
-    if (warp == W) {
+    if (warp == kRgWarps) {
         // ================================= producer =================================
         if (lane == 0) {
             for (int t = ta; t <= tb; ++t) {
-                const int it = t - ta, s = it % kRgSlots;
-                mbar_wait(&s_empty[s], ((it / kRgSlots) & 1) ^ 1);
+                const int it = t - ta, s = it % kRgTeam, rnd = it / kRgTeam;
+                mbar_wait(&s_empty[s], (rnd & 1) ^ 1);
                 float4* slot = s_ring + s * kRgSlotF4;
-                bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, &s_full[s]);
-                if (MASK) bulk_load_g2s(slot + kIpBins, M + (long long)t * kIpBins, kIpBins * 16, &s_full[s]);
-                mbar_arrive_expect_tx(&s_full[s], (MASK ? 2u : 1u) * kIpBins * 16u);
+                uint64_t* full = &s_full[(rnd & 1) * kRgTeam + s];        // the barrier of the team that takes this round
+                bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
+                if (MASK) bulk_load_g2s(slot + kIpBins, M + (long long)t * kIpBins, kIpBins * 16, full);
+                mbar_arrive_expect_tx(full, (MASK ? 2u : 1u) * kIpBins * 16u);
             }
         }
         return;
     }
 
-    // ================================= consumers =================================
+    // ================================= consumers: team = warp / kRgTeam, member = warp % kRgTeam =================================
+    const int team = warp / kRgTeam, member = warp - team * kRgTeam;
+    const int ttid = tid - team * (kRgTeam * 32);       // 0 .. 95 inside the team
+    constexpr int kTeamThreads = kRgTeam * 32;
     const float2* __restrict__ g_win = reinterpret_cast<const float2*>(p.window);   // (w[2k], w[2k+1]), through L1
     float4* scr = s_scr + warp * kScrF4;
-    constexpr int kCons = W * 32;
-    for (int tr = ta; tr <= t_last; tr += W) {
-        const int nf = max(0, min(W, tb - tr + 1));   // live frames of this round (CTA-uniform)
-        const int t = tr + warp;
-        const bool live = warp < nf;                    // warp-uniform
+    const float4* team_scr = s_scr + team * (kRgTeam * kScrF4);
+    // named barriers: 1 + team = the team's frames are parked / its scratches are free again; 3 = token "the overlap-add
+    // before team A's next one is done", 4 = the same for team B.  Team B hands team A the first token.
+    if (team == 1) named_bar_arrive(3, 2 * kTeamThreads);
+    int round = 0;
+    for (int tr = ta; tr <= t_last; tr += W, ++round) {
+        if ((round & 1) != team) continue;              // the teams take alternate rounds
+        const int nf = max(0, min(W, tb - tr + 1));   // live frames of this round (team-uniform)
+        const int t = tr + member;
+        const bool live = member < nf;                  // warp-uniform
         if (live) {
             float2 re[32], im[32];
-            const int it = t - ta, s = it % kRgSlots;
-            // Warps w and w + kRgSlots of a round share a slot (consecutive uses).  A parity wait may only look ONE phase ahead,
-            // so the later warp first waits for the earlier warp's use to land, then for its own.
-            for (int e = warp / kRgSlots; e >= 0; --e) mbar_wait(&s_full[s], ((it / kRgSlots) - e) & 1);
+            const int it = t - ta, s = it % kRgTeam;    // = member: every round uses each slot once
+            mbar_wait(&s_full[team * kRgTeam + s], (round >> 1) & 1);    // this team's (round / 2)-th use of the slot
             const float4* __restrict__ xs = s_ring + s * kRgSlotF4;
             const float4* __restrict__ ms = xs + kIpBins;
             // ---- Z from the rows in the slot: register pairs (r, 31 - r), k1 = 32 r + lane, k2 = 32 (31 - r) + lane
@@ -503,7 +523,7 @@ istft_pk3_kernel(const IstftPkParams p) {
                 ip_combine(p2r, p2i, q2r, q2i, w2, re[31 - r], im[31 - r]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[s]);   // the slot goes back to the producer
+            if (lane == 0) mbar_arrive(&s_empty[s]);   // the slot goes back to the producer: the next round's row may land
             warp_fft1024p_wide<true>(re, im, scr, s_tw, lane);
             // z[k] = (x[2k], x[2k+1]) * n_fft; window (carries 1 / n_fft) and park the frame: scr[k] = samples 2k, 2k+1
 #pragma unroll
@@ -513,9 +533,10 @@ istft_pk3_kernel(const IstftPkParams p) {
                 scr[32 * r + lane] = make_float4(ev.x, ev.y, od.x, od.y);
             }
         }
-        named_bar_sync(1, kCons);   // all frames of the round are parked
+        named_bar_sync(1 + team, kTeamThreads);         // the team's frames are parked
+        named_bar_sync(3 + team, 2 * kTeamThreads);     // ... and the overlap-add of the round before is done (carry)
 
-        // ---- overlap-add of the round (the register form of istft_pk2_kernel), consumers only ------------------
+        // ---- overlap-add of the round (the register form of istft_pk2_kernel) by the team ------------------
         const long long S = (long long)tr * hop;
         const float2* cin = s_carry;
         float2* cout = s_carry;
@@ -525,9 +546,9 @@ istft_pk3_kernel(const IstftPkParams p) {
         const long long rel = S - p.out_start;
         const bool interior = p.ola_fast && nf == W && S >= Pa && S + emit <= Pb && place + rel >= 0 &&
                               place + rel + emit <= p.dst_limit;
-        for (int j = tid; j < hop; j += kCons) {
+        for (int j = ttid; j < hop; j += kTeamThreads) {
             const int kj = (kOla_K - 1) * hop + j < kIpN ? kOla_K - 1 : kOla_K - 2;
-            const float2* __restrict__ sj = reinterpret_cast<const float2*>(s_scr) + j;
+            const float2* __restrict__ sj = reinterpret_cast<const float2*>(team_scr) + j;
             float ev[W], wg[W];
 #pragma unroll
             for (int h = 0; h < W; ++h) {
@@ -579,10 +600,10 @@ istft_pk3_kernel(const IstftPkParams p) {
                 if (i < span) cout[i - emit] = out[h];
             }
         }
-        named_bar_sync(1, kCons);   // the scratches may be overwritten by the next round's frames
+        named_bar_sync(1 + team, kTeamThreads);         // the team's scratches may take the frames of its next round
+        named_bar_arrive(4 - team, 2 * kTeamThreads);   // token: the other team may overlap-add
     }
 }
-
 
 // segments per row: minimise waves * rounds per segment (a round = kIpWarps frames; each segment re-computes the
 // ceil((2048 - hop) / hop) frames that precede its first owned sample)
@@ -618,9 +639,9 @@ static size_t ip_launch_shape(IstftPkParams& p, int n_chunks, int n_sm, int W) {
 static size_t rg_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
     const int rows = n_chunks * p.stems;
     const int total_hops = (p.out_len + p.hop - 1) / p.hop;
-    ip_tiling(rows, total_hops, p.hop, n_sm, kRgWarps, &p.hops_per_cta, &p.segs);
+    ip_tiling(rows, total_hops, p.hop, n_sm, kRgTeam, &p.hops_per_cta, &p.segs);
     return (size_t)2 * 1024 * sizeof(float2) + (size_t)kRgWarps * kScrF4 * sizeof(float4) +
-           (size_t)kRgSlots * kRgSlotF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2) + 2 * kRgSlots * sizeof(uint64_t);
+           (size_t)kRgTeam * kRgSlotF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2) + 3 * kRgTeam * sizeof(uint64_t);
 }
 // [emul-end]
 
