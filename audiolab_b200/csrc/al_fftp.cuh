@@ -33,6 +33,10 @@ __device__ __forceinline__ void pcmul(float2& re, float2& im, float2 w) {
     im = i;
 }
 
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
 // in : re/im[r] = z[32*r + lane];  out: re/im[r] = Z[32*r + lane],
 // Z[k] = sum_n z[n] exp(-+2 pi i n k / 1024) (unnormalised).  tw[k1*32 + n2] = exp(-2 pi i k1 n2 / 1024).
 template <bool INV>
@@ -83,6 +87,37 @@ __device__ __forceinline__ void warp_fft1024p_wide(float2 (&re)[32], float2 (&im
     }
     __syncwarp();
     if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+}
+
+// The same transform with ONE copy of the 32-point butterfly in the instruction stream (a two-trip loop around it):
+// half the code of the form above.  For kernels whose warps drift against each other, where the code every warp streams
+// through has to fit the 32 KB L1.5 instruction cache (profiles/r02zf_*: 34 % of the stall samples of a kernel with a
+// 37 KB consumer loop were instruction fetches).
+template <bool INV>
+__device__ __forceinline__ void warp_fft1024p_wide_rolled(float2 (&re)[32], float2 (&im)[32], float4* scr,
+                                                          const float2* tw, int lane) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
+        if (pass == 0) {
+            float4* wr = scr + lane * 33;
+            const float4* rd = scr + lane;
+            wr[0] = make_float4(re[0].x, re[0].y, im[0].x, im[0].y);
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) {
+                pcmul<INV>(re[k1], im[k1], tw[k1 * 32 + lane]);
+                wr[k1] = make_float4(re[k1].x, re[k1].y, im[k1].x, im[k1].y);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const float4 v = rd[n2 * 33];
+                re[n2] = make_float2(v.x, v.y);
+                im[n2] = make_float2(v.z, v.w);
+            }
+            __syncwarp();
+        }
+    }
 }
 
 #ifndef AL_CPU_EMUL   // (tools/cpu_emul emulates the barrier / shuffle kernels only)

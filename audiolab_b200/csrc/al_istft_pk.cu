@@ -605,6 +605,276 @@ istft_pk3_kernel(const IstftPkParams p) {
     }
 }
 
+// ---- streaming form (AL_IP_RING=2) ------------------------------------------------------------------------------------
+// The ring kernel above still runs its consumers in lock step: a team parks three frames, meets on a barrier, overlap-adds,
+// meets again.  Its profile (profiles/r02zb_*): 45 % of the stall samples sit in the overlap-add phase (predicated register
+// form, dependent loads of 1 / sum(w^2), two named barriers per round), every warp waits for the slowest of its team twice
+// per frame, the parked frames pin 16.5 KB of scratch per warp (so only 6 consumer warps fit), and the Hermitian partner
+// Y[1024 - k] of every bin is loaded and multiplied by its mask a second time by the lane that owns Z[1024 - k].  Here
+//  * the overlap-add is a circular ACCUMULATOR of 2048 stereo positions in shared memory, even and odd positions in two
+//    arrays, each owned by ONE dedicated warp (position parity = warp): frame t adds its sample n to position t hop + n, and
+//    after frame t the hop-block [t hop, (t+1) hop) is final -- scaled by 1 / sum(w^2) (and the chunk weight), stored,
+//    cleared.  The two overlap-add warps run a short loop that stays in the instruction cache and take the frames in
+//    ascending order, so every sample is the same left-to-right sum as in istft_pk2_kernel / istft_pk3_kernel.  (A first
+//    version passed a token between the CONSUMER warps instead: three times slower -- each warp entered the serial section
+//    with cold instructions, 67 % of its stall samples there were instruction fetches, profiles/r02zd_*.)
+//  * consumer warps never meet: row slot -> Z -> iFFT with the SLOT as transposition scratch -> window -> the frame parked
+//    in the same slot (even samples, odd samples) -> "ready" -> next frame.  No per-warp scratch, so 6 slots of rows
+//    (197 KB) are in flight / in use and 9 consumer warps of 168 registers run;
+//  * Z[k] and Z[1024 - k] come from ONE product pair: Z[1024 - k] = conj(A) + i conj(B) for Z[k] = A + i B, sent to the
+//    owning lane with four shuffles -- half the LDS.128 and half the mask multiplications of the row -> Z phase.
+// Barriers (a parity wait can only tell the current phase from the one before, so every waiter sees every phase of its
+// barrier): full[w] per consumer warp (its j-th frame = phase j), ready[s] per slot (the two overlap-add warps take every
+// frame), empty[s] per slot (two arrivals, the producer waits).
+constexpr int kTkC = 9;                    // consumer warps
+constexpr int kTkSlots = 6;                // ring slots: one frame's spectrum row + mask row each, later the frame itself
+constexpr int kTkThreads = (kTkC + 3) * 32;   // + two overlap-add warps + the producer
+constexpr int kTkSlotF4 = 2 * kIpBins;     // float4 per slot (>= kScrF4: the slot is also the warp's transposition scratch)
+constexpr int kTkU = 7;                    // block positions per lane of an overlap-add warp held in registers (hop <= 448)
+static_assert(kTkSlotF4 >= kScrF4, "a slot must hold the transposition tile");
+
+template <bool MASK>
+__global__ void __launch_bounds__(kTkThreads, 1)
+istft_pk4_kernel(const IstftPkParams p) {
+    AL_DYN_SMEM(unsigned char, smem_raw);
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
+    float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
+    float2* s_acc = s_ctw + 1024;                                              // [2][1024] even / odd positions, (L, R)
+    float4* s_ring = reinterpret_cast<float4*>(s_acc + 2048);                  // [kTkSlots][kTkSlotF4]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + kTkSlots * kTkSlotF4);   // [kTkC]
+    uint64_t* s_ready = s_full + kTkC;                                          // [kTkSlots]
+    uint64_t* s_empty = s_ready + kTkSlots;                                     // [kTkSlots]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
+    const int chunk = g / p.stems, stem = g - chunk * p.stems;
+    const int hop = p.hop, T = p.n_frames;
+
+    const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
+    const long long Pend = (long long)p.out_start + p.out_len;
+    const long long Pb = min(Pa + (long long)p.hops_per_cta * hop, Pend);
+    if (Pa >= Pb) return;
+    int ta = (int)((Pa - kIpN) / hop) + 1;              // first frame touching Pa
+    if (Pa < kIpN) ta = 0;
+    ta = max(ta, 0);
+    const int tb = min((int)((Pb - 1) / hop), T - 1);   // last frame touching Pb - 1
+    const int t_last = (int)((Pb - 1) / hop);           // hop-blocks are emitted up to the one holding Pb - 1
+
+    if (tid == 0) {
+        for (int w = 0; w < kTkC; ++w) mbar_init(&s_full[w], 1);
+        for (int s = 0; s < kTkSlots; ++s) {
+            mbar_init(&s_ready[s], 1);
+            mbar_init(&s_empty[s], 2);
+        }
+#ifndef AL_CPU_EMUL
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        fence_async_smem();
+    }
+    for (int i = tid; i < 1024; i += kTkThreads) {
+        s_tw[i] = p.tw[i];
+        s_ctw[i] = p.ctw[i];
+    }
+    for (int i = tid; i < 2048; i += kTkThreads) s_acc[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    if (warp == kTkC + 2) {
+        // ================================= producer =================================
+        if (lane == 0) {
+            const float4* __restrict__ X = p.spec + (long long)(p.spec_has_stems ? g : chunk) * T * kIpBins;
+            const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
+            for (int t = ta; t <= tb; ++t) {
+                const int it = t - ta, s = it % kTkSlots;
+                mbar_wait(&s_empty[s], ((it / kTkSlots) & 1) ^ 1);
+                float4* slot = s_ring + s * kTkSlotF4;
+                uint64_t* full = &s_full[it % kTkC];
+                bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
+                if (MASK) bulk_load_g2s(slot + kIpBins, M + (long long)t * kIpBins, kIpBins * 16, full);
+                mbar_arrive_expect_tx(full, (MASK ? 2u : 1u) * kIpBins * 16u);
+            }
+        }
+        return;
+    }
+
+    if (warp >= kTkC) {
+        // ================================= overlap-add warps: par = position parity =================================
+        const int par = warp - kTkC;
+        const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
+        float* __restrict__ dst0 = p.dst + ((long long)stem * 2) * p.dst_ch_stride + (long long)chunk * p.dst_chunk_stride + place;
+        float* __restrict__ dst1 = dst0 + p.dst_ch_stride;
+        float2* __restrict__ acc = s_acc + par * 1024;
+        const bool small_hop = hop <= 64 * kTkU;        // CTA-uniform
+        // 32-bit positions relative to out_start (a chunk is far below 2^31 samples)
+        const int ra = (int)(Pa - p.out_start), rb = (int)(Pb - p.out_start);
+        const long long lim_lo = -place, lim_hi = p.dst_limit - place;      // stores need lim_lo <= pp < lim_hi
+        const float* __restrict__ envp = p.inv_env + p.out_start;
+        const float* __restrict__ wgp = p.weight;
+#pragma unroll 1
+        for (int it = 0; ta + it <= t_last; ++it) {
+            const int t = ta + it;
+            const int P0 = t * hop;                     // < 2^31: the launcher checks (T + 4) * hop
+            const int odd = P0 & 1, beta = P0 >> 1;
+            // this warp's positions of the frame: samples 2k (+1 when the parities differ) at entries (off + k) & 1023, and of the
+            // hop-block: P = P0 + j0 + 2 m at entries (off + m) & 1023
+            const bool same = par == odd;
+            const int off = same ? beta : beta + odd;
+            const int j0 = par ^ odd;
+            const int n_blk = (hop - j0 + 1) >> 1;
+            const int r0p = P0 + j0 - p.out_start;      // relative position of m = 0
+            // interior block (warp-uniform): every position is owned and lands inside the destination
+            const bool interior = small_hop && r0p >= ra && r0p + 2 * n_blk <= rb && r0p >= lim_lo && r0p + 2 * n_blk <= lim_hi;
+            // 1 / sum(w^2) and chunk weight of the block, fetched before the wait
+            float ev[kTkU], wg[kTkU];
+            if (interior) {
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    const int m = lane + 32 * u;
+                    const bool mine = m < n_blk;
+                    ev[u] = mine ? __ldg(envp + r0p + 2 * m) : 0.f;
+                    wg[u] = (mine && wgp) ? __ldg(wgp + r0p + 2 * m) : 1.f;
+                }
+            }
+            if (t <= tb) {                              // frames past tb only flush their hop-block
+                const int s = it % kTkSlots;
+                mbar_wait(&s_ready[s], (it / kTkSlots) & 1);
+                // the consumer parked the frame already rotated to the accumulator's entries: entry e of this parity at [par][e]
+                const float2* __restrict__ src = reinterpret_cast<const float2*>(s_ring + s * kTkSlotF4) + par * 1024 + lane;
+                float2* __restrict__ ac = acc + lane;
+                {   // all 64 loads in flight before the first add: the warp is paced by shared-memory round trips, not by issue slots
+                    float2 va[32], vs[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        vs[q] = src[32 * q];
+                        va[q] = ac[32 * q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) ac[32 * q] = padd(va[q], vs[q]);
+                }
+                fence_async_smem();                     // generic-proxy accesses of the slot before the next bulk copy into it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[s]);
+            }
+            // ---- the hop-block [P0, P0 + hop) is final: take it out of the accumulator, clear it, scale, store
+            if (interior) {
+                float2 blk[kTkU];
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    const int m = lane + 32 * u;
+                    float2* a = acc + ((off + m) & 1023);
+                    blk[u] = *a;                        // (entries past the block belong to later blocks: read, not cleared)
+                    if (m < n_blk) *a = make_float2(0.f, 0.f);
+                }
+                float* __restrict__ d0 = dst0 + r0p;
+                float* __restrict__ d1 = dst1 + r0p;
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    const int m = lane + 32 * u;
+                    if (m < n_blk) {
+                        float v0 = blk[u].x * ev[u], v1 = blk[u].y * ev[u];
+                        if (wgp) {
+                            v0 *= wg[u];
+                            v1 *= wg[u];
+                        }
+                        d0[2 * m] = v0;
+                        d1[2 * m] = v1;
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int m = lane; m < n_blk; m += 32) {
+                    const int pp = r0p + 2 * m;
+                    float2* a = acc + ((off + m) & 1023);
+                    const float2 v = *a;
+                    *a = make_float2(0.f, 0.f);
+                    if (pp >= ra && pp < rb && pp >= lim_lo && pp < lim_hi) {
+                        const float e = __ldg(envp + pp);
+                        float v0 = v.x * e, v1 = v.y * e;
+                        if (wgp) {
+                            const float wgt = __ldg(wgp + pp);
+                            v0 *= wgt;
+                            v1 *= wgt;
+                        }
+                        dst0[pp] = v0;
+                        dst1[pp] = v1;
+                    }
+                }
+            }
+            __syncwarp();                               // the cleared block before the next frame's adds
+        }
+        return;
+    }
+
+    // ================================= consumers: frame it = warp, warp + kTkC, ... =================================
+    const float2* __restrict__ g_win = reinterpret_cast<const float2*>(p.window);   // (w[2k], w[2k+1]), through L1
+#pragma unroll 1
+    for (int it = warp; ta + it <= tb; it += kTkC) {
+        const int s = it % kTkSlots;
+        float4* slot = s_ring + s * kTkSlotF4;
+        float2 re[32], im[32];
+        mbar_wait(&s_full[warp], (it / kTkC) & 1);
+        {
+            float4* __restrict__ xs = slot;
+            const float4* __restrict__ ms = slot + kIpBins;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // ---- Z[k1] and Z[1024 - k1] from ONE pair P = Y[k1], Q = Y[1024 - k1], written over the two spectrum bins they came
+            // from (no other lane reads those): a rolled loop instead of 16 unrolled register pairs
+            {   // Z[512]: its own Hermitian partner (every lane forms it, the stores coincide)
+                float2 pr, pi, zr, zi;
+                ip_product<MASK>(xs[512], MASK ? ms[512] : z4, pr, pi);
+                ip_combine(pr, pi, pr, pi, s_ctw[512], zr, zi);
+                __syncwarp();
+                xs[512] = make_float4(zr.x, zr.y, zi.x, zi.y);
+            }
+#pragma unroll 4
+            for (int k1 = lane; k1 < 512; k1 += 32) {
+                float2 pr, pi, qr, qi;
+                ip_product<MASK>(xs[k1], MASK ? ms[k1] : z4, pr, pi);
+                ip_product<MASK>(xs[1024 - k1], MASK ? ms[1024 - k1] : z4, qr, qi);
+                if (k1 == 0) {               // C2R ignores Im of the DC and Nyquist bins
+                    pi = make_float2(0.f, 0.f);
+                    qi = make_float2(0.f, 0.f);
+                }
+                const float2 w = s_ctw[k1];
+                const float2 ar = padd(pr, qr), ai = psub(pi, qi);     // A = P + conj(Q)
+                const float2 dr = psub(pr, qr), di = padd(pi, qi);     // D = P - conj(Q)
+                const float2 zr = pfma(dr, w.y, pfma(di, -w.x, ar));    // Z[k1] = A + i D conj(w)
+                const float2 zi = pfma(di, w.y, pfma(dr, w.x, ai));
+                // Z[1024 - k1] = conj(A) + i conj(D conj(w)): the arithmetic ip_combine(Q, P, -conj(w)) would do
+                const float2 ndr = make_float2(-dr.x, -dr.y), nai = make_float2(-ai.x, -ai.y);
+                const float2 mr = pfma(ndr, w.y, pfma(di, w.x, ar));
+                const float2 mi = pfma(di, w.y, pfma(dr, w.x, nai));
+                xs[k1] = make_float4(zr.x, zr.y, zi.x, zi.y);
+                xs[1024 - k1] = make_float4(mr.x, mr.y, mi.x, mi.y);   // (k1 = 0 lands on the dead Nyquist bin)
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float4 v = xs[32 * r + lane];
+                re[r] = make_float2(v.x, v.y);
+                im[r] = make_float2(v.z, v.w);
+            }
+        }
+        __syncwarp();                                   // every lane holds its Z: the slot is scratch now
+        warp_fft1024p_wide_rolled<true>(re, im, slot, s_tw, lane);
+        // z[k] = (x[2k], x[2k+1]) * n_fft; window (carries 1 / n_fft) and park the frame in the slot, per position parity and
+        // ALREADY ROTATED to the accumulator: sample 2k sits at position P0 + 2k = entry (beta + k) & 1023 of parity P0 & 1, sample
+        // 2k + 1 at entry (beta + k + odd) & 1023 of the other parity, so the overlap-add warps add entry to entry
+        const int P0 = (ta + it) * hop;
+        const int odd = P0 & 1, beta = P0 >> 1;
+        float2* pA = reinterpret_cast<float2*>(slot) + (odd ? 1024 : 0);
+        float2* pB = reinterpret_cast<float2*>(slot) + (odd ? 0 : 1024);
+        const int ea = beta + lane, eb = beta + odd + lane;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const float2 w = __ldg(g_win + 32 * r + lane);
+            pA[(ea + 32 * r) & 1023] = pscale(re[r], w.x);
+            pB[(eb + 32 * r) & 1023] = pscale(im[r], w.y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_ready[s]);
+    }
+}
+
 // segments per row: minimise waves * rounds per segment (a round = kIpWarps frames; each segment re-computes the
 // ceil((2048 - hop) / hop) frames that precede its first owned sample)
 static void ip_tiling(int rows, int total_hops, int hop, int n_sm, int kIpWarps, int* hpc_out, int* segs_out) {
@@ -643,6 +913,29 @@ static size_t rg_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
     return (size_t)2 * 1024 * sizeof(float2) + (size_t)kRgWarps * kScrF4 * sizeof(float4) +
            (size_t)kRgTeam * kRgSlotF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2) + 3 * kRgTeam * sizeof(uint64_t);
 }
+// launch shape of istft_pk4_kernel: one CTA per SM; a segment costs its hops + the halo frames it recomputes + the fill of the warp pipeline
+static size_t tk_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
+    const int rows = n_chunks * p.stems;
+    const int total_hops = (p.out_len + p.hop - 1) / p.hop;
+    const int halo = (kIpN - 1) / p.hop;
+    long long best = -1;
+    int best_segs = 1;
+    const int max_segs = total_hops / 8 > 1 ? total_hops / 8 : 1;
+    for (int segs = 1; segs <= max_segs; ++segs) {
+        const int hpc = (total_hops + segs - 1) / segs;
+        const int real_segs = (total_hops + hpc - 1) / hpc;
+        const long long waves = ((long long)rows * real_segs + n_sm - 1) / n_sm;
+        const long long cost = waves * (hpc + halo + kTkC);
+        if (best < 0 || cost < best) {
+            best = cost;
+            best_segs = segs;
+        }
+    }
+    p.hops_per_cta = (total_hops + best_segs - 1) / best_segs;
+    p.segs = (total_hops + p.hops_per_cta - 1) / p.hops_per_cta;
+    return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kTkSlots * kTkSlotF4 * sizeof(float4) +
+           (size_t)(kTkC + 2 * kTkSlots) * sizeof(uint64_t);
+}
 // [emul-end]
 
 cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
@@ -650,7 +943,26 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     const int n_sm = sm_count();
     const int rows = n_chunks * p.stems;
     // the ring-buffered kernel (default; AL_IP_RING=0 selects the register-pipelined one): hop >= 410 (register-form overlap-add)
-    static const int ring = (getenv("AL_IP_RING") && atoi(getenv("AL_IP_RING")) == 0) ? 0 : 1;
+    // AL_IP_RING: 2 (default) = the streaming kernel, 1 = the ring kernel with teams, 0 = the register-pipelined kernel
+    static const int ring = getenv("AL_IP_RING") ? atoi(getenv("AL_IP_RING")) : 2;
+    if (ring == 2 && (long long)(p.n_frames + 8) * p.hop < 0x7fffffffLL && (long long)p.out_start + p.out_len < 0x7fffffffLL) {
+        // the streaming kernel: any hop (the accumulator is position-addressed); positions are 32-bit inside a chunk
+        p.ola_fast = 0;
+        p.l2_prefetch = 0;
+        const size_t smem4 = tk_launch_shape(p, n_chunks, n_sm);
+        static PerDeviceOnce attr4[2];
+        PerDeviceOnce& a4 = attr4[p.mask ? 1 : 0];
+        if (a4.needed()) {
+            cudaError_t e = p.mask ? cudaFuncSetAttribute(istft_pk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                   : cudaFuncSetAttribute(istft_pk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+            a4.mark();
+        }
+        if (p.mask) istft_pk4_kernel<true><<<(unsigned)(rows * p.segs), kTkThreads, smem4, stream>>>(p);
+        else istft_pk4_kernel<false><<<(unsigned)(rows * p.segs), kTkThreads, smem4, stream>>>(p);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (ring && (kIpN + p.hop - 1) / p.hop <= kIpKMax) {
         static const int ola_fast3 = (getenv("AL_IP_OLAFAST") && atoi(getenv("AL_IP_OLAFAST")) == 0) ? 0 : 1;
         p.ola_fast = ola_fast3;

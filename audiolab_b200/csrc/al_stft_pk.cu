@@ -29,10 +29,6 @@ constexpr int kPkThreads = (kPkWarps + kPkProd) * 32;
 constexpr int kPkMaxStages = 4;
 constexpr int kPkCtw = 544;          // combine twiddles (513 used, padded for the r = 16 row)
 
-__device__ __forceinline__ float2 shfl2(float2 v, int src) {
-    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
-
 template <int LAYOUT, bool FULL>
 __global__ void __launch_bounds__(kPkThreads, 1)
 stft_pk2_kernel(const StftPkParams p) {

@@ -769,8 +769,8 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "roofline": roofline_block(gemm, k2, pk, traffic),
             "roofline_spectral": {
-                "kernel": "al_istft (istft_pk2_kernel<mask>, stereo-packed): complex mask (.) spec + C2R iFFT + window "
-                          "+ OLA + /env",
+                "kernel": "al_istft (istft_pk4_kernel<mask>, stereo-packed, producer / consumer / overlap-add warps): complex mask (.) "
+                          "spec + C2R iFFT + window + OLA + /env",
                 "bound": "hbm", "achieved": k2["achieved_gbs"] if k2 else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": (k2["achieved_gbs"] / pk["hbm_gbs"]) if k2 else None, "traffic": traffic,
                 "peak_source": pk["source"], "bytes_per_launch": k2["bytes_per_launch"] if k2 else None,

@@ -226,6 +226,42 @@ def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warp
             assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("hop,T,stems,use_mask,consumers,n_sm", [(441, 21, 1, True, 11, 3), (441, 13, 2, True, 7, 3),
+                                                                     (512, 17, 1, False, 11, 3), (1024, 9, 1, True, 7, 1),
+                                                                     (441, 61, 1, True, 11, 1), (300, 33, 1, False, 11, 2)])
+def test_token_ordered_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, consumers, n_sm):
+    """istft_pk4_kernel: producer warp + ring of row slots, Z[k] / Z[1024 - k] from one product pair (mirror through shuffles),
+    the slot as transposition scratch, overlap-add in a circular even / odd accumulator ordered by a token on mbarriers (odd and
+    even hops, hops above 448 = the in-place emission loop, hop 300 = seven frames per position), several segments per chunk,
+    flush blocks past the last frame."""
+    import torch
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emul.emul_istft_pk4.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I]
+    emul.emul_istft_pk4.restype = I
+    n_fft, F, n_chunks = 2048, 1025, 2
+    rs = np.random.RandomState(hop + T)
+    cplx = lambda *shape: (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+    spec = cplx(n_chunks, T, F, 2)                                         # [chunk, t, f, channel]
+    mask = cplx(n_chunks, stems, T, F, 2) if use_mask else None
+    out_len = (T - 1) * hop
+    _, ws, tw, _, env = _plan_tables(n_fft, hop, T)
+    k = np.arange(1024)
+    ctw_full = np.ascontiguousarray(np.stack((np.cos(-2 * np.pi * k / n_fft), np.sin(-2 * np.pi * k / n_fft)), -1).astype(np.float32))
+    weight = rs.uniform(0.5, 1.5, out_len).astype(np.float32)
+    dst = np.full((n_chunks, stems, 2, out_len), np.nan, np.float32)
+    segs = emul.emul_istft_pk4(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), n_fft // 2, out_len,
+                               _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, n_chunks, consumers, n_sm)
+    assert segs >= 1
+    assert np.isfinite(dst).all()
+    win = torch.hann_window(n_fft)
+    for c in range(n_chunks):
+        for s_ in range(stems):
+            y = spec[c] * (mask[c, s_] if use_mask else 1.0)               # [t, f, ch]
+            ref = torch.istft(torch.tensor(np.ascontiguousarray(y.transpose(2, 1, 0))), n_fft, hop, window=win, center=True)
+            ref = ref.numpy() * weight
+            assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("hop,T,layout,crop,low,n_chunks", [(441, 21, 3, 1025, 0, 2), (441, 9, 0, 1025, 0, 1), (512, 12, 3, 1000, 3, 2),
                                                            (441, 26, 3, 1025, 0, 3)])
 def test_packed_stft_emulated_matches_torch(emul, hop, T, layout, crop, low, n_chunks):

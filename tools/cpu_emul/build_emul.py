@@ -171,6 +171,28 @@ extern "C" int emul_istft_pk(const float* spec, const float* mask, int n_frames,
     return p.segs;
 }
 
+extern "C" int emul_istft_pk4(const float* spec, const float* mask, int n_frames, int stems, int spec_has_stems, int hop,
+                              const float* window, const float* tw, const float* ctw_full, const float* inv_env,
+                              int out_start, int out_len, const float* weight, float* dst, long long dst_ch_stride,
+                              long long dst_chunk_stride, long long dst_off0, long long dst_off_step, long long dst_limit,
+                              int n_chunks, int consumers, int n_sm) {
+    IstftPkParams p{};
+    p.spec = reinterpret_cast<const float4*>(spec); p.mask = reinterpret_cast<const float4*>(mask); p.n_frames = n_frames;
+    p.stems = stems; p.spec_has_stems = spec_has_stems; p.hop = hop; p.window = window;
+    p.tw = reinterpret_cast<const float2*>(tw); p.ctw = reinterpret_cast<const float2*>(ctw_full); p.inv_env = inv_env;
+    p.out_start = out_start; p.out_len = out_len; p.weight = weight; p.dst = dst; p.dst_ch_stride = dst_ch_stride;
+    p.dst_chunk_stride = dst_chunk_stride; p.dst_offsets = nullptr; p.dst_off0 = dst_off0; p.dst_off_step = dst_off_step;
+    p.dst_limit = dst_limit;
+    (void)consumers;
+    const size_t smem = tk_launch_shape(p, n_chunks, n_sm);
+    if (smem > sizeof(g_smem)) return -2;
+    std::memset(g_smem, 0xFF, sizeof(g_smem));
+    const dim3 grid(n_chunks * stems * p.segs), block(kTkThreads);
+    if (mask) emul_launch(grid, block, [&] { istft_pk4_kernel<true>(p); });
+    else emul_launch(grid, block, [&] { istft_pk4_kernel<false>(p); });
+    return p.segs;
+}
+
 extern "C" void emul_ola_gather(const float* chunks, int n_chunks, int data_chunk0, int rows, int chunk_len,
                                 const long long* offsets, const int* mult, const float* wtab, const int* tab_id,
                                 long long n_total, long long p0, long long p1, const float* halo_in, int raw_out,

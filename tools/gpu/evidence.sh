@@ -10,7 +10,7 @@ echo "== kernel_bench" ; timeout 120 python tools/kernel_bench.py --gelu > $OUT/
 echo "== bench" ; timeout 200 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; echo "rc=$?" ; cat $OUT/bench.json ; tail -5 $OUT/bench.err
 echo "== smoke" ; timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1 ; echo "rc=$?" ; tail -2 $OUT/smoke.log
 echo "== ncu full: al_istft inside the bench step (traffic)"
-timeout 120 ncu --set full --clock-control none --profile-from-start off -k regex:'istft_pk2_kernel' -c 1 -o $OUT/prof_bench_istft -f \
+timeout 120 ncu --set full --clock-control none --profile-from-start off -k regex:'istft_pk[234]_kernel' -c 1 -o $OUT/prof_bench_istft -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-mode --track-seconds 60 > $OUT/prof_bench_istft.log 2>&1 ; echo "rc=$?"
 ncu -i $OUT/prof_bench_istft.ncu-rep --page raw --csv > $OUT/prof_bench_istft_raw.csv 2>/dev/null
 rm -f $OUT/prof_bench_istft.ncu-rep

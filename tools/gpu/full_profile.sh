@@ -15,7 +15,7 @@ echo "== ncu launch list (one timed bench step on a 16 s track)"
 timeout 480 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_bench.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-mode --track-seconds 16 > $OUT/launches_bench.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: al_istft inside the bench step (traffic)"
-timeout 200 ncu --set full --clock-control none --profile-from-start off -k regex:'istft_pk2_kernel' -c 1 -o $OUT/prof_bench_istft -f \
+timeout 200 ncu --set full --clock-control none --profile-from-start off -k regex:'istft_pk[234]_kernel' -c 1 -o $OUT/prof_bench_istft -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile-mode --track-seconds 60 > $OUT/prof_bench_istft.log 2>&1 ; echo "rc=$?"
 ncu -i $OUT/prof_bench_istft.ncu-rep --page raw --csv > $OUT/prof_bench_istft_raw.csv 2>/dev/null
 echo "== ncu full: spectral kernels, kernel_bench --once"
