@@ -95,7 +95,14 @@ __device__ __forceinline__ void warp_fft1024p_wide(float2 (&re)[32], float2 (&im
 // 37 KB consumer loop were instruction fetches).
 template <bool INV>
 __device__ __forceinline__ void warp_fft1024p_wide_rolled(float2 (&re)[32], float2 (&im)[32], float4* scr,
-                                                          const float2* tw, int lane) {
+                                                          const float2* tw, int lane, uint64_t* release = nullptr);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar);
+__device__ __forceinline__ void fence_async_smem();
+// release (optional): an mbarrier that takes one arrival as soon as the scratch has been read back (the scratch is a ring
+// slot that goes back to its producer half way through the transform)
+template <bool INV>
+__device__ __forceinline__ void warp_fft1024p_wide_rolled(float2 (&re)[32], float2 (&im)[32], float4* scr,
+                                                          const float2* tw, int lane, uint64_t* release) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         if (INV) fft32p_inv(re, im); else fft32p_fwd(re, im);
@@ -115,7 +122,9 @@ __device__ __forceinline__ void warp_fft1024p_wide_rolled(float2 (&re)[32], floa
                 re[n2] = make_float2(v.x, v.y);
                 im[n2] = make_float2(v.z, v.w);
             }
+            if (release) fence_async_smem();            // generic-proxy accesses of the scratch before the next bulk copy into it
             __syncwarp();
+            if (release && lane == 0) mbar_arrive(release);
         }
     }
 }
@@ -162,6 +171,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// wait whose suspension is bounded by `ns` nanoseconds per try (a waiter on a serial hand-off chain must notice the phase
+// flip at once; 0 = the plain form)
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    if (ns == 0) { mbar_wait(bar, parity); return; }
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 #else   // host emulation (tools/cpu_emul): the same protocol on std::atomic_ref, bulk copies done at issue time
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) { std::memcpy(gdst, ssrc, bytes); }
 __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t*) { std::memcpy(sdst, gsrc, bytes); }
@@ -184,10 +212,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t) { mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) { mbar_arrive(bar); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     std::atomic_ref<uint64_t> a(*bar);
     while ((a.load() & 1) == parity) std::this_thread::yield();
 }
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t) { mbar_wait(bar, parity); }
 #endif  // AL_CPU_EMUL
 
 }  // namespace al

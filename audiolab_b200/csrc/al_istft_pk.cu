@@ -50,6 +50,31 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* g, uint32_t bytes) 
 #endif
 }
 
+// streaming read-only load that does not take a line of the (few KB of) L1 the window table lives in
+__device__ __forceinline__ float ldg_stream(const float* g) {
+#ifndef AL_CPU_EMUL
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(g));
+    return v;
+#else
+    return *g;
+#endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* g) {
+#ifndef AL_CPU_EMUL
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+#else
+    (void)g;
+#endif
+}
+__device__ __forceinline__ void prefetch_l1(const void* g) {
+#ifndef AL_CPU_EMUL
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(g));
+#else
+    (void)g;
+#endif
+}
+
 // Y = x * m per channel; returns packed (L, R) real and imaginary parts
 template <bool MASK>
 __device__ __forceinline__ void ip_product(const float4 x, const float4 m, float2& yr, float2& yi) {
@@ -629,7 +654,10 @@ istft_pk3_kernel(const IstftPkParams p) {
 constexpr int kTkC = 9;                    // consumer warps
 constexpr int kTkSlots = 6;                // ring slots: one frame's spectrum row + mask row each, later the frame itself
 constexpr int kTkThreads = (kTkC + 3) * 32;   // + two overlap-add warps + the producer
-constexpr int kTkSlotF4 = 2 * kIpBins;     // float4 per slot (>= kScrF4: the slot is also the warp's transposition scratch)
+constexpr int kTkMaskOff = 1032;           // the mask row starts on a 128-byte line of the slot (1025 would split every quarter-warp access)
+constexpr int kTkSlotF4 = 2064;            // float4 per slot: spectrum row, mask row at kTkMaskOff, rounded to 128 bytes (>= kScrF4:
+                                           // the slot is also the warp's transposition scratch)
+static_assert(kTkMaskOff + kIpBins <= kTkSlotF4, "slot too small");
 constexpr int kTkU = 7;                    // block positions per lane of an overlap-add warp held in registers (hop <= 448)
 static_assert(kTkSlotF4 >= kScrF4, "a slot must hold the transposition tile");
 
@@ -689,7 +717,7 @@ istft_pk4_kernel(const IstftPkParams p) {
                 float4* slot = s_ring + s * kTkSlotF4;
                 uint64_t* full = &s_full[it % kTkC];
                 bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
-                if (MASK) bulk_load_g2s(slot + kIpBins, M + (long long)t * kIpBins, kIpBins * 16, full);
+                if (MASK) bulk_load_g2s(slot + kTkMaskOff, M + (long long)t * kIpBins, kIpBins * 16, full);
                 mbar_arrive_expect_tx(full, (MASK ? 2u : 1u) * kIpBins * 16u);
             }
         }
@@ -730,8 +758,8 @@ istft_pk4_kernel(const IstftPkParams p) {
                 for (int u = 0; u < kTkU; ++u) {
                     const int m = lane + 32 * u;
                     const bool mine = m < n_blk;
-                    ev[u] = mine ? __ldg(envp + r0p + 2 * m) : 0.f;
-                    wg[u] = (mine && wgp) ? __ldg(wgp + r0p + 2 * m) : 1.f;
+                    ev[u] = mine ? ldg_stream(envp + r0p + 2 * m) : 0.f;
+                    wg[u] = (mine && wgp) ? ldg_stream(wgp + r0p + 2 * m) : 1.f;
                 }
             }
             if (t <= tb) {                              // frames past tb only flush their hop-block
@@ -787,10 +815,10 @@ istft_pk4_kernel(const IstftPkParams p) {
                     const float2 v = *a;
                     *a = make_float2(0.f, 0.f);
                     if (pp >= ra && pp < rb && pp >= lim_lo && pp < lim_hi) {
-                        const float e = __ldg(envp + pp);
+                        const float e = ldg_stream(envp + pp);
                         float v0 = v.x * e, v1 = v.y * e;
                         if (wgp) {
-                            const float wgt = __ldg(wgp + pp);
+                            const float wgt = ldg_stream(wgp + pp);
                             v0 *= wgt;
                             v1 *= wgt;
                         }
@@ -814,7 +842,7 @@ istft_pk4_kernel(const IstftPkParams p) {
         mbar_wait(&s_full[warp], (it / kTkC) & 1);
         {
             float4* __restrict__ xs = slot;
-            const float4* __restrict__ ms = slot + kIpBins;
+            const float4* __restrict__ ms = slot + kTkMaskOff;
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             // ---- Z[k1] and Z[1024 - k1] from ONE pair P = Y[k1], Q = Y[1024 - k1], written over the two spectrum bins they came
             // from (no other lane reads those): a rolled loop instead of 16 unrolled register pairs
@@ -872,6 +900,266 @@ istft_pk4_kernel(const IstftPkParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_ready[s]);
+    }
+}
+
+// ---- streaming form, overlap-add from registers (AL_IP_RING=3) -----------------------------------------------------------
+// istft_pk4_kernel is paced by the shared-memory pipe (profiles/r02zi_*: 72 % busy in the steady state, the same 21.5 M
+// wavefronts and the same 0.127 ms for three different overlap-add codes): per frame 256 wavefronts of rows written by the
+// bulk copies + 1 540 by the warps, of which 256 are Z written to the slot and read back (the price of the rolled Z loop), 256
+// the parked frame written and read back, 256 the accumulator.  This form drops both round trips:
+//  * Z is formed in registers (16 unrolled register pairs, the mirror through four shuffles) -- affordable now that the FFT
+//    has one copy of the butterfly: the consumer loop stays near 32 KB of instructions;
+//  * the windowed frame goes from the registers straight into the accumulator.  Frames must be added in ascending order, so
+//    the consumer warps pass TOKENS (one mbarrier per warp and accumulator parity): a warp waits for the token of parity
+//    P0 & 1, adds its even samples, takes the final hop-block entries of that parity out, passes the token on, scales and
+//    stores them, then does the same with its odd samples on the other parity -- two chains, so two frames are being added at
+//    any time.  (The first token kernel of this round did this with 112 KB of code and lost to instruction fetches.)
+//  * the slot goes back to the producer as soon as the transposition has been read back: slots are held for rows -> Z ->
+//    half an iFFT only, 11 consumer warps.
+constexpr int kSrC = 11;                   // consumer warps
+constexpr int kSrSlots = 6;
+constexpr int kSrThreads = (kSrC + 1) * 32;
+
+template <bool MASK>
+__global__ void __launch_bounds__(kSrThreads, 1)
+istft_pk5_kernel(const IstftPkParams p) {
+    AL_DYN_SMEM(unsigned char, smem_raw);
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
+    float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
+    float2* s_acc = s_ctw + 1024;                                              // [2][1024] even / odd positions, (L, R)
+    float4* s_ring = reinterpret_cast<float4*>(s_acc + 2048);                  // [kSrSlots][kTkSlotF4]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + kSrSlots * kTkSlotF4);   // [kSrC]
+    uint64_t* s_empty = s_full + kSrC;                                          // [kSrSlots]
+    uint64_t* s_tok = s_empty + kSrSlots;                                       // [2][kSrC]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
+    const int chunk = g / p.stems, stem = g - chunk * p.stems;
+    const int hop = p.hop, T = p.n_frames;
+
+    const long long Pa = (long long)p.out_start + (long long)seg * p.hops_per_cta * hop;
+    const long long Pend = (long long)p.out_start + p.out_len;
+    const long long Pb = min(Pa + (long long)p.hops_per_cta * hop, Pend);
+    if (Pa >= Pb) return;
+    int ta = (int)((Pa - kIpN) / hop) + 1;              // first frame touching Pa
+    if (Pa < kIpN) ta = 0;
+    ta = max(ta, 0);
+    const int tb = min((int)((Pb - 1) / hop), T - 1);   // last frame touching Pb - 1
+    const int t_last = (int)((Pb - 1) / hop);           // hop-blocks are emitted up to the one holding Pb - 1
+
+    if (tid == 0) {
+        for (int w = 0; w < kSrC; ++w) {
+            mbar_init(&s_full[w], 1);
+            mbar_init(&s_tok[w], 1);
+            mbar_init(&s_tok[kSrC + w], 1);
+        }
+        for (int s = 0; s < kSrSlots; ++s) mbar_init(&s_empty[s], 1);
+#ifndef AL_CPU_EMUL
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+        fence_async_smem();
+        mbar_arrive(&s_tok[0]);                         // the first frame has no predecessor on either parity
+        mbar_arrive(&s_tok[kSrC]);
+    }
+    for (int i = tid; i < 1024; i += kSrThreads) {
+        s_tw[i] = p.tw[i];
+        s_ctw[i] = p.ctw[i];
+    }
+    for (int i = tid; i < 2048; i += kSrThreads) s_acc[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    if (warp == kSrC) {
+        // ================================= producer =================================
+        if (lane == 0) {
+            const float4* __restrict__ X = p.spec + (long long)(p.spec_has_stems ? g : chunk) * T * kIpBins;
+            const float4* __restrict__ M = MASK ? p.mask + (long long)g * T * kIpBins : nullptr;
+            for (int t = ta; t <= tb; ++t) {
+                const int it = t - ta, s = it % kSrSlots;
+                mbar_wait(&s_empty[s], ((it / kSrSlots) & 1) ^ 1);
+                float4* slot = s_ring + s * kTkSlotF4;
+                uint64_t* full = &s_full[it % kSrC];
+                bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
+                if (MASK) bulk_load_g2s(slot + kTkMaskOff, M + (long long)t * kIpBins, kIpBins * 16, full);
+                mbar_arrive_expect_tx(full, (MASK ? 2u : 1u) * kIpBins * 16u);
+            }
+        }
+        return;
+    }
+
+    // ================================= consumers: frame it = warp, warp + kSrC, ... =================================
+    const long long place = p.dst_offsets ? p.dst_offsets[chunk] : p.dst_off0 + (long long)chunk * p.dst_off_step;
+    float* __restrict__ dst0 = p.dst + ((long long)stem * 2) * p.dst_ch_stride + (long long)chunk * p.dst_chunk_stride + place;
+    float* __restrict__ dst1 = dst0 + p.dst_ch_stride;
+    const float2* __restrict__ g_win = reinterpret_cast<const float2*>(p.window);   // (w[2k], w[2k+1]), through L1
+    const int nxt = (warp + 1) % kSrC;
+    // 32-bit positions relative to out_start (the launcher checks the range)
+    const int ra = (int)(Pa - p.out_start), rb = (int)(Pb - p.out_start);
+    const long long lim_lo = -place, lim_hi = p.dst_limit - place;          // stores need lim_lo <= pp < lim_hi
+    const float* __restrict__ envp = p.inv_env + p.out_start;
+    const float* __restrict__ wgp = p.weight;
+#pragma unroll 1
+    for (int it = warp; ta + it <= t_last; it += kSrC) {
+        const int t = ta + it;
+        const bool live = t <= tb;                      // warp-uniform; frames past tb only flush their hop-block
+        const uint32_t ph = (uint32_t)(it / kSrC) & 1u;
+        {   // 1 / sum(w^2) and chunk weight of this frame's hop-block: into L2 now, read around the tokens
+            const int pp = t * hop - p.out_start + 32 * lane;
+            if (32 * lane < hop + 32 && pp >= ra && pp < rb) {
+                prefetch_l2(envp + pp);
+                if (wgp) prefetch_l2(wgp + pp);
+            }
+        }
+        float2 re[32], im[32];
+        if (live) {
+            const int s = it % kSrSlots;
+            float4* slot = s_ring + s * kTkSlotF4;
+            mbar_wait(&s_full[warp], ph);
+            {
+                float4* __restrict__ xs = slot;
+                const float4* __restrict__ ms = slot + kTkMaskOff;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                // ---- Z[k1] and Z[1024 - k1] from ONE pair P = Y[k1], Q = Y[1024 - k1], written over the two spectrum bins they came
+                // from (no other lane reads those): a rolled loop instead of 16 unrolled register pairs
+                {   // Z[512]: its own Hermitian partner (every lane forms it, the stores coincide)
+                    float2 pr, pi, zr, zi;
+                    ip_product<MASK>(xs[512], MASK ? ms[512] : z4, pr, pi);
+                    ip_combine(pr, pi, pr, pi, s_ctw[512], zr, zi);
+                    __syncwarp();
+                    xs[512] = make_float4(zr.x, zr.y, zi.x, zi.y);
+                }
+    #pragma unroll 4
+                for (int k1 = lane; k1 < 512; k1 += 32) {
+                    float2 pr, pi, qr, qi;
+                    ip_product<MASK>(xs[k1], MASK ? ms[k1] : z4, pr, pi);
+                    ip_product<MASK>(xs[1024 - k1], MASK ? ms[1024 - k1] : z4, qr, qi);
+                    if (k1 == 0) {               // C2R ignores Im of the DC and Nyquist bins
+                        pi = make_float2(0.f, 0.f);
+                        qi = make_float2(0.f, 0.f);
+                    }
+                    const float2 w = s_ctw[k1];
+                    const float2 ar = padd(pr, qr), ai = psub(pi, qi);     // A = P + conj(Q)
+                    const float2 dr = psub(pr, qr), di = padd(pi, qi);     // D = P - conj(Q)
+                    const float2 zr = pfma(dr, w.y, pfma(di, -w.x, ar));    // Z[k1] = A + i D conj(w)
+                    const float2 zi = pfma(di, w.y, pfma(dr, w.x, ai));
+                    // Z[1024 - k1] = conj(A) + i conj(D conj(w)): the arithmetic ip_combine(Q, P, -conj(w)) would do
+                    const float2 ndr = make_float2(-dr.x, -dr.y), nai = make_float2(-ai.x, -ai.y);
+                    const float2 mr = pfma(ndr, w.y, pfma(di, w.x, ar));
+                    const float2 mi = pfma(di, w.y, pfma(dr, w.x, nai));
+                    xs[k1] = make_float4(zr.x, zr.y, zi.x, zi.y);
+                    xs[1024 - k1] = make_float4(mr.x, mr.y, mi.x, mi.y);   // (k1 = 0 lands on the dead Nyquist bin)
+                }
+                __syncwarp();
+    #pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float4 v = xs[32 * r + lane];
+                    re[r] = make_float2(v.x, v.y);
+                    im[r] = make_float2(v.z, v.w);
+                }
+            }
+            __syncwarp();                               // every lane holds its Z: the slot is scratch now
+            warp_fft1024p_wide_rolled<true>(re, im, slot, s_tw, lane, &s_empty[s]);
+            // z[k] = (x[2k], x[2k+1]) * n_fft; the window carries 1 / n_fft.  The stages below take the accumulator parities in a
+            // FIXED order (even positions, then odd positions: with the sample order instead, an odd hop makes frame f's second
+            // stage and frame f + 1's first stage meet on the same parity and the two chains collapse into one that also holds
+            // the stores in between -- profiles/r02zk_*): re[] gets the samples of the even positions, im[] those of the odd ones
+            if ((t * hop) & 1) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float2 w = __ldg(g_win + 32 * r + lane);
+                    const float2 ev = pscale(re[r], w.x);
+                    re[r] = pscale(im[r], w.y);
+                    im[r] = ev;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const float2 w = __ldg(g_win + 32 * r + lane);
+                    re[r] = pscale(re[r], w.x);
+                    im[r] = pscale(im[r], w.y);
+                }
+            }
+        }
+        const int P0 = t * hop;
+        const int odd = P0 & 1, beta = P0 >> 1;
+        // ---- two stages: parity 0 (even positions), parity 1.  ONE copy of the stage in the instruction stream: the second trip
+        // finds its samples moved into re[]
+#pragma unroll 1
+        for (int arr = 0; arr < 2; ++arr) {
+            const int j0 = arr ^ odd;                   // the block's positions of this parity: P0 + j0 + 2 m
+            const int off = beta + (arr ? 0 : odd);     // the frame's k-th sample of this parity -> entry (off + k) & 1023; block entry m -> (off + m) & 1023
+            const int n_blk = (hop - j0 + 1) >> 1;
+            const int r0p = P0 + j0 - p.out_start;      // relative position of m = 0
+            // interior block (warp-uniform): every position is owned and lands inside the destination
+            const bool interior = hop <= 64 * kTkU && r0p >= ra && r0p + 2 * n_blk <= rb && r0p >= lim_lo && r0p + 2 * n_blk <= lim_hi;
+            float2* __restrict__ acc = s_acc + arr * 1024;
+            mbar_wait_hint(&s_tok[arr * kSrC + warp], ph, (uint32_t)p.tok_hint_ns);
+            if (live) {
+                const int e0 = off + lane;
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    float2 va[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) va[q] = acc[(e0 + 32 * (r0 + q)) & 1023];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[(e0 + 32 * (r0 + q)) & 1023] = padd(va[q], re[r0 + q]);
+                }
+                __syncwarp();
+            }
+            // the entries of this parity in the hop-block [P0, P0 + hop) are final: take them out, clear them
+            if (interior) {
+                float2 blk[kTkU];
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    const int m = lane + 32 * u;
+                    float2* a = acc + ((off + m) & 1023);
+                    blk[u] = *a;                        // (entries past the block belong to later blocks: read, not cleared)
+                    if (m < n_blk) *a = make_float2(0.f, 0.f);
+                }
+                __syncwarp();
+                if (lane == 0) { if (p.tok_relaxed) mbar_arrive_relaxed(&s_tok[arr * kSrC + nxt]); else mbar_arrive(&s_tok[arr * kSrC + nxt]); }
+                // scale and store outside the chain
+                const float* __restrict__ ep = envp + r0p + 2 * lane;
+                const float* __restrict__ wp = wgp ? wgp + r0p + 2 * lane : nullptr;
+                float* __restrict__ d0 = dst0 + r0p + 2 * lane;
+                float* __restrict__ d1 = dst1 + r0p + 2 * lane;
+                float ev[kTkU], wg[kTkU];              // all loads in flight before the first store (one latency, not seven)
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    const bool mine = lane + 32 * u < n_blk;
+                    ev[u] = mine ? ldg_stream(ep + 64 * u) : 0.f;
+                    wg[u] = (mine && wp) ? ldg_stream(wp + 64 * u) : 1.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kTkU; ++u) {
+                    if (lane + 32 * u < n_blk) {
+                        const float e = ev[u] * wg[u];
+                        d0[64 * u] = blk[u].x * e;
+                        d1[64 * u] = blk[u].y * e;
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int m = lane; m < n_blk; m += 32) {
+                    const int pp = r0p + 2 * m;
+                    float2* a = acc + ((off + m) & 1023);
+                    const float2 v = *a;
+                    *a = make_float2(0.f, 0.f);
+                    if (pp >= ra && pp < rb && pp >= lim_lo && pp < lim_hi) {
+                        float e = ldg_stream(envp + pp);
+                        if (wgp) e *= ldg_stream(wgp + pp);
+                        dst0[pp] = v.x * e;
+                        dst1[pp] = v.y * e;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { if (p.tok_relaxed) mbar_arrive_relaxed(&s_tok[arr * kSrC + nxt]); else mbar_arrive(&s_tok[arr * kSrC + nxt]); }
+            }
+            if (arr == 0 && live) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) re[r] = im[r];
+            }
+        }
     }
 }
 
@@ -936,6 +1224,12 @@ static size_t tk_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
     return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kTkSlots * kTkSlotF4 * sizeof(float4) +
            (size_t)(kTkC + 2 * kTkSlots) * sizeof(uint64_t);
 }
+// launch shape of istft_pk5_kernel: the segments of istft_pk4_kernel
+static size_t sr_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
+    tk_launch_shape(p, n_chunks, n_sm);
+    return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kSrSlots * kTkSlotF4 * sizeof(float4) +
+           (size_t)(3 * kSrC + kSrSlots) * sizeof(uint64_t);
+}
 // [emul-end]
 
 cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t stream) {
@@ -945,6 +1239,27 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
     // the ring-buffered kernel (default; AL_IP_RING=0 selects the register-pipelined one): hop >= 410 (register-form overlap-add)
     // AL_IP_RING: 2 (default) = the streaming kernel, 1 = the ring kernel with teams, 0 = the register-pipelined kernel
     static const int ring = getenv("AL_IP_RING") ? atoi(getenv("AL_IP_RING")) : 2;
+    if (ring == 3 && (long long)(p.n_frames + 8) * p.hop < 0x7fffffffLL && (long long)p.out_start + p.out_len < 0x7fffffffLL) {
+        p.ola_fast = 0;
+        p.l2_prefetch = 0;
+        static const int hint5 = getenv("AL_IP_HINT") ? atoi(getenv("AL_IP_HINT")) : 0;
+        static const int relaxed5 = getenv("AL_IP_RELAXED") ? atoi(getenv("AL_IP_RELAXED")) : 0;
+        p.tok_hint_ns = hint5;
+        p.tok_relaxed = relaxed5;
+        const size_t smem5 = sr_launch_shape(p, n_chunks, n_sm);
+        static PerDeviceOnce attr5[2];
+        PerDeviceOnce& a5 = attr5[p.mask ? 1 : 0];
+        if (a5.needed()) {
+            cudaError_t e = p.mask ? cudaFuncSetAttribute(istft_pk5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                   : cudaFuncSetAttribute(istft_pk5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+            a5.mark();
+        }
+        if (p.mask) istft_pk5_kernel<true><<<(unsigned)(rows * p.segs), kSrThreads, smem5, stream>>>(p);
+        else istft_pk5_kernel<false><<<(unsigned)(rows * p.segs), kSrThreads, smem5, stream>>>(p);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (ring == 2 && (long long)(p.n_frames + 8) * p.hop < 0x7fffffffLL && (long long)p.out_start + p.out_len < 0x7fffffffLL) {
         // the streaming kernel: any hop (the accumulator is position-addressed); positions are 32-bit inside a chunk
         p.ola_fast = 0;

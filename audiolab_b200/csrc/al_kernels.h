@@ -133,6 +133,8 @@ struct IstftPkParams {
     long long dst_limit;
     int ola_fast;             // interior rounds take the predicate-free overlap-add (AL_IP_OLAFAST=0 disables)
     int l2_prefetch;          // bulk L2 prefetch of the next round's rows (AL_IP_L2PF=0 disables)
+    int tok_hint_ns;          // istft_pk5_kernel: suspend-time hint of the token waits (0 = plain try_wait; AL_IP_HINT)
+    int tok_relaxed;          // istft_pk5_kernel: token arrivals with .relaxed semantics (experiment; AL_IP_RELAXED)
     // filled by the launcher
     int hops_per_cta;
     int segs;

@@ -226,14 +226,17 @@ def test_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, warp
             assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("hop,T,stems,use_mask,consumers,n_sm", [(441, 21, 1, True, 11, 3), (441, 13, 2, True, 7, 3),
-                                                                     (512, 17, 1, False, 11, 3), (1024, 9, 1, True, 7, 1),
-                                                                     (441, 61, 1, True, 11, 1), (300, 33, 1, False, 11, 2)])
+@pytest.mark.parametrize("hop,T,stems,use_mask,consumers,n_sm", [(441, 21, 1, True, 4, 3), (441, 13, 2, True, 4, 3),
+                                                                     (512, 17, 1, False, 4, 3), (1024, 9, 1, True, 4, 1),
+                                                                     (441, 61, 1, True, 4, 1), (300, 33, 1, False, 4, 2),
+                                                                     (441, 21, 1, True, 5, 3), (441, 13, 2, True, 5, 3),
+                                                                     (512, 17, 1, False, 5, 3), (1024, 9, 1, True, 5, 1),
+                                                                     (441, 61, 1, True, 5, 1), (300, 33, 1, False, 5, 2)])
 def test_token_ordered_packed_istft_emulated_matches_torch(emul, hop, T, stems, use_mask, consumers, n_sm):
-    """istft_pk4_kernel: producer warp + ring of row slots, Z[k] / Z[1024 - k] from one product pair (mirror through shuffles),
-    the slot as transposition scratch, overlap-add in a circular even / odd accumulator ordered by a token on mbarriers (odd and
-    even hops, hops above 448 = the in-place emission loop, hop 300 = seven frames per position), several segments per chunk,
-    flush blocks past the last frame."""
+    """istft_pk4_kernel (consumers = 4) and istft_pk5_kernel (5): producer warp + ring of row slots, Z[k] / Z[1024 - k] from one
+    product pair, the slot as transposition scratch, overlap-add in a circular even / odd accumulator -- by two dedicated warps
+    from the parked frame (pk4) or from the consumers' registers in token order (pk5); odd and even hops, hops above 448 = the
+    in-place emission loop, hop 300 = seven frames per position, several segments per chunk, flush blocks past the last frame."""
     import torch
     P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
     emul.emul_istft_pk4.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I]

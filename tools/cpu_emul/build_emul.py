@@ -183,7 +183,15 @@ extern "C" int emul_istft_pk4(const float* spec, const float* mask, int n_frames
     p.out_start = out_start; p.out_len = out_len; p.weight = weight; p.dst = dst; p.dst_ch_stride = dst_ch_stride;
     p.dst_chunk_stride = dst_chunk_stride; p.dst_offsets = nullptr; p.dst_off0 = dst_off0; p.dst_off_step = dst_off_step;
     p.dst_limit = dst_limit;
-    (void)consumers;
+    if (consumers == 5) {
+        const size_t smem5 = sr_launch_shape(p, n_chunks, n_sm);
+        if (smem5 > sizeof(g_smem)) return -2;
+        std::memset(g_smem, 0xFF, sizeof(g_smem));
+        const dim3 grid5(n_chunks * stems * p.segs), block5(kSrThreads);
+        if (mask) emul_launch(grid5, block5, [&] { istft_pk5_kernel<true>(p); });
+        else emul_launch(grid5, block5, [&] { istft_pk5_kernel<false>(p); });
+        return p.segs;
+    }
     const size_t smem = tk_launch_shape(p, n_chunks, n_sm);
     if (smem > sizeof(g_smem)) return -2;
     std::memset(g_smem, 0xFF, sizeof(g_smem));
