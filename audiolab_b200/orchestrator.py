@@ -8,8 +8,10 @@ the hot path, the post-blend residual de-bleed, and the htdemucs_6s multi-stem s
 DEVICE between stages -- the reference writes a PCM_16 temp WAV, runs ``separator.separate`` and
 re-loads the outputs for every model x file (:264-355).  ``pcm16_handoff=True`` reproduces that
 quantisation (:57-75) so the pipeline can be compared with the reference's sample for sample.
-Options that need architectures outside the hot path (VR de-noise / de-reverb, MDX23C drum split, ...)
-raise ``NotImplementedError`` instead of silently doing nothing.
+The post-ensemble transform chain (:777-839, call order :903-934) runs the reverb / echo removal (Mel-band RoFormer
+checkpoints) and crowd removal (MDX-Net) models the same way; options that need architectures outside the hot path (the VR
+de-noise model, MDX23C drum split, background-vocal split, reverb IR extraction, ...) raise ``NotImplementedError``
+instead of silently doing nothing.
 """
 from __future__ import annotations
 
@@ -45,9 +47,61 @@ STEM_LABELS = {
 
 _OUT_OF_SCOPE = {
     "separate_bg_vocals": False, "separate_drums": False, "separate_woodwinds": False, "alt_bass_model": False,
-    "reverb_removal": "Nothing", "echo_removal": "Nothing", "delay_removal": "Nothing",
-    "crowd_removal": "Nothing", "noise_removal": "Nothing", "store_reverb_ir": False,
+    "store_reverb_ir": False,
 }
+# (`delay_removal` is accepted and ignored, like the reference: its chain only looks at `echo_removal`, :797)
+TRANSFORM_SETTINGS = ("Nothing", "All", "All Vocals", "Main Vocals")
+
+
+def should_apply_transform(stem_name: str, setting: str) -> bool:
+    """stem_separator.py:679-700: which stems ("(vocals)", "(instrumental)", "(bg_vocals ...)") a setting covers."""
+    if setting == "All":
+        return True
+    if setting == "All Vocals":
+        return "vocals)" in stem_name.lower()
+    if setting == "Main Vocals":
+        return "vocals)" in stem_name and "(bg_vocals" not in stem_name.lower()
+    return False
+
+
+def transformations(opts: Dict) -> List[tuple]:
+    """(model file, label of the output to keep, setting) in the reference's order (:795-800, default models :147-149)."""
+    return [
+        ("dereverb_mel_band_roformer_anvuew_sdr_19.1729.ckpt", "No Reverb", opts.get("reverb_removal", "Nothing")),
+        (opts.get("delay_removal_model", "dereverb-echo_mel_band_roformer_sdr_13.4843_v2.ckpt"), "dry",
+         opts.get("echo_removal", "Nothing")),
+        (opts.get("crowd_removal_model", "UVR-MDX-NET_Crowd_HQ_1.onnx"), "No Crowd", opts.get("crowd_removal", "Nothing")),
+        (opts.get("noise_removal_model", "UVR-DeNoise.pth"), "No Noise", opts.get("noise_removal", "Nothing")),
+    ]
+
+
+def apply_transform_chain(sep, wav: torch.Tensor, stem_label: str, opts: Dict, skip_transforms=(), pcm16: bool = False,
+                          on_step: Optional[Callable] = None) -> torch.Tensor:
+    """stem_separator.py:777-839 on the device: every transform whose setting covers this stem loads its model, separates
+    the CURRENT array and keeps the output whose name carries the transform's label (of two outputs: the first if it
+    carries the label, else the second).  `pcm16` reproduces the PCM_16 temp WAV each model input goes through (:811)."""
+    current = wav
+    for model_file, out_label, setting in transformations(opts):
+        if out_label in skip_transforms or not should_apply_transform(f"({stem_label})", setting):
+            continue
+        arch = _arch_of(model_file)
+        if arch not in SUPPORTED_ARCHS:
+            raise NotImplementedError(f"{out_label} removal with {model_file}: the {arch} architecture is outside this "
+                                      "engine's scope (SURVEY.md section 8 row f3)")
+        sep.load_model(model_file)
+        stems = sep.separate_tensor(pcm16_roundtrip(current) if pcm16 else current)
+        names = list(stems)
+        key = out_label.replace(" ", "").lower()
+        chosen = None
+        if len(names) == 2:
+            chosen = names[0] if key in names[0].replace(" ", "").lower() else names[1]
+        else:
+            chosen = next((n for n in names if key in n.replace(" ", "").lower()), None)
+        if chosen is not None:
+            current = stems[chosen]
+        if on_step is not None:
+            on_step(f"TRANSFORM: {out_label} on {stem_label}")
+    return current
 
 
 def ensemble_models(strength: int):
@@ -168,14 +222,20 @@ def separate_music(input_dict: Dict[str, List[str]], callback: Optional[Callable
     sep = separator or Separator(log_level=logging.ERROR, invert_using_spec=True, use_autocast=True,
                                  model_file_dir=kwargs.get("model_file_dir", "models/audio_separator"),
                                  allow_random_init=bool(kwargs.get("allow_random_init", False)))
-    total_steps = len(models) * len(files) + (0 if vocals_only else len(files)) + 1 + len(files)
+    for key in ("reverb_removal", "echo_removal", "crowd_removal", "noise_removal"):
+        if kwargs.get(key, "Nothing") not in TRANSFORM_SETTINGS:
+            raise ValueError(f"{key}={kwargs[key]!r}: one of {TRANSFORM_SETTINGS}")
+    # progress accounting of predict_with_model (:885-888: reverb, crowd and noise removal count, echo removal does not)
+    trans_opts = [kwargs.get(k, "Nothing") for k in ("reverb_removal", "crowd_removal", "noise_removal")]
+    transform_steps = (sum(o in ("All", "All Vocals", "Main Vocals") for o in trans_opts) + sum(o == "All" for o in trans_opts)) * len(files)
+    total_steps = len(models) * len(files) + transform_steps + (0 if vocals_only else len(files)) + 1 + len(files)
     step = 0
 
     def advance(desc: str):
         nonlocal step
         step += 1
         if callback is not None:
-            callback(step / total_steps, desc, total_steps)
+            callback(min(step / total_steps, 1.0), desc, total_steps)
 
     if callback is not None:
         callback(0, "Starting ensemble separation...", total_steps)
@@ -201,6 +261,21 @@ def separate_music(input_dict: Dict[str, List[str]], callback: Optional[Callable
         res["instrumental"] = blend_tracks(res.pop("instrumental_list"), wi)
         res["instrumental"] = debleed_instrumental(mixes[i], res["vocals"], res["instrumental"], sep.sample_rate,
                                                    residual_blend)
+    # transform chain (:903-934; the background-vocal split between its two halves is out of scope): reverb removal runs the
+    # WHOLE chain on the vocals first; with crowd or noise removal set the chain runs again on the vocals without its reverb
+    # step, and on the instrumental
+    if kwargs.get("reverb_removal", "Nothing") != "Nothing":
+        for i, res in enumerate(results):
+            base = os.path.basename(files[i][1])
+            res["vocals"] = apply_transform_chain(sep, res["vocals"], "vocals", kwargs, pcm16=pcm16,
+                                                  on_step=lambda d, b=base: advance(f"{d} for {b}"))
+    if any(kwargs.get(k, "Nothing") != "Nothing" for k in ("crowd_removal", "noise_removal")):
+        for i, res in enumerate(results):
+            base = os.path.basename(files[i][1])
+            res["vocals"] = apply_transform_chain(sep, res["vocals"], "vocals", kwargs, skip_transforms=("No Reverb",),
+                                                  pcm16=pcm16, on_step=lambda d, b=base: advance(f"{d} for {b}"))
+            res["instrumental"] = apply_transform_chain(sep, res["instrumental"], "instrumental", kwargs, pcm16=pcm16,
+                                                        on_step=lambda d, b=base: advance(f"{d} for {b}"))
     if not vocals_only:
         # 6-stem stage on the full mix (stem_separator.py:459-503); vocals / instrumental stay the ensemble's
         sep.load_model("htdemucs_6s.yaml")

@@ -26,6 +26,17 @@ from .configs import HTDemucsConfig, MdxConfig, RoformerConfig
 from .demix import HTDemucsDemixer, MdxDemixer, RoformerDemixer
 from .wavio import read_wav, write_wav
 
+# (primary, secondary) stem names of the single-target models the orchestrator's transform chain loads; the reference picks
+# the output to keep by looking for its label ("No Reverb", "dry", "No Crowd") in the file names audio-separator derives
+# from these (stem_separator.py:795-822, debug_reverb :1046-1056 lists the dry / wet strings of the de-reverb models)
+STEMS_OF = {
+    "dereverb_mel_band_roformer_anvuew_sdr_19.1729.ckpt": ("noreverb", "reverb"),
+    "dereverb_mel_band_roformer_less_aggressive_anvuew_sdr_18.8050.ckpt": ("noreverb", "reverb"),
+    "dereverb-echo_mel_band_roformer_sdr_10.0169.ckpt": ("dry", "No dry"),
+    "dereverb-echo_mel_band_roformer_sdr_13.4843_v2.ckpt": ("dry", "No dry"),
+    "UVR-MDX-NET_Crowd_HQ_1.onnx": ("No Crowd", "Crowd"),
+}
+
 DEMUCS_4 = ["Drums", "Bass", "Other", "Vocals"]
 DEMUCS_6 = ["Drums", "Bass", "Other", "Vocals", "Guitar", "Piano"]
 
@@ -246,6 +257,9 @@ class Separator:
             raise NotImplementedError(
                 f"{model_filename}: the {arch} architecture is outside this engine's scope "
                 "(north star: MDX-Net, BS/Mel-RoFormer, HTDemucs)")
+        if model_filename in STEMS_OF and len(inst.stem_names) == 1:
+            inst.primary_stem, inst.secondary_stem = STEMS_OF[model_filename]
+            inst.stem_names = [inst.primary_stem]
         self.model_instance = inst
         self.model_name = os.path.splitext(model_filename)[0]
         return inst

@@ -119,6 +119,79 @@ def test_separate_music_orchestration(tmp_path):
     assert np.abs(got_i - want_i).max() <= 2e-6
 
 
+@pytest.mark.parametrize("stem", ["(vocals)", "(Vocals)", "(instrumental)", "(bg_vocals)", "(bg_vocals) (vocals)", "(drums)"])
+@pytest.mark.parametrize("setting", ["Nothing", "All", "All Vocals", "Main Vocals", "Something else"])
+def test_should_apply_transform_truth_table(stem, setting):
+    from oracle import transforms as tref
+    assert orch.should_apply_transform(stem, setting) == tref.should_apply_transform(stem, setting)
+
+
+class _ChainSeparator(_StubSeparator):
+    """Transform models scale their input by a model-specific factor; output names follow audiolab_b200.separator.STEMS_OF."""
+    FACT = {"dereverb": 0.9, "dereverb-echo": 0.8, "UVR-MDX-NET_Crowd": 0.7}
+
+    def separate_tensor(self, mix):
+        from audiolab_b200.separator import STEMS_OF
+        if self.name in STEMS_OF:
+            self.inputs.append(mix.clone())
+            prim, sec = STEMS_OF[self.name]
+            k = next(v for p, v in sorted(self.FACT.items(), key=lambda kv: -len(kv[0])) if self.name.startswith(p))
+            return {prim: mix * k, sec: mix * (1 - k)}
+        return super().separate_tensor(mix)
+
+
+@pytest.mark.parametrize("opts", [
+    dict(reverb_removal="Main Vocals"),
+    dict(reverb_removal="All Vocals", echo_removal="All Vocals", crowd_removal="All"),
+    dict(crowd_removal="All"),
+    dict(echo_removal="All"),                      # the reference only enters the chain for reverb / crowd / noise: no-op
+    dict(reverb_removal="All", crowd_removal="Main Vocals", delay_removal="All"),
+])
+def test_transform_chain_follows_the_reference_order_and_output_choice(tmp_path, opts):
+    """separate_music's transform stage against the oracle restatement of stem_separator.py:777-839 / :903-934 with the same
+    stub models: order of the loaded models, the chain running twice on the vocals when reverb AND crowd removal are set,
+    and which of a model's two outputs is kept."""
+    from audiolab_b200.separator import STEMS_OF
+    from audiolab_b200.wavio import read_wav, write_wav
+    from oracle import transforms as tref
+    mix = synth_mix(12000, seed=11)
+    src = tmp_path / "song.wav"
+    write_wav(str(src), mix, 44100, "FLOAT")
+    out_dir = str(tmp_path / "stems")
+    stub = _ChainSeparator()
+    orch.separate_music({out_dir: [str(src)]}, separator=stub, vocals_only=True, ensemble_strength=1, **opts)
+    # oracle side: the same fake models on numpy arrays
+    log = []
+
+    def run_model(model_file, arr):
+        log.append(model_file)
+        prim, sec = STEMS_OF[model_file]
+        k = next(v for p, v in sorted(_ChainSeparator.FACT.items(), key=lambda kv: -len(kv[0])) if model_file.startswith(p))
+        return [(f"song_({prim})_{model_file}", arr * np.float32(k)), (f"song_({sec})_{model_file}", arr * np.float32(1 - k))]
+
+    voc0 = ref.blend_tracks([mix * np.float32(0.6)], [8.6])       # the stub's ensemble output with one model loaded
+    inst0 = ref.debleed_instrumental(mix, voc0, ref.blend_tracks([mix * np.float32(0.4)], [16.0]), 44100, 0.2)
+    results = {"song": {"vocals": voc0, "instrumental": inst0}}
+    tref.transform_stage(results, opts, run_model)
+    assert stub.loaded[1:] == log
+    got_v, _ = read_wav(os.path.join(out_dir, "song__(Vocals).wav"))
+    got_i, _ = read_wav(os.path.join(out_dir, "song__(Instrumental).wav"))
+    assert np.abs(got_v - results["song"]["vocals"]).max() <= 1e-6
+    assert np.abs(got_i - results["song"]["instrumental"]).max() <= 2e-6
+
+
+def test_transform_chain_refuses_models_outside_the_scope(tmp_path):
+    from audiolab_b200.wavio import write_wav
+    src = tmp_path / "song.wav"
+    write_wav(str(src), synth_mix(6000, seed=12), 44100, "FLOAT")
+    with pytest.raises(NotImplementedError):       # UVR-DeNoise.pth is a VR-architecture model (SURVEY.md 8 row f3)
+        orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, noise_removal="All")
+    with pytest.raises(ValueError):
+        orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, crowd_removal="Everything")
+    with pytest.raises(NotImplementedError):
+        orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, store_reverb_ir=True)
+
+
 @pytest.mark.gpu
 def test_orchestrator_gpu():
     """The same de-bleed arithmetic on the device, and the real Separator through separate_music (random-init nets)."""
@@ -130,3 +203,42 @@ def test_orchestrator_gpu():
     got = orch.debleed_instrumental(torch.from_numpy(mix).cuda(), torch.from_numpy(voc).cuda(), torch.from_numpy(est).cuda(),
                                     44100, 0.4).cpu().numpy()
     assert np.abs(got - want).max() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_transform_chain_gpu(tmp_path):
+    """The transform stage with the real Separator on the device (small random-init networks through model_overrides): the
+    de-reverb Mel-band RoFormer and the crowd MDX-Net load under the reference's file names, their outputs carry the stem
+    names the chain looks for, and the vocals that come out are the chain applied to the ensemble's vocals."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from audiolab_b200.separator import Separator
+    from audiolab_b200.wavio import read_wav, write_wav
+    small = dict(dim=64, depth=1, heads=2, dim_head=32, chunk_size=441 * 60)
+    sep = Separator(log_level=40, allow_random_init=True, use_autocast=False,
+                    mdx_params={"segment_size": 16, "full_size_net": False},
+                    model_overrides={"mel_roformer": small, "bs_roformer": small})
+    mix = synth_mix(441 * 150, seed=21)
+    src = tmp_path / "clip.wav"
+    write_wav(str(src), mix, 44100, "FLOAT")
+    out_dir = str(tmp_path / "stems")
+    outs = orch.separate_music({out_dir: [str(src)]}, separator=sep, ensemble_strength=1, reverb_removal="Main Vocals",
+                               crowd_removal="All")
+    assert sorted(os.path.basename(o) for o in outs) == ["clip__(Instrumental).wav", "clip__(Vocals).wav"]
+    # the same stages by hand
+    x = sep.prepare_mix(torch.from_numpy(mix), 44100)
+    sep.load_model("vocals_mel_band_roformer.ckpt")
+    st = sep.separate_tensor(x)
+    voc = orch.blend_tracks([st["Vocals"]], [8.6])
+    inst = orch.debleed_instrumental(x, voc, orch.blend_tracks([st["Instrumental"]], [16.0]), 44100, 0.2)
+    for name, key in (("dereverb_mel_band_roformer_anvuew_sdr_19.1729.ckpt", "noreverb"), ("UVR-MDX-NET_Crowd_HQ_1.onnx", "No Crowd"),
+                      ("UVR-MDX-NET_Crowd_HQ_1.onnx", "No Crowd")):
+        sep.load_model(name)
+        assert list(sep.separate_tensor(voc))[0] == key
+        voc = sep.separate_tensor(voc)[key]
+    sep.load_model("UVR-MDX-NET_Crowd_HQ_1.onnx")
+    inst = sep.separate_tensor(inst)["No Crowd"]
+    got_v, _ = read_wav(os.path.join(out_dir, "clip__(Vocals).wav"))
+    got_i, _ = read_wav(os.path.join(out_dir, "clip__(Instrumental).wav"))
+    assert np.abs(got_v - voc.cpu().numpy()).max() <= 1e-6
+    assert np.abs(got_i - inst.cpu().numpy()).max() <= 1e-6
