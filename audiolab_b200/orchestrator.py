@@ -10,8 +10,9 @@ re-loads the outputs for every model x file (:264-355).  ``pcm16_handoff=True`` 
 quantisation (:57-75) so the pipeline can be compared with the reference's sample for sample.
 The post-ensemble transform chain (:777-839, call order :903-934) runs the reverb / echo removal (Mel-band RoFormer
 checkpoints) and crowd removal (MDX-Net) models the same way; options that need architectures outside the hot path (the VR
-de-noise model, MDX23C drum split, background-vocal split, reverb IR extraction, ...) raise ``NotImplementedError``
-instead of silently doing nothing.
+de-noise model, MDX23C drum split, background-vocal split, ...) raise ``NotImplementedError``
+instead of silently doing nothing.  ``store_reverb_ir`` writes ``impulse_response.ir`` (reverb_ir.py) from the de-reverb
+pass's two outputs (:823-829).
 """
 from __future__ import annotations
 
@@ -47,7 +48,6 @@ STEM_LABELS = {
 
 _OUT_OF_SCOPE = {
     "separate_bg_vocals": False, "separate_drums": False, "separate_woodwinds": False, "alt_bass_model": False,
-    "store_reverb_ir": False,
 }
 # (`delay_removal` is accepted and ignored, like the reference: its chain only looks at `echo_removal`, :797)
 TRANSFORM_SETTINGS = ("Nothing", "All", "All Vocals", "Main Vocals")
@@ -76,7 +76,7 @@ def transformations(opts: Dict) -> List[tuple]:
 
 
 def apply_transform_chain(sep, wav: torch.Tensor, stem_label: str, opts: Dict, skip_transforms=(), pcm16: bool = False,
-                          on_step: Optional[Callable] = None) -> torch.Tensor:
+                          on_step: Optional[Callable] = None, ir_path: Optional[str] = None) -> torch.Tensor:
     """stem_separator.py:777-839 on the device: every transform whose setting covers this stem loads its model, separates
     the CURRENT array and keeps the output whose name carries the transform's label (of two outputs: the first if it
     carries the label, else the second).  `pcm16` reproduces the PCM_16 temp WAV each model input goes through (:811)."""
@@ -99,6 +99,14 @@ def apply_transform_chain(sep, wav: torch.Tensor, stem_label: str, opts: Dict, s
             chosen = next((n for n in names if key in n.replace(" ", "").lower()), None)
         if chosen is not None:
             current = stems[chosen]
+            # :823-829: the reverb the de-reverb pass took out of the VOCALS, as an impulse response next to the stems
+            if out_label == "No Reverb" and stem_label.lower() == "vocals" and ir_path and len(names) == 2:
+                from .reverb_ir import extract_reverb
+                alt = names[1] if chosen == names[0] else names[0]
+                try:
+                    extract_reverb(stems[chosen], stems[alt], sep.sample_rate, ir_path)
+                except Exception as e:             # the reference logs and carries on (:828-829)
+                    logger.error(f"Error extracting IR: {e}")
         if on_step is not None:
             on_step(f"TRANSFORM: {out_label} on {stem_label}")
     return current
@@ -267,7 +275,11 @@ def separate_music(input_dict: Dict[str, List[str]], callback: Optional[Callable
     if kwargs.get("reverb_removal", "Nothing") != "Nothing":
         for i, res in enumerate(results):
             base = os.path.basename(files[i][1])
-            res["vocals"] = apply_transform_chain(sep, res["vocals"], "vocals", kwargs, pcm16=pcm16,
+            ir_path = None
+            if kwargs.get("store_reverb_ir", False):
+                os.makedirs(files[i][0], exist_ok=True)
+                ir_path = os.path.join(files[i][0], "impulse_response.ir")
+            res["vocals"] = apply_transform_chain(sep, res["vocals"], "vocals", kwargs, pcm16=pcm16, ir_path=ir_path,
                                                   on_step=lambda d, b=base: advance(f"{d} for {b}"))
     if any(kwargs.get(k, "Nothing") != "Nothing" for k in ("crowd_removal", "noise_removal")):
         for i, res in enumerate(results):

@@ -189,7 +189,55 @@ def test_transform_chain_refuses_models_outside_the_scope(tmp_path):
     with pytest.raises(ValueError):
         orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, crowd_removal="Everything")
     with pytest.raises(NotImplementedError):
-        orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, store_reverb_ir=True)
+        orch.separate_music({str(tmp_path / "o"): [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, separate_drums=True)
+
+
+def _reverb_case(n=30000, sr=8000, seed=5):
+    rs = np.random.RandomState(seed)
+    dry = (rs.randn(n, 2) * np.exp(-np.arange(n) / 9000.0)[:, None]).astype(np.float32) * 0.3
+    t = np.arange(int(0.3 * sr))
+    ir = np.exp(-t / (0.04 * sr)) * rs.randn(t.size) * 0.2
+    ir[0] = 1.0
+    wet = np.stack([np.convolve(dry[:, c], ir)[:n] for c in range(2)], axis=1).astype(np.float32)
+    # an envelope whose dB curve IS the model the reference fits (a exp(-b t) + c, b = 3 -> "decay time" 1 s): a well-posed fit
+    tt = np.arange(n) / sr
+    env = 10.0 ** ((40.0 * np.exp(-3.0 * tt) - 60.0) / 20.0)
+    wet = (np.sign(wet + 1e-12) * env[:, None] / np.sqrt(2.0)).astype(np.float32)
+    return dry, wet, sr
+
+
+def test_reverb_ir_extraction_matches_the_reference_restatement(tmp_path):
+    """audiolab_b200/reverb_ir.py (torch.fft, fp64) against oracle/reverb_ir.py (numpy restatement of handlers/reverb.py:113-172):
+    pre-delay, RT60 fit, Wiener-deconvolved impulse response and its statistics; the JSON file of the reference."""
+    import json
+    from audiolab_b200 import reverb_ir
+    from oracle import reverb_ir as rref
+    dry, wet, sr = _reverb_case()
+    want = rref.extract_params(dry, wet, sr)
+    got = reverb_ir.extract_reverb_params(torch.from_numpy(dry.T.copy()), torch.from_numpy(wet.T.copy()), sr)
+    assert set(got) == set(want)
+    for k in ("sample_rate", "pre_delay"):
+        assert got[k] == want[k]
+    assert abs(got["decay_time"] - 1.0) < 1e-3 and abs(got["decay_time"] - want["decay_time"]) <= 1e-6
+    # fp64 on both sides; the division by |H|^2 + 1e-6 amplifies the last-bit differences of two FFT libraries
+    for k in ("early_reflection_ratio", "late_reverb_ratio", "diffusion", "spectral_centroid"):
+        assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), k
+    ir_w = np.array(want["impulse_response"])
+    assert np.abs(np.array(got["impulse_response"]) - ir_w).max() <= 1e-6 * np.abs(ir_w).max()
+    p = reverb_ir.extract_reverb(torch.from_numpy(dry.T.copy()), torch.from_numpy(wet.T.copy()), sr, str(tmp_path / "ir.json"))
+    assert json.load(open(p))["decay_time"] == got["decay_time"]
+
+
+def test_store_reverb_ir_writes_the_impulse_response_of_the_vocals_pass(tmp_path):
+    import json
+    from audiolab_b200.wavio import write_wav
+    src = tmp_path / "song.wav"
+    write_wav(str(src), synth_mix(9000, seed=13), 44100, "FLOAT")
+    out_dir = str(tmp_path / "stems")
+    orch.separate_music({out_dir: [str(src)]}, separator=_ChainSeparator(), ensemble_strength=1, reverb_removal="All",
+                        store_reverb_ir=True)
+    params = json.load(open(os.path.join(out_dir, "impulse_response.ir")))
+    assert params["sample_rate"] == 44100 and len(params["impulse_response"]) == 9000   # shorter than 2 s: the whole signal
 
 
 @pytest.mark.gpu
@@ -242,3 +290,20 @@ def test_transform_chain_gpu(tmp_path):
     got_i, _ = read_wav(os.path.join(out_dir, "clip__(Instrumental).wav"))
     assert np.abs(got_v - voc.cpu().numpy()).max() <= 1e-6
     assert np.abs(got_i - inst.cpu().numpy()).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_reverb_ir_extraction_gpu():
+    """The same extraction with the stems on the device (cuFFT fp64) against the numpy restatement of the reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from audiolab_b200 import reverb_ir
+    from oracle import reverb_ir as rref
+    dry, wet, sr = _reverb_case(n=120000, sr=44100, seed=6)
+    want = rref.extract_params(dry, wet, sr)
+    got = reverb_ir.extract_reverb_params(torch.from_numpy(dry.T.copy()).cuda(), torch.from_numpy(wet.T.copy()).cuda(), sr)
+    assert got["pre_delay"] == want["pre_delay"] and abs(got["decay_time"] - want["decay_time"]) <= 1e-5
+    for k in ("early_reflection_ratio", "late_reverb_ratio", "diffusion", "spectral_centroid"):
+        assert abs(got[k] - want[k]) <= 1e-6 * max(1.0, abs(want[k])), k
+    ir_w = np.array(want["impulse_response"])
+    assert np.abs(np.array(got["impulse_response"]) - ir_w).max() <= 1e-6 * np.abs(ir_w).max()
