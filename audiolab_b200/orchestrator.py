@@ -213,6 +213,9 @@ def separate_music(input_dict: Dict[str, List[str]], callback: Optional[Callable
     for key, off in _OUT_OF_SCOPE.items():
         if kwargs.get(key, off) not in (off, None):
             raise NotImplementedError(f"{key}={kwargs[key]!r} needs a model family outside this engine's scope")
+    for key in ("reverb_removal", "echo_removal", "crowd_removal", "noise_removal"):
+        if kwargs.get(key, "Nothing") not in TRANSFORM_SETTINGS:
+            raise ValueError(f"{key}={kwargs[key]!r}: one of {TRANSFORM_SETTINGS}")
     vocals_only = bool(kwargs.get("vocals_only", True))
     strength = int(kwargs.get("ensemble_strength", 2))
     models = ensemble_models(strength)
@@ -230,9 +233,6 @@ def separate_music(input_dict: Dict[str, List[str]], callback: Optional[Callable
     sep = separator or Separator(log_level=logging.ERROR, invert_using_spec=True, use_autocast=True,
                                  model_file_dir=kwargs.get("model_file_dir", "models/audio_separator"),
                                  allow_random_init=bool(kwargs.get("allow_random_init", False)))
-    for key in ("reverb_removal", "echo_removal", "crowd_removal", "noise_removal"):
-        if kwargs.get(key, "Nothing") not in TRANSFORM_SETTINGS:
-            raise ValueError(f"{key}={kwargs[key]!r}: one of {TRANSFORM_SETTINGS}")
     # progress accounting of predict_with_model (:885-888: reverb, crowd and noise removal count, echo removal does not)
     trans_opts = [kwargs.get(k, "Nothing") for k in ("reverb_removal", "crowd_removal", "noise_removal")]
     transform_steps = (sum(o in ("All", "All Vocals", "Main Vocals") for o in trans_opts) + sum(o == "All" for o in trans_opts)) * len(files)

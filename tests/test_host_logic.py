@@ -180,7 +180,10 @@ def test_separate_wrapper_surface_and_cache(tmp_path, monkeypatch):
 def test_orchestrator_rejects_out_of_scope_options():
     from audiolab_b200.orchestrator import separate_music
     with pytest.raises(NotImplementedError):
-        separate_music({"/tmp/x": []}, reverb_removal="All")
+        separate_music({"/tmp/x": []}, separate_bg_vocals=True)
+    with pytest.raises(ValueError):
+        separate_music({"/tmp/x": ["/nonexistent.wav"]}, reverb_removal="Everything")
+    assert separate_music({"/tmp/x": ["/nonexistent.wav"]}, reverb_removal="All") == []   # in scope since the transform chain
     with pytest.raises(NotImplementedError):          # MDX23C is the 4th model of the reference's list
         separate_music({"/tmp/x": []}, ensemble_strength=4)
     assert separate_music({"/tmp/x": ["/nonexistent.wav"]}) == []
