@@ -644,10 +644,15 @@ istft_pk3_kernel(const IstftPkParams p) {
 //    version passed a token between the CONSUMER warps instead: three times slower -- each warp entered the serial section
 //    with cold instructions, 67 % of its stall samples there were instruction fetches, profiles/r02zd_*.)
 //  * consumer warps never meet: row slot -> Z -> iFFT with the SLOT as transposition scratch -> window -> the frame parked
-//    in the same slot (even samples, odd samples) -> "ready" -> next frame.  No per-warp scratch, so 6 slots of rows
-//    (197 KB) are in flight / in use and 9 consumer warps of 168 registers run;
-//  * Z[k] and Z[1024 - k] come from ONE product pair: Z[1024 - k] = conj(A) + i conj(B) for Z[k] = A + i B, sent to the
-//    owning lane with four shuffles -- half the LDS.128 and half the mask multiplications of the row -> Z phase.
+//    in the same slot, per position parity and already rotated to the accumulator's entries -> "ready" -> next frame.  No
+//    per-warp scratch, so 6 slots of rows (198 KB) are in flight / in use and 9 consumer warps of 168 registers run;
+//  * Z[k] and Z[1024 - k] come from ONE product pair: Z[1024 - k] = conj(A) + i conj(B) for Z[k] = A + i B -- half the LDS.128
+//    and half the mask multiplications of the row -> Z phase -- in a ROLLED loop that writes both over the spectrum bins they
+//    were made from (the lane that forms Z[1024 - k] does not own it; 16 unrolled register pairs + shuffles would save the
+//    round trip through the slot but not fit the instruction cache, see below);
+//  * the loop body all nine consumers stream through is ~1 600 SASS lines (+ 650 of the overlap-add warps): with the Z pairs
+//    unrolled and two inlined FFT passes (6 000 - 7 000 lines) 25 - 34 % of the stall samples were instruction fetches and the
+//    kernel ran 2 - 3 x slower than istft_pk3_kernel; warp_fft1024p_wide_rolled has ONE copy of the 32-point butterfly.
 // Barriers (a parity wait can only tell the current phase from the one before, so every waiter sees every phase of its
 // barrier): full[w] per consumer warp (its j-th frame = phase j), ready[s] per slot (the two overlap-add warps take every
 // frame), empty[s] per slot (two arrivals, the producer waits).
