@@ -639,6 +639,13 @@ def run_ours(args) -> None:
         shard_info = {"halo_bytes_per_boundary": int(mx[2].item()), "halo_bytes_total_per_step": int(sm[2].item()),
                       "halo_wait_ms_max_over_ranks": round(float(mx[3].item()), 4),
                       "tail_chunks_first": st.get("tail_chunks"),
+                      # why the driver's weak-scaling efficiency against the N = 1 line (ONE 60 s track) cannot reach 1: a track of
+                      # N x 60 s has overlap - 1 more chunks per interior boundary than N separate 60 s tracks (whose first and last
+                      # 6 s are covered by fewer chunks); every chunk is still evaluated exactly once, nothing is recomputed
+                      "chunks_in_this_track": len(offs),
+                      "chunks_in_n_separate_tracks": world * len(roformer_schedule(track_seconds * SR, cfg.chunk_size, cfg.step)[0]),
+                      "ideal_weak_efficiency_vs_n1": round(world * len(roformer_schedule(track_seconds * SR, cfg.chunk_size, cfg.step)[0])
+                                                           / len(offs), 4),
                       "selfcheck_vs_single_gpu_ola": {"max_abs_diff": float(mx[0].item()), "bitwise_all_ranks": mx[1].item() == 0.0},
                       "note": "halo_wait_ms = time the compute stream blocks on the exchange after the interior chunks "
                               "(the isend/irecv were posted before them)"}
