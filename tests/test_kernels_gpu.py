@@ -144,10 +144,12 @@ def test_istft_fused_complex_mask_and_stems(cuda):
 
 
 @pytest.mark.parametrize("hop,T,stems,use_mask", [(441, 301, 2, True), (441, 61, 1, False), (512, 130, 1, True),
-                                                  (300, 97, 3, True)])
+                                                  (300, 97, 3, True), (100, 150, 1, True), (256, 77, 2, False),
+                                                  (777, 45, 1, True), (1024, 33, 2, True)])
 def test_istft_frame_interleaved_packed_path_matches_torch(cuda, hop, T, stems, use_mask):
     """Layout 3 (RoFormer 'b t (f c)'), stereo, n_fft 2048 -> the packed fast path of K2 (al_istft_pk.cu).
-    Arbitrary spectrum incl. Im(DC) / Im(Nyquist) != 0, fused mask, stems, ragged out_len, several segments."""
+    Arbitrary spectrum incl. Im(DC) / Im(Nyquist) != 0, fused mask, stems, ragged out_len, several segments; hops from 100
+    (21 frames per position) to 1024, odd and even, below and above the 448 of the register-held hop-block emission."""
     from audiolab_b200 import spectral as sp
     n_fft, F, nch = 2048, 1025, 2
     L = (T - 1) * hop - 37                                                       # out_len not a multiple of hop
