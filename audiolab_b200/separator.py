@@ -199,10 +199,22 @@ class Separator:
                             overlap=float(self.mdx_params["overlap"]), denoise=bool(self.mdx_params["enable_denoise"]),
                             zero_low_bins=3)
             cfg = replace(cfg, **ov)
+            if net is None and os.path.isfile(path):
+                # the released .onnx itself, as a device-resident torch module (nets/onnx_graph.py: own protobuf reader + graph
+                # executor; the reference's onnx2torch branch, handlers/patch_separate.py:54-63, without the onnx packages)
+                from .nets.onnx_graph import OnnxGraphNet
+                net = OnnxGraphNet.from_file(path)
+                if net.dim_f:
+                    cfg = replace(cfg, dim_f=int(net.dim_f))
+                if net.dim_t and net.dim_t != cfg.dim_t:
+                    if net.dim_t & (net.dim_t - 1):
+                        raise ValueError(f"{path}: model dim_t {net.dim_t} is not a power of two")
+                    self.logger.warning(f"{model_filename}: segment_size {seg} != the model's dim_t {net.dim_t}; using the model's")
+                    seg = int(net.dim_t)
+                    cfg = replace(cfg, dim_t_log2=int(np.log2(seg)))
             if net is None:
-                # No onnxruntime / onnx importer here (handlers/patch_separate.py:45-63 runs the .onnx through ORT).  A
-                # released model is taken as a converted state dict `<name>.pt` / `.pth` next to the `.onnx` name (KUIELab
-                # module names, nets/tfc_tdf.py::ConvTdfNet); otherwise seeded random weights of the released shape.
+                # Without the .onnx: a released model as a converted state dict `<name>.pt` / `.pth` next to the `.onnx` name
+                # (KUIELab module names, nets/tfc_tdf.py::ConvTdfNet); otherwise seeded random weights of the released shape.
                 from .nets.tfc_tdf import ConvTdfNet
                 stem = os.path.splitext(path)[0]
                 converted = next((stem + ext for ext in (".pt", ".pth", ".ckpt") if os.path.exists(stem + ext)), None)
@@ -210,7 +222,7 @@ class Separator:
                     sd = torch.load(converted, map_location="cpu", weights_only=True)
                     net = ConvTdfNet.from_state_dict(sd.get("state_dict", sd) if isinstance(sd, dict) else sd, cfg.dim_f)
                 elif not self.allow_random_init:
-                    raise FileNotFoundError(f"{path}: no ONNX importer in this build and no converted state dict "
+                    raise FileNotFoundError(f"{path}: neither the .onnx file nor a converted state dict "
                                             f"({stem}.pt); pass model_overrides[...]['net'] or allow_random_init=True")
                 else:
                     torch.manual_seed(4321)
