@@ -154,4 +154,5 @@ def test_separator_runs_an_mdx_model_from_its_onnx_file(tmp_path):
     net = OnnxGraphNet.from_file(str(tmp_path / "UVR-MDX-NET-Voc_FT.onnx")).eval()
     ocfg = omdx.MdxConfig(n_fft=6144, dim_f=3072, dim_t_log2=4, overlap=0.25, zero_low_bins=3)
     ref = omdx.demix_windowed(mix, copy.deepcopy(net), ocfg)
-    assert max_abs_err(got, ref) <= 1e-4
+    # the random graph amplifies (|output| ~ 1e3): the 1e-4 of unit-scale stems, relative to the peak
+    assert max_abs_err(got, ref) <= 1e-4 * max(1.0, float(np.abs(ref).max()))
