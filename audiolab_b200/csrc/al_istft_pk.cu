@@ -645,7 +645,8 @@ istft_pk3_kernel(const IstftPkParams p) {
 //    with cold instructions, 67 % of its stall samples there were instruction fetches, profiles/r02zd_*.)
 //  * consumer warps never meet: row slot -> Z -> iFFT with the SLOT as transposition scratch -> window -> the frame parked
 //    in the same slot, per position parity and already rotated to the accumulator's entries -> "ready" -> next frame.  No
-//    per-warp scratch, so 6 slots of rows (198 KB) are in flight / in use and 9 consumer warps of 168 registers run;
+//    per-warp scratch, so 8 spectrum-row slots + 3 mask-row slots (181 KB) are in flight / in use and 9 consumer warps of 168
+//    registers run;
 //  * Z[k] and Z[1024 - k] come from ONE product pair: Z[1024 - k] = conj(A) + i conj(B) for Z[k] = A + i B -- half the LDS.128
 //    and half the mask multiplications of the row -> Z phase -- in a ROLLED loop that writes both over the spectrum bins they
 //    were made from (the lane that forms Z[1024 - k] does not own it; 16 unrolled register pairs + shuffles would save the
@@ -655,28 +656,36 @@ istft_pk3_kernel(const IstftPkParams p) {
 //    kernel ran 2 - 3 x slower than istft_pk3_kernel; warp_fft1024p_wide_rolled has ONE copy of the 32-point butterfly.
 // Barriers (a parity wait can only tell the current phase from the one before, so every waiter sees every phase of its
 // barrier): full[w] per consumer warp (its j-th frame = phase j), ready[s] per slot (the two overlap-add warps take every
-// frame), empty[s] per slot (two arrivals, the producer waits).
+// frame), empty[s] per slot (two arrivals, the producer waits), mempty[s] per mask slot (the consumer's arrival after its Z loop).
 constexpr int kTkC = 9;                    // consumer warps
-constexpr int kTkSlots = 6;                // ring slots: one frame's spectrum row + mask row each, later the frame itself
+// TWO rings: the spectrum row's slot lives long (row -> Z -> transposition tile -> parked frame -> overlap-add), the mask row is
+// dead after the Z loop.  With one 33 KB slot for both, 6 frames were all that fitted and the consumers waited for rows a third
+// of the time; 8 long-lived slots of 16.5 KB + 3 short-lived mask slots fit in the same shared memory.
+constexpr int kTkSlots = 8;                // X ring: spectrum row, later Z / the transposition tile / the parked frame
+constexpr int kTkSlotF4 = kScrF4;          // float4 per X slot (16 896 B >= the 1025-bin row)
+constexpr int kTkMSlots = 4;               // M ring: mask rows (3 left the producer waiting for a mask slot, profiles/r03e_*;
+                                           // the depths are compile-time: as run-time parameters the kernel lost 24 %, profiles/r03g_*)
+constexpr int kTkMSlotF4 = 1032;           // float4 per M slot (the row rounded to 128 bytes)
 constexpr int kTkThreads = (kTkC + 3) * 32;   // + two overlap-add warps + the producer
-constexpr int kTkMaskOff = 1032;           // the mask row starts on a 128-byte line of the slot (1025 would split every quarter-warp access)
-constexpr int kTkSlotF4 = 2064;            // float4 per slot: spectrum row, mask row at kTkMaskOff, rounded to 128 bytes (>= kScrF4:
-                                           // the slot is also the warp's transposition scratch)
-static_assert(kTkMaskOff + kIpBins <= kTkSlotF4, "slot too small");
+static_assert(kTkSlotF4 >= kIpBins && kTkMSlotF4 >= kIpBins, "slot too small");
+// (istft_pk5_kernel keeps the single ring of 6 row + mask slots)
+constexpr int kTkMaskOff = 1032;           // pk5: the mask row starts on a 128-byte line of the slot
+constexpr int kSrSlotF4 = 2064;            // pk5: float4 per slot: spectrum row, mask row at kTkMaskOff, rounded to 128 bytes
 constexpr int kTkU = 7;                    // block positions per lane of an overlap-add warp held in registers (hop <= 448)
-static_assert(kTkSlotF4 >= kScrF4, "a slot must hold the transposition tile");
 
 template <bool MASK>
 __global__ void __launch_bounds__(kTkThreads, 1)
 istft_pk4_kernel(const IstftPkParams p) {
     AL_DYN_SMEM(unsigned char, smem_raw);
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
-    float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
-    float2* s_acc = s_ctw + 1024;                                              // [2][1024] even / odd positions, (L, R)
+    float2* s_acc = s_tw + 1024;                                               // [2][1024] even / odd positions, (L, R)
+    const float2* __restrict__ g_ctw = p.ctw;                                  // [1024] W^k through L1 (8 KB of shared memory = half a mask slot)
     float4* s_ring = reinterpret_cast<float4*>(s_acc + 2048);                  // [kTkSlots][kTkSlotF4]
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + kTkSlots * kTkSlotF4);   // [kTkC]
+    float4* s_mring = s_ring + kTkSlots * kTkSlotF4;                           // [kTkMSlots][kTkMSlotF4]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_mring + kTkMSlots * kTkMSlotF4);   // [kTkC]
     uint64_t* s_ready = s_full + kTkC;                                          // [kTkSlots]
     uint64_t* s_empty = s_ready + kTkSlots;                                     // [kTkSlots]
+    uint64_t* s_mempty = s_empty + kTkSlots;                                    // [kTkMSlots]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x / p.segs, seg = blockIdx.x - g * p.segs;   // g = chunk*stems + stem
@@ -699,15 +708,13 @@ istft_pk4_kernel(const IstftPkParams p) {
             mbar_init(&s_ready[s], 1);
             mbar_init(&s_empty[s], 2);
         }
+        for (int s = 0; s < kTkMSlots; ++s) mbar_init(&s_mempty[s], 1);
 #ifndef AL_CPU_EMUL
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
         fence_async_smem();
     }
-    for (int i = tid; i < 1024; i += kTkThreads) {
-        s_tw[i] = p.tw[i];
-        s_ctw[i] = p.ctw[i];
-    }
+    for (int i = tid; i < 1024; i += kTkThreads) s_tw[i] = p.tw[i];
     for (int i = tid; i < 2048; i += kTkThreads) s_acc[i] = make_float2(0.f, 0.f);
     __syncthreads();
 
@@ -722,7 +729,11 @@ istft_pk4_kernel(const IstftPkParams p) {
                 float4* slot = s_ring + s * kTkSlotF4;
                 uint64_t* full = &s_full[it % kTkC];
                 bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
-                if (MASK) bulk_load_g2s(slot + kTkMaskOff, M + (long long)t * kIpBins, kIpBins * 16, full);
+                if (MASK) {
+                    const int sm = it % kTkMSlots;
+                    mbar_wait(&s_mempty[sm], ((it / kTkMSlots) & 1) ^ 1);
+                    bulk_load_g2s(s_mring + sm * kTkMSlotF4, M + (long long)t * kIpBins, kIpBins * 16, full);
+                }
                 mbar_arrive_expect_tx(full, (MASK ? 2u : 1u) * kIpBins * 16u);
             }
         }
@@ -847,14 +858,14 @@ istft_pk4_kernel(const IstftPkParams p) {
         mbar_wait(&s_full[warp], (it / kTkC) & 1);
         {
             float4* __restrict__ xs = slot;
-            const float4* __restrict__ ms = slot + kTkMaskOff;
+            const float4* __restrict__ ms = s_mring + (it % kTkMSlots) * kTkMSlotF4;
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             // ---- Z[k1] and Z[1024 - k1] from ONE pair P = Y[k1], Q = Y[1024 - k1], written over the two spectrum bins they came
             // from (no other lane reads those): a rolled loop instead of 16 unrolled register pairs
             {   // Z[512]: its own Hermitian partner (every lane forms it, the stores coincide)
                 float2 pr, pi, zr, zi;
                 ip_product<MASK>(xs[512], MASK ? ms[512] : z4, pr, pi);
-                ip_combine(pr, pi, pr, pi, s_ctw[512], zr, zi);
+                ip_combine(pr, pi, pr, pi, __ldg(g_ctw + 512), zr, zi);
                 __syncwarp();
                 xs[512] = make_float4(zr.x, zr.y, zi.x, zi.y);
             }
@@ -867,7 +878,7 @@ istft_pk4_kernel(const IstftPkParams p) {
                     pi = make_float2(0.f, 0.f);
                     qi = make_float2(0.f, 0.f);
                 }
-                const float2 w = s_ctw[k1];
+                const float2 w = __ldg(g_ctw + k1);
                 const float2 ar = padd(pr, qr), ai = psub(pi, qi);     // A = P + conj(Q)
                 const float2 dr = psub(pr, qr), di = padd(pi, qi);     // D = P - conj(Q)
                 const float2 zr = pfma(dr, w.y, pfma(di, -w.x, ar));    // Z[k1] = A + i D conj(w)
@@ -880,6 +891,7 @@ istft_pk4_kernel(const IstftPkParams p) {
                 xs[1024 - k1] = make_float4(mr.x, mr.y, mi.x, mi.y);   // (k1 = 0 lands on the dead Nyquist bin)
             }
             __syncwarp();
+            if (MASK && lane == 0) mbar_arrive(&s_mempty[it % kTkMSlots]);   // the mask row is dead: its slot takes the next one
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const float4 v = xs[32 * r + lane];
@@ -933,8 +945,8 @@ istft_pk5_kernel(const IstftPkParams p) {
     float2* s_tw = reinterpret_cast<float2*>(smem_raw);                       // [1024]
     float2* s_ctw = s_tw + 1024;                                               // [1024] W^k
     float2* s_acc = s_ctw + 1024;                                              // [2][1024] even / odd positions, (L, R)
-    float4* s_ring = reinterpret_cast<float4*>(s_acc + 2048);                  // [kSrSlots][kTkSlotF4]
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + kSrSlots * kTkSlotF4);   // [kSrC]
+    float4* s_ring = reinterpret_cast<float4*>(s_acc + 2048);                  // [kSrSlots][kSrSlotF4]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_ring + kSrSlots * kSrSlotF4);   // [kSrC]
     uint64_t* s_empty = s_full + kSrC;                                          // [kSrSlots]
     uint64_t* s_tok = s_empty + kSrSlots;                                       // [2][kSrC]
 
@@ -982,7 +994,7 @@ istft_pk5_kernel(const IstftPkParams p) {
             for (int t = ta; t <= tb; ++t) {
                 const int it = t - ta, s = it % kSrSlots;
                 mbar_wait(&s_empty[s], ((it / kSrSlots) & 1) ^ 1);
-                float4* slot = s_ring + s * kTkSlotF4;
+                float4* slot = s_ring + s * kSrSlotF4;
                 uint64_t* full = &s_full[it % kSrC];
                 bulk_load_g2s(slot, X + (long long)t * kIpBins, kIpBins * 16, full);
                 if (MASK) bulk_load_g2s(slot + kTkMaskOff, M + (long long)t * kIpBins, kIpBins * 16, full);
@@ -1018,7 +1030,7 @@ istft_pk5_kernel(const IstftPkParams p) {
         float2 re[32], im[32];
         if (live) {
             const int s = it % kSrSlots;
-            float4* slot = s_ring + s * kTkSlotF4;
+            float4* slot = s_ring + s * kSrSlotF4;
             mbar_wait(&s_full[warp], ph);
             {
                 float4* __restrict__ xs = slot;
@@ -1226,13 +1238,13 @@ static size_t tk_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
     }
     p.hops_per_cta = (total_hops + best_segs - 1) / best_segs;
     p.segs = (total_hops + p.hops_per_cta - 1) / p.hops_per_cta;
-    return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kTkSlots * kTkSlotF4 * sizeof(float4) +
-           (size_t)(kTkC + 2 * kTkSlots) * sizeof(uint64_t);
+    return (size_t)(1024 + 2048) * sizeof(float2) + (size_t)(kTkSlots * kTkSlotF4 + kTkMSlots * kTkMSlotF4) * sizeof(float4) +
+           (size_t)(kTkC + 2 * kTkSlots + kTkMSlots) * sizeof(uint64_t);
 }
 // launch shape of istft_pk5_kernel: the segments of istft_pk4_kernel
 static size_t sr_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
     tk_launch_shape(p, n_chunks, n_sm);
-    return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kSrSlots * kTkSlotF4 * sizeof(float4) +
+    return (size_t)(2 * 1024 + 2048) * sizeof(float2) + (size_t)kSrSlots * kSrSlotF4 * sizeof(float4) +
            (size_t)(3 * kSrC + kSrSlots) * sizeof(uint64_t);
 }
 // [emul-end]
