@@ -645,7 +645,7 @@ istft_pk3_kernel(const IstftPkParams p) {
 //    with cold instructions, 67 % of its stall samples there were instruction fetches, profiles/r02zd_*.)
 //  * consumer warps never meet: row slot -> Z -> iFFT with the SLOT as transposition scratch -> window -> the frame parked
 //    in the same slot, per position parity and already rotated to the accumulator's entries -> "ready" -> next frame.  No
-//    per-warp scratch, so 8 spectrum-row slots + 3 mask-row slots (181 KB) are in flight / in use and 9 consumer warps of 168
+//    per-warp scratch, so 8 spectrum-row slots + 4 mask-row slots (197 KB) are in flight / in use and 9 consumer warps of 168
 //    registers run;
 //  * Z[k] and Z[1024 - k] come from ONE product pair: Z[1024 - k] = conj(A) + i conj(B) for Z[k] = A + i B -- half the LDS.128
 //    and half the mask multiplications of the row -> Z phase -- in a ROLLED loop that writes both over the spectrum bins they
@@ -661,9 +661,9 @@ constexpr int kTkC = 9;                    // consumer warps
 // TWO rings: the spectrum row's slot lives long (row -> Z -> transposition tile -> parked frame -> overlap-add), the mask row is
 // dead after the Z loop.  With one 33 KB slot for both, 6 frames were all that fitted and the consumers waited for rows a third
 // of the time; 8 long-lived slots of 16.5 KB + 3 short-lived mask slots fit in the same shared memory.
-constexpr int kTkSlots = 8;                // X ring: spectrum row, later Z / the transposition tile / the parked frame
+constexpr int kTkXDefault = 8;             // X ring: spectrum row, later Z / the transposition tile / the parked frame
 constexpr int kTkSlotF4 = kScrF4;          // float4 per X slot (16 896 B >= the 1025-bin row)
-constexpr int kTkMSlots = 4;               // M ring: mask rows (3 left the producer waiting for a mask slot, profiles/r03e_*;
+constexpr int kTkMDefault = 4;             // M ring: mask rows (3 left the producer waiting for a mask slot, profiles/r03e_*;
                                            // the depths are compile-time: as run-time parameters the kernel lost 24 %, profiles/r03g_*)
 constexpr int kTkMSlotF4 = 1032;           // float4 per M slot (the row rounded to 128 bytes)
 constexpr int kTkThreads = (kTkC + 3) * 32;   // + two overlap-add warps + the producer
@@ -673,7 +673,7 @@ constexpr int kTkMaskOff = 1032;           // pk5: the mask row starts on a 128-
 constexpr int kSrSlotF4 = 2064;            // pk5: float4 per slot: spectrum row, mask row at kTkMaskOff, rounded to 128 bytes
 constexpr int kTkU = 7;                    // block positions per lane of an overlap-add warp held in registers (hop <= 448)
 
-template <bool MASK>
+template <bool MASK, int kTkSlots = kTkXDefault, int kTkMSlots = kTkMDefault>
 __global__ void __launch_bounds__(kTkThreads, 1)
 istft_pk4_kernel(const IstftPkParams p) {
     AL_DYN_SMEM(unsigned char, smem_raw);
@@ -1219,7 +1219,7 @@ static size_t rg_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
            (size_t)kRgTeam * kRgSlotF4 * sizeof(float4) + (size_t)(kIpN - p.hop) * sizeof(float2) + 3 * kRgTeam * sizeof(uint64_t);
 }
 // launch shape of istft_pk4_kernel: one CTA per SM; a segment costs its hops + the halo frames it recomputes + the fill of the warp pipeline
-static size_t tk_launch_shape(IstftPkParams& p, int n_chunks, int n_sm) {
+static size_t tk_launch_shape(IstftPkParams& p, int n_chunks, int n_sm, int kTkSlots = kTkXDefault, int kTkMSlots = kTkMDefault) {
     const int rows = n_chunks * p.stems;
     const int total_hops = (p.out_len + p.hop - 1) / p.hop;
     const int halo = (kIpN - 1) / p.hop;
@@ -1281,17 +1281,25 @@ cudaError_t launch_istft_pk(const IstftPkParams& p0, int n_chunks, cudaStream_t 
         // the streaming kernel: any hop (the accumulator is position-addressed); positions are 32-bit inside a chunk
         p.ola_fast = 0;
         p.l2_prefetch = 0;
-        const size_t smem4 = tk_launch_shape(p, n_chunks, n_sm);
-        static PerDeviceOnce attr4[2];
-        PerDeviceOnce& a4 = attr4[p.mask ? 1 : 0];
-        if (a4.needed()) {
-            cudaError_t e = p.mask ? cudaFuncSetAttribute(istft_pk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                                   : cudaFuncSetAttribute(istft_pk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) return e;
-            a4.mark();
+        // AL_IP_SPLIT=75 selects 7 spectrum-row + 5 mask-row slots (A/B of the split; default 8 + 4)
+        static const int split75 = getenv("AL_IP_SPLIT") && atoi(getenv("AL_IP_SPLIT")) == 75;
+        const size_t smem4 = split75 ? tk_launch_shape(p, n_chunks, n_sm, 7, 5) : tk_launch_shape(p, n_chunks, n_sm);
+#define AL_TK_LAUNCH(KERNEL)                                                                                          \
+    do {                                                                                                               \
+        static PerDeviceOnce attr4;                                                                                    \
+        if (attr4.needed()) {                                                                                          \
+            cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);     \
+            if (e != cudaSuccess) return e;                                                                            \
+            attr4.mark();                                                                                              \
+        }                                                                                                              \
+        KERNEL<<<(unsigned)(rows * p.segs), kTkThreads, smem4, stream>>>(p);                                          \
+    } while (0)
+        if (split75) {
+            if (p.mask) AL_TK_LAUNCH((istft_pk4_kernel<true, 7, 5>)); else AL_TK_LAUNCH((istft_pk4_kernel<false, 7, 5>));
+        } else {
+            if (p.mask) AL_TK_LAUNCH((istft_pk4_kernel<true>)); else AL_TK_LAUNCH((istft_pk4_kernel<false>));
         }
-        if (p.mask) istft_pk4_kernel<true><<<(unsigned)(rows * p.segs), kTkThreads, smem4, stream>>>(p);
-        else istft_pk4_kernel<false><<<(unsigned)(rows * p.segs), kTkThreads, smem4, stream>>>(p);
+#undef AL_TK_LAUNCH
         count_launch();
         return cudaGetLastError();
     }
