@@ -265,6 +265,45 @@ def test_token_ordered_packed_istft_emulated_matches_torch(emul, hop, T, stems, 
             assert np.abs(dst[c, s_] - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("kernel", [4, 5])
+def test_streaming_packed_istft_emulated_placement_weight_and_clipping(emul, kernel):
+    """istft_pk4_kernel / istft_pk5_kernel: ragged out_len (not a multiple of the hop), chunk weight, per-chunk placement into a
+    track (dst_off0 + chunk * dst_off_step) and the dst_limit clip of the last chunk -- the paths that leave the 'interior'
+    hop-block emission -- against torch.istft; nothing is written outside the clipped spans."""
+    import torch
+    P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+    emul.emul_istft_pk4.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I]
+    emul.emul_istft_pk4.restype = I
+    n_fft, F, hop, T, n_chunks = 2048, 1025, 441, 19, 3
+    rs = np.random.RandomState(17)
+    cplx = lambda *shape: (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+    spec = cplx(n_chunks, T, F, 2)
+    mask = cplx(n_chunks, 1, T, F, 2)
+    L = (T - 1) * hop - 57                                                 # ragged
+    _, ws, tw, _, env = _plan_tables(n_fft, hop, T)
+    k = np.arange(1024)
+    ctw_full = np.ascontiguousarray(np.stack((np.cos(-2 * np.pi * k / n_fft), np.sin(-2 * np.pi * k / n_fft)), -1).astype(np.float32))
+    weight = rs.uniform(0.5, 1.5, L).astype(np.float32)
+    off0, off_step = 100, L + 37
+    n_track = off0 + 2 * off_step + L - 300                                # the last chunk is clipped by dst_limit
+    track = np.full((2, n_track + 64), -77.0, np.float32)                  # guard band past dst_limit
+    segs = emul.emul_istft_pk4(_p(spec), _p(mask), T, 1, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), n_fft // 2, L,
+                               _p(weight), _p(track), n_track + 64, 0, off0, off_step, n_track, n_chunks, kernel, 2)
+    assert segs >= 1
+    win = torch.hann_window(n_fft)
+    exp = np.full_like(track, -77.0)
+    for c in range(n_chunks):
+        y = spec[c] * mask[c, 0]
+        ref = torch.istft(torch.tensor(np.ascontiguousarray(y.transpose(2, 1, 0))), n_fft, hop, window=win, center=True,
+                          length=L).numpy() * weight
+        a = off0 + c * off_step
+        b = min(a + L, n_track)
+        exp[:, a:b] = ref[:, : b - a]
+    written = exp != -77.0
+    assert np.array_equal(track != -77.0, written)
+    assert np.abs(track[written] - exp[written]).max() <= 2e-5 * max(1.0, np.abs(exp[written]).max())
+
+
 @pytest.mark.parametrize("hop,T,layout,crop,low,n_chunks", [(441, 21, 3, 1025, 0, 2), (441, 9, 0, 1025, 0, 1), (512, 12, 3, 1000, 3, 2),
                                                            (441, 26, 3, 1025, 0, 3)])
 def test_packed_stft_emulated_matches_torch(emul, hop, T, layout, crop, low, n_chunks):
