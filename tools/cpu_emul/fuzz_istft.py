@@ -3,8 +3,8 @@
 
     python tools/cpu_emul/fuzz_istft.py [--n 40] [--seed 0]
 
-Draws (n_fft, hop, frames, frame_pad, cropped bins, out_start / out_len windows, stems, mask, weight, warps per CTA, SM
-count for the tiling) and compares every emitted sample with a torch.istft of the same (padded) spectrum.  Test
+Draws (n_fft, hop, frames, frame_pad, cropped bins, out_start / out_len windows, stems, mask, weight, the packed kernel
+(istft_pk2 / istft_pk4 / istft_pk5), warps per CTA, SM count for the tiling) and compares every emitted sample with a torch.istft of the same (padded) spectrum.  Test
 infrastructure (like tests/test_kernel_emulation.py, which holds the fixed cases)."""
 import argparse
 import ctypes
@@ -33,6 +33,8 @@ def load():
     P, LL, I = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
     lib.emul_istft_pk.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I, I, I]
     lib.emul_istft_pk.restype = I
+    lib.emul_istft_pk4.argtypes = [P, P, I, I, I, I, P, P, P, P, I, I, P, P, LL, LL, LL, LL, LL, I, I, I]
+    lib.emul_istft_pk4.restype = I
     return lib
 
 
@@ -40,6 +42,9 @@ def one(lib, rs, packed):
     if packed:
         n_fft = 2048
         hop = int(rs.choice([441, 512, 256, 1024, 300, 777]))
+        kernel = int(rs.choice([2, 4, 5]))        # 2: istft_pk2_kernel (register pipeline), 4 / 5: the streaming kernels
+        if kernel == 2 and (n_fft + hop - 1) // hop > 5:
+            kernel = 4                            # the register-form overlap-add of istft_pk2 needs <= 5 frames per position
     else:
         n_fft = int(rs.choice([2048, 4096, 6144]))
         hop = int(rs.choice([n_fft // 4, n_fft // 6, 441, 1024, n_fft // 2, 1000]))
@@ -67,9 +72,13 @@ def one(lib, rs, packed):
         k = np.arange(1024)
         ctw_full = np.ascontiguousarray(np.stack((np.cos(-2 * np.pi * k / n_fft), np.sin(-2 * np.pi * k / n_fft)), -1).astype(np.float32))
         warps, n_sm, fast = int(rs.choice([4, 8])), int(rs.choice([1, 2, 5])), int(rs.randint(0, 2))
-        desc.update(warps=warps, n_sm=n_sm, fast=fast)
-        rc = lib.emul_istft_pk(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), out_start, out_len,
-                               _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, 1, warps, n_sm, 0, fast)
+        desc.update(warps=warps, n_sm=n_sm, fast=fast, kernel=kernel)
+        if kernel == 2:
+            rc = lib.emul_istft_pk(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), out_start, out_len,
+                                   _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, 1, warps, n_sm, 0, fast)
+        else:
+            rc = lib.emul_istft_pk4(_p(spec), _p(mask), T, stems, 0, hop, _p(ws), _p(tw), _p(ctw_full), _p(env), out_start, out_len,
+                                    _p(weight), _p(dst), out_len, stems * 2 * out_len, 0, 0, out_len, 1, kernel, n_sm)
         full = [spec[0] * (mask[0, s] if use_mask else 1.0) for s in range(stems)]          # [t, f, ch]
         full = [y.transpose(2, 1, 0) for y in full]                                          # [ch, f, t]
     else:
